@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DeMethify deconvolution hot path on B200.
+
+Workload (BASELINE.json metric "... at 1M CpG x K x N", configs[4] shape): partial-reference deconvolution,
+M = 1,000,000 CpGs x N = 256 samples, K = 6 known + n_u = 2 unknown cell types, fp64, synthetic data
+(recipe of test/gen_data.ipynb cell 5).  One STEP = OUTER_PER_STEP outer iterations of mdwbssmf_deconv
+(deconvolution.py:206-221) with n_iter2 = 20: 20 update_u + 20 update_alpha inner iterations + cost_f_w each,
+tol = 0 so no step stops early.  metric = update iterations / second (inner iterations of U and alpha).
+
+  value     : inputs resident in HBM when the timed region starts (FitBatch.enqueue_outer)
+  e2e       : the public call demethify_b200.deconvolution.mdwbssmf_deconv with HOST (pinned) numpy buffers;
+              H2D of X, d_x, R_trunc, u0, alpha0 and D2H of u, alpha inside the timed region
+  roofline  : dominant kernel (update_u pass), algorithmic bytes / CUDA-event duration
+  cpu_baseline / --impl reference : the numpy port of the reference loop (oracle/) on the host cores, on a
+              bounded row sample of the same workload (cost is linear in M; the sample and the scaling are stated)
+
+N > 1 GPUs: fit sharding (restarts / n_u sweep members are independent fits, ic.py:192-207): every rank runs
+its own fit on its own copy of the problem, no data-path collective -> "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_FULL, N_S, K_KNOWN, N_UNK = 1_000_000, 256, 6, 2
+N_ITER2 = 20
+OUTER_PER_STEP = 2
+CPU_SAMPLE_ROWS = 100_000
+METRIC = "update_iters_per_sec"
+UNIT = "inner update iterations/s at 1M CpG x 256 samples (K=6, n_u=2)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=M_FULL, help="override M (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    return ap.parse_args()
+
+
+def workload_config(M, extra=None):
+    cfg = {"workload": "partial-reference deconvolution (mdwbssmf_deconv), BASELINE configs[4] shape",
+           "M_cpg": M, "N_samples": N_S, "K_known": K_KNOWN, "n_unknown": N_UNK, "n_iter2": N_ITER2,
+           "outer_iterations_per_step": OUTER_PER_STEP, "update_iters_per_step": 2 * N_ITER2 * OUTER_PER_STEP,
+           "tol": 0.0, "init": "uniform_", "cache": "inputs (>= 2.6 GB per pass) exceed the 126 MB L2"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def synth_host(M, seed=0):
+    """Small-M synthetic problem on the host (CPU baseline sample)."""
+    rs = np.random.RandomState(seed)
+    a = rs.uniform(0.2, 1.0, size=K_KNOWN + N_UNK)
+    Rf = rs.beta(a, a, size=(M, K_KNOWN + N_UNK))
+    unk = rs.uniform(0, 0.9, size=N_S)
+    Ak = rs.dirichlet(np.ones(K_KNOWN), N_S).T * (1 - unk)
+    Au = rs.dirichlet(np.ones(N_UNK), N_S).T * unk
+    D = rs.poisson(50, size=(M, N_S)) + 1
+    X = rs.binomial(D, np.clip(Rf @ np.vstack([Ak, Au]), 0, 1)) / D
+    return X, D.astype(np.int64), np.ascontiguousarray(Rf[:, :K_KNOWN])
+
+
+def cpu_reference_leg(steps, warmup, rows=CPU_SAMPLE_ROWS):
+    """The reference algorithm's numpy port (oracle/bssmf_numpy.py, pinned to the reference by
+    tests/test_oracle_golden.py) timed on the host cores.  One step = ONE outer iteration on a row sample."""
+    from oracle import bssmf_numpy as orc
+    X, D, Rk = synth_host(rows)
+    Df = D.astype(np.float64)
+    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, N_UNK, seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, Df, Rk, N_UNK, 1, N_ITER2, 0.0)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times[warmup:]))
+    its_sample = 2 * N_ITER2 / t
+    cores = os.cpu_count()
+    return {"value": its_sample * rows / M_FULL, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{rows} of {M_FULL} CpG rows x {N_S} samples, 1 outer iteration (40 inner updates + cost) per step, "
+                      f"{its_sample:.2f} it/s on the sample scaled by {rows}/{M_FULL} (cost linear in M); numpy/OpenBLAS threads",
+            "s_per_step_sample": t}
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    leg = cpu_reference_leg(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": leg["s_per_step_sample"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(M_FULL),
+            "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as g
+    g.build()
+    import demethify_b200
+    from demethify_b200 import deconvolution as dec
+    from demethify_b200.engine import DeviceProblem, FitBatch
+    demethify_b200.set_precision(args.precision)
+    M = args.rows
+    tdt = torch.float64 if args.precision == "fp64" else torch.float32
+
+    # ---- synthetic inputs, generated on the device (same recipe as synth_host), then mirrored into pinned host memory
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    Kt = K_KNOWN + N_UNK
+    conc = torch.rand(Kt, device=dev, generator=gen, dtype=torch.float64) * 0.8 + 0.2
+    g1 = torch._standard_gamma(conc.expand(M, Kt).contiguous(), generator=gen)
+    g2 = torch._standard_gamma(conc.expand(M, Kt).contiguous(), generator=gen)
+    Rf = g1 / (g1 + g2)
+    del g1, g2
+    unk = torch.rand(N_S, device=dev, generator=gen, dtype=torch.float64) * 0.9
+    ek = -torch.log1p(-torch.rand(K_KNOWN, N_S, device=dev, generator=gen, dtype=torch.float64))
+    eu = -torch.log1p(-torch.rand(N_UNK, N_S, device=dev, generator=gen, dtype=torch.float64))
+    A_true = torch.cat([ek / ek.sum(0) * (1 - unk), eu / eu.sum(0) * unk], 0)
+    D = torch.poisson(torch.full((M, N_S), 50.0, device=dev), generator=gen).to(torch.int64) + 1
+    P = (Rf @ A_true).clamp_(0, 1)
+    cnt = torch.binomial(D.to(torch.float64), P, generator=gen)
+    X = cnt / D.to(torch.float64)
+    del P, cnt
+    Rk = Rf[:, :K_KNOWN].contiguous()
+    del Rf
+    hX = torch.empty(X.shape, dtype=torch.float64, pin_memory=True); hX.copy_(X)
+    hD = torch.empty(D.shape, dtype=torch.int64, pin_memory=True); hD.copy_(D)
+    hR = torch.empty(Rk.shape, dtype=torch.float64, pin_memory=True); hR.copy_(Rk)
+    u0, R0_unused, a0 = None, None, None
+    rs = np.random.RandomState(1 + rank)
+    u0 = rs.uniform(size=(M, N_UNK)); a0 = rs.dirichlet(np.ones(Kt), N_S).T.copy()
+    hU = torch.empty(u0.shape, dtype=torch.float64, pin_memory=True); hU.copy_(torch.from_numpy(u0))
+    hA = torch.empty(a0.shape, dtype=torch.float64, pin_memory=True); hA.copy_(torch.from_numpy(a0))
+    torch.cuda.synchronize()
+
+    # ---- resident arm
+    prob = DeviceProblem(X, D, Rk, precision=args.precision)
+    del X, D
+    batch = FitBatch(prob, N_UNK, [hU], [hA])
+    batch.pass_init()
+    geom = batch.geometry()
+    sT = 8 if args.precision == "fp64" else 4
+    sW = 2 if prob.wtype == 1 else sT
+    bytes_u = M * (sT * (N_S + K_KNOWN + 3 * N_UNK) + sW * N_S)          # SURVEY 8 d4, U inner iteration
+    bytes_a = M * (sT * (N_S + Kt) + sW * N_S)                             # alpha inner iteration / cost
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(ev=None):
+        for _ in range(OUTER_PER_STEP):
+            if ev is not None:
+                e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+                e0.record()
+            for _i in range(N_ITER2):
+                batch.pass_u()
+            if ev is not None:
+                e1.record()
+            for _i in range(N_ITER2):
+                batch.pass_alpha()
+            if ev is not None:
+                e2.record()
+            batch.pass_cost(0.0)
+            if ev is not None:
+                e3.record()
+                ev.append((e0, e1, e2, e3))
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = batch.launch_count()
+    evs = []
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        one_step(evs)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    launches = batch.launch_count() - launches0
+    t_u = float(np.mean([a.elapsed_time(b) for a, b, _, _ in evs])) / N_ITER2      # ms per update_u launch
+    t_a = float(np.mean([b.elapsed_time(c) for _, b, c, _ in evs])) / N_ITER2
+    t_c = float(np.mean([c.elapsed_time(d) for _, _, c, d in evs]))
+    st = batch.states()[0]
+    assert st.n_outer == (args.warmup + args.steps) * OUTER_PER_STEP and np.isfinite(st.cost)
+
+    # ---- end-to-end arm: public API, host buffers in, host arrays out
+    nX, nD, nR, nU, nA = hX.numpy(), hD.numpy(), hR.numpy(), hU.numpy(), hA.numpy()
+    batch.close()
+    del batch, prob
+    torch.cuda.empty_cache()
+    e2e_times = []
+    for i in range(2 + min(args.steps, 3)):
+        barrier()
+        t0 = time.perf_counter()
+        u_out, a_out = dec.mdwbssmf_deconv(nU, None, nA, nX, nD, nR, N_UNK, n_iter1=OUTER_PER_STEP, n_iter2=N_ITER2, tol=0.0)
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_times[2:]))
+    h2d = hX.numel() * 8 + hD.numel() * 8 + hR.numel() * 8 + hU.numel() * 8 + hA.numel() * 8
+    d2h = u_out.nbytes + a_out.nbytes
+
+    # ---- reduce over ranks: device time = max over ranks, work = sum over ranks
+    its_per_step = 2 * N_ITER2 * OUTER_PER_STEP
+    tmax = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_s = float(tmax[0]), float(tmax[1])
+    value = world * its_per_step * args.steps / (elapsed_ms * 1e-3)
+    e2e_value = world * its_per_step / e2e_s
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        ach = bytes_u / (t_u * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
+            "config": workload_config(M, {"weights_storage": "u16" if prob_wtype_is_u16(sW, sT) else "float",
+                                          "parallelism": f"fit-sharded x{world}", "ctas_per_fit": geom["ctas_per_fit"],
+                                          "tile_rows": geom["tile_rows"], "smem_bytes": geom["smem_bytes"]}),
+            "fits_per_sec_at_100_outer": value / (2 * N_ITER2 * 100),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "s_per_call": e2e_s, "call": "demethify_b200.deconvolution.mdwbssmf_deconv(numpy in, numpy out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "u_pass_kernel (update_u inner iteration)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bytes_u), "ms_per_launch": t_u,
+                         "alpha_pass": {"ms_per_launch": t_a, "achieved": bytes_a / (t_a * 1e-3) / 1e9, "algorithmic_bytes_per_launch": int(bytes_a)},
+                         "cost_pass": {"ms_per_launch": t_c, "achieved": bytes_a / (t_c * 1e-3) / 1e9}},
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            leg = cpu_reference_leg(2, 1)
+            line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def prob_wtype_is_u16(sW, sT):
+    return sW == 2 and sT != 2
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,21 @@
+"""demethify_b200 — B200-native (sm_100a) implementation of DeMethify's NMF deconvolution hot path.
+
+Python entry points mirror the reference's modules (`deconvolution`, `bootstrap`, `ic`, `init_func`,
+`demethify` CLI); the arithmetic runs in libdemethify_sm100.so (hand-written CUDA, C ABI declared in
+include/demethify_b200.h).  There is no CPU fallback: importing works anywhere, computing needs a B200.
+"""
+__version__ = "0.1.0"
+
+_PRECISION = "fp64"
+
+
+def set_precision(mode):
+    """'fp64' (default; max|d alpha| <= 1e-6 vs the reference) or 'fp32' (<= 1e-4)."""
+    global _PRECISION
+    if mode not in ("fp64", "fp32"):
+        raise ValueError("precision must be 'fp64' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION

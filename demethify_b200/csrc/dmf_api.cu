@@ -1,0 +1,464 @@
+// dmf_api.cu — extern "C" surface of libdemethify_sm100.so (see include/demethify_b200.h).
+// Host logic only: shape validation, launch geometry, kernel dispatch, the outer-loop driver.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/demethify_b200.h"
+#include "dmf_device.cuh"
+#include "dmf_inst.h"
+
+using namespace dmf;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) return fail(DMF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct dmf_handle_s {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+};
+
+struct dmf_batch_s {
+    dmf_handle_s* h;
+    dmf_shape_t shape;
+    Geom g;
+    FitDev* fits_dev;       // in workspace
+    FitState* states_dev;   // in workspace, contiguous [n_fits]
+    int ktb, nub;           // register-tile buckets
+    int c_alpha, c_u;       // columns per thread in the alpha/cost and U kernels
+    int ntc_alpha, ntc_u;
+    unsigned smem_alpha, smem_u, smem_cost;
+    int occ;
+    long long launches;
+    FitState* pinned;       // host staging for state polling
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// kernel tables: the template instantiations live in dmf_inst_*.cu (one translation unit per storage-type pair)
+kern_t by_types(const dmf_shape_t& s, kern_t (*f[4])(int, int, int), int a, int b, int c) {
+    const int i = (s.dtype == DMF_F64 ? 0 : 2) + (s.wtype == DMF_W_U16 ? 1 : 0);
+    return f[i](a, b, c);
+}
+kern_t (*g_cost[4])(int, int, int) = {pick_cost_f64_f64, pick_cost_f64_u16, pick_cost_f32_f32, pick_cost_f32_u16};
+kern_t (*g_alpha[4])(int, int, int) = {pick_alpha_f64_f64, pick_alpha_f64_u16, pick_alpha_f32_f32, pick_alpha_f32_u16};
+kern_t (*g_u[4])(int, int, int) = {pick_u_f64_f64, pick_u_f64_u16, pick_u_f32_f32, pick_u_f32_u16};
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ---------------------------------------------------------------------------------------------
+// Geometry.  One stage of the ring holds tile_rows rows of every streamed matrix with the global pitch.
+struct Plan {
+    int ktb, nub, c_alpha, c_u, ntc_alpha, ntc_u;
+    int tile_rows, n_tiles, n_parts, n_groups, part_stride, occ;
+    unsigned offX, offD, offR, offU, offUp, stage_bytes, smem_alpha, smem_u, smem_cost, row_bulk;
+    size_t ws_bytes, off_fits, off_states, off_tickets, off_part, off_gpart, per_fit_tickets, per_fit_part, per_fit_gpart;
+};
+
+int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
+    if (s.M <= 0 || s.N <= 0 || s.K < 0 || s.n_u <= 0 || s.n_fits <= 0) return fail(DMF_E_SHAPE, "M, N, n_u, n_fits must be positive and K >= 0");
+    if (s.mode == DMF_MODE_UNSUPERVISED && s.K != 0) return fail(DMF_E_SHAPE, "unsupervised mode requires K = 0");
+    if (s.mode == DMF_MODE_PURITY && s.K == 0) return fail(DMF_E_SHAPE, "purity mode requires K >= 1");
+    if (s.dtype != DMF_F64 && s.dtype != DMF_F32) return fail(DMF_E_ARG, "dtype must be DMF_F64 or DMF_F32");
+    if (s.wtype != DMF_W_FLOAT && s.wtype != DMF_W_U16) return fail(DMF_E_ARG, "wtype must be DMF_W_FLOAT or DMF_W_U16");
+    if (s.ldx < s.N || s.ldd < s.N || (s.K && s.ldr < s.K)) return fail(DMF_E_SHAPE, "row pitch smaller than the row");
+    const int Kt = s.K + s.n_u;
+    if (s.u_slot < s.M * s.n_u || (s.u_slot * (s.dtype == DMF_F64 ? 8 : 4)) % 16) return fail(DMF_E_SHAPE, "u_slot must be >= M*n_u and a multiple of 16 bytes");
+    if (Kt > kMaxKt) return fail(DMF_E_SHAPE, "K + n_u > 32 is not supported by this build");
+    p.ktb = Kt <= 8 ? 8 : (Kt <= 16 ? 16 : 32);
+    p.nub = s.n_u <= 2 ? 2 : (s.n_u <= 8 ? 8 : (s.n_u <= 16 && p.ktb == 16 ? 16 : 32));
+    if (p.nub > p.ktb) p.nub = p.ktb;
+    if (p.ktb == 8 && p.nub > 8) p.nub = 8;
+    // columns per thread: as few as the register budget allows, more when N needs it
+    const int c_min = (s.N + kConsumers - 1) / kConsumers;
+    if (p.ktb == 8) { p.c_alpha = c_min <= 2 ? 2 : 4; p.c_u = c_min <= 2 ? 2 : 4; }
+    else if (p.ktb == 16) { p.c_alpha = c_min <= 1 ? 1 : 2; p.c_u = c_min <= 1 ? 1 : 2; }
+    else { p.c_alpha = 1; p.c_u = 1; }
+    if (c_min > p.c_alpha) return fail(DMF_E_SHAPE, "N too large for this K + n_u in this build (N <= 1024 / 512 / 256 for Kt <= 8 / 16 / 32)");
+    p.ntc_alpha = next_pow2((s.N + p.c_alpha - 1) / p.c_alpha);
+    p.ntc_u = next_pow2((s.N + p.c_u - 1) / p.c_u);
+
+    const size_t sT = s.dtype == DMF_F64 ? 8 : 4;
+    const size_t sW = s.wtype == DMF_W_U16 ? 2 : sT;
+    const size_t px = s.ldx * sT, pd = s.ldd * sW, pr = s.K ? s.ldr * sT : 0, pu = (size_t)s.n_u * sT;
+    // smallest row multiple that keeps every tile start 16-byte aligned
+    int ra = 1;
+    while (ra < 16 && ((ra * px) % 16 || (ra * pd) % 16 || (ra * pr) % 16 || (ra * pu) % 16)) ra <<= 1;
+    const size_t row_bytes = px + pd + pr + 2 * pu;
+    p.occ = (p.ktb == 8) ? 2 : 1;
+    const size_t smem_cap = (size_t)h->max_smem_optin;
+    const size_t budget = (p.occ == 2 ? std::min<size_t>(smem_cap, 110 * 1024) : std::min<size_t>(smem_cap, 200 * 1024)) - kCtlBytes - 8192;
+    const size_t stage_target = budget / kStages;
+    long long tr = (long long)(stage_target / row_bytes) / ra * ra;
+    if (tr < ra) {
+        // a single row group does not fit twice per SM: fall back to one CTA per SM
+        p.occ = 1;
+        const size_t b1 = std::min<size_t>(smem_cap, 200 * 1024) - kCtlBytes - 8192;
+        tr = (long long)(b1 / kStages / row_bytes) / ra * ra;
+        if (tr < ra) return fail(DMF_E_SHAPE, "one row tile does not fit in shared memory (N too large)");
+    }
+    tr = std::min<long long>(tr, 512);
+    tr = std::min<long long>(tr, (long long)align_up((size_t)s.M, ra));
+    p.tile_rows = (int)tr;
+    p.n_tiles = (int)((s.M + tr - 1) / tr);
+    auto a128 = [](size_t v) { return (unsigned)align_up(v, 128); };
+    p.offX = 0;
+    p.offD = a128(p.offX + tr * px);
+    p.offR = a128(p.offD + tr * pd);
+    p.offU = a128(p.offR + tr * pr);
+    p.offUp = a128(p.offU + tr * pu);
+    p.stage_bytes = a128(p.offUp + tr * pu);
+    p.row_bulk = (px % 16 == 0 ? 1u : 0u) | (pd % 16 == 0 ? 2u : 0u) | ((pr % 16 == 0 && pr) ? 4u : 0u);
+
+    // CTAs per fit: fill the GPU (SMs x occupancy) across the whole batch, never more than tiles
+    long long target = (long long)h->sm_count * p.occ;
+    long long per_fit = std::max<long long>(1, target / s.n_fits);
+    if (s.max_ctas_per_fit > 0) per_fit = std::min<long long>(per_fit, s.max_ctas_per_fit);
+    p.n_parts = (int)std::min<long long>(per_fit, p.n_tiles);
+    p.n_groups = (p.n_parts + kGroup - 1) / kGroup;
+    p.part_stride = (int)align_up((size_t)std::max(Kt * s.N, 4), 2);
+
+    const size_t pipe = kCtlBytes + (size_t)kStages * p.stage_bytes;
+    const size_t epi_alpha = kCtlBytes + ((size_t)(Kt + 1) * s.N + 32) * 8;
+    const int wpr_u = (p.ntc_u + 31) / 32;
+    const size_t red_u = wpr_u > 1 ? (size_t)2 * tr * wpr_u * s.n_u * 8 : 0;
+    p.smem_alpha = (unsigned)std::max(pipe, epi_alpha);
+    p.smem_u = (unsigned)std::max(pipe + red_u, (size_t)kCtlBytes + 512);
+    p.smem_cost = (unsigned)std::max(pipe, (size_t)kCtlBytes + 512);
+    if (std::max(p.smem_alpha, p.smem_u) > smem_cap) return fail(DMF_E_SHAPE, "shared-memory plan exceeds the device limit");
+
+    // workspace layout
+    p.off_fits = 0;
+    p.off_states = align_up(p.off_fits + sizeof(FitDev) * s.n_fits, 256);
+    p.per_fit_tickets = align_up(sizeof(unsigned) * (p.n_groups + 1), 128);
+    p.per_fit_part = align_up((size_t)p.n_parts * p.part_stride * 8, 128);
+    p.per_fit_gpart = align_up((size_t)p.n_groups * p.part_stride * 8, 128);
+    p.off_tickets = align_up(p.off_states + sizeof(FitState) * s.n_fits, 256);
+    p.off_part = align_up(p.off_tickets + p.per_fit_tickets * s.n_fits, 256);
+    p.off_gpart = align_up(p.off_part + p.per_fit_part * s.n_fits, 256);
+    p.ws_bytes = align_up(p.off_gpart + p.per_fit_gpart * s.n_fits, 256);
+    return DMF_OK;
+}
+
+int set_smem(kern_t k, unsigned bytes) {
+    if (!k) return fail(DMF_E_SHAPE, "no kernel instantiation for this shape");
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DMF_OK;
+}
+
+int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_inner, double tol, cudaStream_t st) {
+    if (!k) return fail(DMF_E_SHAPE, "no kernel instantiation for this shape");
+    PassArgs a;
+    a.g = b->g;
+    a.g.ntc = ntc;
+    a.g.rg = kConsumers / ntc;
+    a.fits = b->fits_dev;
+    a.k_inner = k_inner;
+    a.flags = flags;
+    a.tol = tol;
+    dim3 grid(b->g.n_parts, b->shape.n_fits, 1);
+    k<<<grid, kThreads, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    return DMF_OK;
+}
+
+kern_t k_cost(dmf_batch_s* b) { return by_types(b->shape, g_cost, b->ktb, 0, b->c_alpha); }
+kern_t k_alpha(dmf_batch_s* b) { return by_types(b->shape, g_alpha, b->ktb, 0, b->c_alpha); }
+kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->ktb, b->nub, b->c_u); }
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+template <typename S>
+__global__ void pack_u16_kernel(const S* src, long long n, uint16_t* dst, int* bad) {
+    int local_bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const S v = src[i];
+        const double d = (double)v;
+        const bool ok = d >= 0.0 && d <= 65535.0 && d == floor(d);
+        if (!ok) local_bad = 1;
+        dst[i] = ok ? (uint16_t)d : (uint16_t)0;
+    }
+    if (local_bad) atomicAdd(bad, 1);
+}
+
+__global__ void gather_rows_kernel(const char* src, const int32_t* rows, long long n_rows, long long row_bytes, char* dst) {
+    // one warp per destination row; 16-byte vectors when the row allows it
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < n_rows; r += nwarps) {
+        const char* s = src + (long long)rows[r] * row_bytes;
+        char* d = dst + r * row_bytes;
+        if ((row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+            for (long long o = lane * 16LL; o < row_bytes; o += 512) *reinterpret_cast<int4*>(d + o) = *reinterpret_cast<const int4*>(s + o);
+        } else {
+            for (long long o = lane; o < row_bytes; o += 32) d[o] = s[o];
+        }
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int dmf_abi_version(void) { return DMF_ABI_VERSION; }
+const char* dmf_last_error(void) { return g_err.c_str(); }
+
+int dmf_create(int device, dmf_handle_t* out) {
+    if (!out) return fail(DMF_E_ARG, "out is NULL");
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(DMF_E_ARG, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(DMF_E_CUDA, "libdemethify_sm100 requires an sm_100-class (Blackwell) GPU");
+    dmf_handle_s* h = new dmf_handle_s;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = h;
+    return DMF_OK;
+}
+
+int dmf_destroy(dmf_handle_t h) {
+    delete h;
+    return DMF_OK;
+}
+
+int dmf_sm_count(dmf_handle_t h, int* out) {
+    if (!h || !out) return fail(DMF_E_ARG, "NULL argument");
+    *out = h->sm_count;
+    return DMF_OK;
+}
+
+int dmf_batch_workspace_bytes(dmf_handle_t h, const dmf_shape_t* shape, size_t* bytes) {
+    if (!h || !shape || !bytes) return fail(DMF_E_ARG, "NULL argument");
+    Plan p;
+    int rc = make_plan(h, *shape, p);
+    if (rc) return rc;
+    *bytes = p.ws_bytes;
+    return DMF_OK;
+}
+
+int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_desc_t* fits, void* ws, size_t ws_bytes,
+                     void* stream, dmf_batch_t* out) {
+    if (!h || !shape || !fits || !ws || !out) return fail(DMF_E_ARG, "NULL argument");
+    Plan p;
+    int rc = make_plan(h, *shape, p);
+    if (rc) return rc;
+    if (ws_bytes < p.ws_bytes) return fail(DMF_E_ARG, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(DMF_E_ARG, "workspace must be 256-byte aligned");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const dmf_shape_t& s = *shape;
+    std::vector<FitDev> host(s.n_fits);
+    char* base = static_cast<char*>(ws);
+    bool gather = false;
+    for (int i = 0; i < s.n_fits; ++i) {
+        const dmf_fit_desc_t& d = fits[i];
+        if (!d.X || !d.D || !d.U || !d.A || (s.K && !d.Rk)) return fail(DMF_E_ARG, "fit descriptor has a NULL matrix");
+        if (s.mode == DMF_MODE_PURITY && !d.purity) return fail(DMF_E_ARG, "purity mode needs a purity vector");
+        const uintptr_t al = reinterpret_cast<uintptr_t>(d.X) | reinterpret_cast<uintptr_t>(d.D) | reinterpret_cast<uintptr_t>(d.Rk) |
+                             reinterpret_cast<uintptr_t>(d.U) | reinterpret_cast<uintptr_t>(d.A);
+        if (al & 15) return fail(DMF_E_ARG, "matrix base pointers must be 16-byte aligned");
+        FitDev& f = host[i];
+        f.X = static_cast<const char*>(d.X);
+        f.D = static_cast<const char*>(d.D);
+        f.Rk = static_cast<const char*>(d.Rk);
+        f.rows = d.rows;
+        gather |= (d.rows != nullptr);
+        f.U = static_cast<char*>(d.U);
+        f.A = static_cast<char*>(d.A);
+        f.purity = d.purity;
+        f.trace = d.cost_trace;
+        f.trace_cap = d.cost_trace ? d.trace_cap : 0;
+        f.part = reinterpret_cast<double*>(base + p.off_part + p.per_fit_part * i);
+        f.gpart = reinterpret_cast<double*>(base + p.off_gpart + p.per_fit_gpart * i);
+        f.tickets = reinterpret_cast<unsigned*>(base + p.off_tickets + p.per_fit_tickets * i);
+        f.st = reinterpret_cast<FitState*>(base + p.off_states) + i;
+        f.pad = 0;
+    }
+    dmf_batch_s* b = new dmf_batch_s;
+    b->h = h;
+    b->shape = s;
+    b->launches = 0;
+    b->pinned = nullptr;
+    Geom& g = b->g;
+    g.M = s.M; g.N = s.N; g.K = s.K; g.nu = s.n_u; g.Kt = s.K + s.n_u;
+    g.ldx = s.ldx; g.ldd = s.ldd; g.ldr = s.K ? s.ldr : 0;
+    g.uslot_bytes = s.u_slot * (s.dtype == DMF_F64 ? 8 : 4);
+    g.tile_rows = p.tile_rows; g.n_tiles = p.n_tiles;
+    g.ntc = p.ntc_alpha; g.rg = kConsumers / p.ntc_alpha;
+    g.n_parts = p.n_parts; g.n_groups = p.n_groups; g.part_stride = p.part_stride;
+    g.offX = p.offX; g.offD = p.offD; g.offR = p.offR; g.offU = p.offU; g.offUp = p.offUp; g.stage_bytes = p.stage_bytes;
+    g.row_bulk = p.row_bulk; g.mode = s.mode; g.gather = gather ? 1 : 0;
+    b->ktb = p.ktb; b->nub = p.nub; b->c_alpha = p.c_alpha; b->c_u = p.c_u;
+    b->ntc_alpha = p.ntc_alpha; b->ntc_u = p.ntc_u;
+    b->smem_alpha = p.smem_alpha; b->smem_u = p.smem_u; b->smem_cost = p.smem_cost; b->occ = p.occ;
+    b->fits_dev = reinterpret_cast<FitDev*>(base + p.off_fits);
+    b->states_dev = reinterpret_cast<FitState*>(base + p.off_states);
+    if ((rc = set_smem(k_cost(b), b->smem_cost)) || (rc = set_smem(k_alpha(b), b->smem_alpha)) || (rc = set_smem(k_u(b), b->smem_u))) {
+        delete b;
+        return rc;
+    }
+    // zero states + tickets, upload descriptors (pageable source: the copy is staged before return)
+    cudaError_t e = cudaMemsetAsync(base + p.off_states, 0, p.off_part - p.off_states, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->fits_dev, host.data(), sizeof(FitDev) * s.n_fits, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->pinned, sizeof(FitState) * s.n_fits);
+    if (e != cudaSuccess) {
+        delete b;
+        return fail(DMF_E_CUDA, std::string("batch set-up: ") + cudaGetErrorString(e));
+    }
+    *out = b;
+    return DMF_OK;
+}
+
+int dmf_batch_destroy(dmf_batch_t b) {
+    if (!b) return DMF_OK;
+    if (b->pinned) cudaFreeHost(b->pinned);
+    delete b;
+    return DMF_OK;
+}
+
+int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows, int32_t* smem_bytes) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (ctas_per_fit) *ctas_per_fit = b->g.n_parts;
+    if (tile_rows) *tile_rows = b->g.tile_rows;
+    if (smem_bytes) *smem_bytes = (int32_t)std::max(b->smem_alpha, b->smem_u);
+    return DMF_OK;
+}
+
+int dmf_pass_init(dmf_batch_t b, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    return launch(b, k_cost(b), b->ntc_alpha, b->smem_cost, kFlagInitial, 0, 0.0, (cudaStream_t)stream);
+}
+int dmf_pass_cost(dmf_batch_t b, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    return launch(b, k_cost(b), b->ntc_alpha, b->smem_cost, 0, 0, tol, (cudaStream_t)stream);
+}
+int dmf_pass_u(dmf_batch_t b, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    return launch(b, k_u(b), b->ntc_u, b->smem_u, 0, 0, 0.0, (cudaStream_t)stream);
+}
+int dmf_pass_alpha(dmf_batch_t b, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (b->shape.mode == DMF_MODE_PURITY) return fail(DMF_E_STATE, "purity batches use dmf_pass_fw");
+    return launch(b, k_alpha(b), b->ntc_alpha, b->smem_alpha, 0, 0, 0.0, (cudaStream_t)stream);
+}
+int dmf_pass_fw(dmf_batch_t b, int32_t k_inner, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (b->shape.mode != DMF_MODE_PURITY) return fail(DMF_E_STATE, "Frank-Wolfe steps need a purity batch");
+    return launch(b, k_alpha(b), b->ntc_alpha, b->smem_alpha, kFlagFW, k_inner, 0.0, (cudaStream_t)stream);
+}
+
+int dmf_enqueue_outer(dmf_batch_t b, int32_t n_outer, int32_t n_iter2, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    int rc;
+    for (int o = 0; o < n_outer; ++o) {
+        for (int i = 0; i < n_iter2; ++i)
+            if ((rc = dmf_pass_u(b, stream))) return rc;
+        for (int i = 0; i < n_iter2; ++i)
+            if ((rc = (b->shape.mode == DMF_MODE_PURITY) ? dmf_pass_fw(b, i, stream) : dmf_pass_alpha(b, stream))) return rc;
+        if ((rc = dmf_pass_cost(b, tol, stream))) return rc;
+    }
+    return DMF_OK;
+}
+
+int dmf_batch_read_state(dmf_batch_t b, dmf_fit_state_t* out, int32_t n, void* stream) {
+    if (!b || !out) return fail(DMF_E_ARG, "NULL argument");
+    if (n > b->shape.n_fits) n = b->shape.n_fits;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(b->pinned, b->states_dev, sizeof(FitState) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) {
+        const FitState& s = b->pinned[i];
+        out[i].cost = s.cf; out[i].cost_prev = s.cf_prev; out[i].l_w = s.l_w; out[i].l_h = s.l_h;
+        out[i].a1 = s.a1; out[i].a2 = s.a2; out[i].dmax = s.dmax;
+        out[i].n_outer = s.n_outer; out[i].done = s.done; out[i].u_slot = s.u_cur; out[i].a_slot = s.a_cur;
+    }
+    return DMF_OK;
+}
+
+int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (n_iter1 < 0 || n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dmf_pass_init(b, stream);
+    if (rc) return rc;
+    // Outer iterations are enqueued in chunks; after each chunk the per-fit `done` flags come back through
+    // pinned memory.  Terminated fits skip their launches on the device, so over-enqueueing is harmless.
+    int issued = 0, chunk = 2;
+    const int n = b->shape.n_fits;
+    while (issued < n_iter1) {
+        const int todo = std::min(chunk, n_iter1 - issued);
+        if ((rc = dmf_enqueue_outer(b, todo, n_iter2, tol, stream))) return rc;
+        issued += todo;
+        CUDA_TRY(cudaMemcpyAsync(b->pinned, b->states_dev, sizeof(FitState) * n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        bool all_done = true;
+        for (int i = 0; i < n; ++i) {
+            if (b->pinned[i].done == 3) return fail(DMF_E_STATE, "non-finite values reached the simplex projection (fit " + std::to_string(i) + ")");
+            all_done &= (b->pinned[i].done != 0);
+        }
+        if (all_done) break;
+        chunk = std::min(chunk * 2, 16);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DMF_OK;
+}
+
+int dmf_batch_launch_count(dmf_batch_t b, int64_t* out) {
+    if (!b || !out) return fail(DMF_E_ARG, "NULL argument");
+    *out = b->launches;
+    return DMF_OK;
+}
+
+int dmf_pack_weights_u16(const void* src, int32_t kind, int64_t count, uint16_t* dst, int32_t* bad_dev, void* stream) {
+    if (!src || !dst || !bad_dev || count < 0) return fail(DMF_E_ARG, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(bad_dev, 0, sizeof(int32_t), st));
+    if (count == 0) return DMF_OK;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((count + threads - 1) / threads, 148 * 16);
+    if (kind == 0) pack_u16_kernel<double><<<blocks, threads, 0, st>>>((const double*)src, count, dst, bad_dev);
+    else if (kind == 1) pack_u16_kernel<float><<<blocks, threads, 0, st>>>((const float*)src, count, dst, bad_dev);
+    else if (kind == 2) pack_u16_kernel<long long><<<blocks, threads, 0, st>>>((const long long*)src, count, dst, bad_dev);
+    else return fail(DMF_E_ARG, "src_kind must be 0 (f64), 1 (f32) or 2 (i64)");
+    CUDA_TRY(cudaGetLastError());
+    return DMF_OK;
+}
+
+int dmf_gather_rows(const void* src, const int32_t* rows, int64_t n_rows, int64_t row_elems, int32_t elem_bytes, void* dst, void* stream) {
+    if (!src || !rows || !dst || n_rows < 0 || row_elems <= 0) return fail(DMF_E_ARG, "bad argument");
+    if (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8) return fail(DMF_E_ARG, "elem_bytes must be 1, 2, 4 or 8");
+    if (n_rows == 0) return DMF_OK;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((n_rows * 32 + threads - 1) / threads, 148 * 16);
+    gather_rows_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((const char*)src, rows, n_rows, row_elems * elem_bytes, (char*)dst);
+    CUDA_TRY(cudaGetLastError());
+    return DMF_OK;
+}
+
+}  // extern "C"

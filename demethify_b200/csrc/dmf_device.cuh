@@ -1,0 +1,240 @@
+// dmf_device.cuh — device-side building blocks shared by the sm_100a deconvolution kernels:
+// mbarrier / bulk-copy (TMA, UBLKCP) wrappers, the producer-warp tile pipeline, and the
+// deterministic two-level cross-CTA reduction ("last CTA of a group, last group of the fit").
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dmf {
+
+constexpr int kConsumers = 256;             // consumer threads per CTA (8 warps)
+constexpr int kThreads = kConsumers + 32;   // + one producer warp
+constexpr int kStages = 4;                  // smem ring depth
+constexpr int kGroup = 16;                  // CTAs per first-level reduction group
+constexpr int kMaxKt = 32;                  // K + n_u supported by the register-tiled kernels
+
+// ------------------------------------------------------------------------------------------------
+// Device-side descriptors (mirrors of the host structs in dmf_api.cu)
+struct FitState {
+    double a1, a2;                 // extrapolation scalars (deconvolution.py:84,96)
+    double l_w, l_w_old;           // ||alpha_unk||^2 * dmax^2 and its previous value
+    double l_h, l_h_old;           // ||R||^2 * dmax^2 and its previous value
+    double cf, cf_prev;            // cost after / before the last outer iteration
+    double dmax, dmax2;            // max d_x and its square
+    double ssq_rk, ssq_u;          // ||R_trunc||_F^2 (constant) and ||u||_F^2 (current)
+    int u_cur, a_cur;              // ping-pong slots holding the current iterate
+    int n_outer, done;             // done: 0 running, 1 converged, 3 numerical failure (NaN in projection)
+    int pad[4];
+};
+
+struct FitDev {
+    const char* X;
+    const char* D;
+    const char* Rk;
+    const int32_t* rows;
+    char* U;
+    char* A;
+    const double* purity;
+    double* trace;
+    double* part;        // [n_parts][part_stride] per-CTA partial sums
+    double* gpart;       // [n_groups][part_stride] per-group partial sums
+    unsigned* tickets;   // [n_groups + 1]
+    FitState* st;
+    int trace_cap;
+    int pad;
+};
+
+struct Geom {
+    long long M;
+    int N, K, nu, Kt;
+    long long ldx, ldd, ldr;       // row pitches in elements
+    long long uslot_bytes;         // bytes between the two U slots
+    int tile_rows, n_tiles;
+    int ntc, rg;                   // threads per row (power of two), row groups per CTA
+    int n_parts, n_groups;         // CTAs per fit, reduction groups per fit
+    int part_stride;               // doubles per partial record
+    unsigned offX, offD, offR, offU, offUp, stage_bytes;   // smem stage layout (bytes)
+    unsigned row_bulk;             // bit0 X, bit1 D, bit2 Rk: per-row bulk copies legal in gather mode
+    int mode;                      // DMF_MODE_*
+    int gather;                    // any fit uses a row index
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernel argument block and shared-memory control block
+struct PassArgs {
+    Geom g;
+    const FitDev* fits;
+    int k_inner;      // Frank-Wolfe iteration index
+    int flags;        // kFlag*
+    double tol;
+};
+constexpr int kFlagInitial = 1;   // init_cost_kernel: set-up pass (norms, max d, no termination test)
+constexpr int kFlagFW = 2;        // alpha_pass_kernel: Frank-Wolfe step instead of projected gradient
+
+struct SmemCtl {
+    unsigned long long full[kStages];
+    unsigned long long empty[kStages];
+    int flag;
+    int pad;
+};
+constexpr unsigned kCtlBytes = 128;
+static_assert(sizeof(SmemCtl) <= kCtlBytes, "control block too large");
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// weights: stored as T or as uint16 coverage counts
+template <typename T, typename WT>
+__device__ __forceinline__ T wload(const void* base, long long idx) {
+    return (T) reinterpret_cast<const WT*>(base)[idx];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile pipeline.  One stage holds `tile_rows` rows of X, D, Rk, U(cur) and optionally U(prev).
+struct TileSrc {
+    const char* base;      // global base of the matrix (fit-specific)
+    long long pitch;       // bytes per row
+    unsigned off;          // offset inside the stage
+    bool gathered;         // rows come through the fit's row index
+    bool row_bulk;         // per-row bulk copy legal (pitch % 16 == 0)
+};
+
+// Executed by the whole producer warp.  Fills stage `sbase` with rows [r0, r0+nrows) of every source
+// and arms `full_bar` with the number of bytes that will arrive asynchronously.
+__device__ __forceinline__ void produce_tile(const TileSrc* src, int nsrc, const int32_t* rows, long long r0, int nrows,
+                                             char* sbase, uint32_t full_bar, int lane) {
+    uint32_t tx = 0;
+    // pass 1: everything that cannot go through the bulk-copy engine is copied by the warp itself
+    for (int s = 0; s < nsrc; ++s) {
+        const TileSrc& m = src[s];
+        if (m.base == nullptr) continue;
+        char* dst = sbase + m.off;
+        if (m.gathered && rows != nullptr) {
+            if (m.row_bulk) {
+                tx += (uint32_t)(nrows * m.pitch);
+            } else {
+                for (int r = 0; r < nrows; ++r) {
+                    const char* g = m.base + (long long)rows[r0 + r] * m.pitch;
+                    for (long long b = lane; b < m.pitch; b += 32) dst[r * m.pitch + b] = g[b];
+                }
+            }
+        } else {
+            const long long total = (long long)nrows * m.pitch;
+            const long long bulk = total & ~15LL;
+            tx += (uint32_t)bulk;
+            const char* g = m.base + r0 * m.pitch;
+            for (long long b = bulk + lane; b < total; b += 32) dst[b] = g[b];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(full_bar, tx);
+    __syncwarp();
+    // pass 2: issue the bulk copies
+    for (int s = 0; s < nsrc; ++s) {
+        const TileSrc& m = src[s];
+        if (m.base == nullptr) continue;
+        const uint32_t dst = smem_u32(sbase + m.off);
+        if (m.gathered && rows != nullptr) {
+            if (m.row_bulk) {
+                for (int r = lane; r < nrows; r += 32)
+                    bulk_g2s(dst + (uint32_t)(r * m.pitch), m.base + (long long)rows[r0 + r] * m.pitch, (uint32_t)m.pitch,
+                             full_bar);
+            }
+        } else if (lane == 0) {
+            const long long bulk = ((long long)nrows * m.pitch) & ~15LL;
+            // one copy may not exceed the mbarrier tx-count range comfortably; chunk at 64 KB
+            const char* g = m.base + r0 * m.pitch;
+            for (long long o = 0; o < bulk; o += 65536) {
+                const uint32_t n = (uint32_t)((bulk - o) < 65536 ? (bulk - o) : 65536);
+                bulk_g2s(dst + (uint32_t)o, g + o, n, full_bar);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic two-level reduction of per-CTA partial records.
+// Every CTA of the fit has written `n` doubles to f.part[blockIdx.x * stride ...].  Returns true in
+// exactly one CTA of the fit, in which out_sm[0..n) holds the totals, summed in CTA-index order
+// inside each group and in group order across groups (independent of arrival order).
+__device__ __forceinline__ bool hier_reduce(const Geom& g, const FitDev& f, double* out_sm, int n, int* s_flag) {
+    const int tid = threadIdx.x;
+    const int grp = blockIdx.x / kGroup;
+    const int gfirst = grp * kGroup;
+    const int gsize = min(kGroup, g.n_parts - gfirst);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_flag = (atomicAdd(&f.tickets[grp], 1u) == (unsigned)(gsize - 1));
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    const bool single = (g.n_groups == 1);
+    for (int e = tid; e < n; e += blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < gsize; ++p) s += __ldcg(&f.part[(size_t)(gfirst + p) * g.part_stride + e]);
+        if (single)
+            out_sm[e] = s;
+        else
+            f.gpart[(size_t)grp * g.part_stride + e] = s;
+    }
+    if (tid == 0) f.tickets[grp] = 0u;   // re-arm for the next launch
+    if (single) {
+        __syncthreads();
+        return true;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_flag = (atomicAdd(&f.tickets[g.n_groups], 1u) == (unsigned)(g.n_groups - 1));
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    for (int e = tid; e < n; e += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < g.n_groups; ++q) s += __ldcg(&f.gpart[(size_t)q * g.part_stride + e]);
+        out_sm[e] = s;
+    }
+    if (tid == 0) f.tickets[g.n_groups] = 0u;
+    __syncthreads();
+    return true;
+}
+
+// extrapolation weight of the accelerated projected-gradient steps (deconvolution.py:83-85, 95-97)
+__device__ __forceinline__ double next_momentum(double a_prev) { return (1.0 + sqrt(1.0 + 4.0 * a_prev * a_prev)) / 2.0; }
+__device__ __forceinline__ double extrap_beta(double a_prev, double a_next, double l_old, double l_new) {
+    return fmin((a_prev - 1.0) / a_next, 0.9999 * sqrt(l_old / l_new));
+}
+
+}  // namespace dmf

@@ -1,0 +1,12 @@
+// dmf_inst.h — kernel lookup functions, one set per (element type, weight storage) translation unit.
+#pragma once
+#include "dmf_device.cuh"
+namespace dmf {
+typedef void (*kern_t)(const PassArgs);
+#define DMF_DECL(TAG)                                      \
+    kern_t pick_cost_##TAG(int ktb, int nub, int c);       \
+    kern_t pick_alpha_##TAG(int ktb, int nub, int c);      \
+    kern_t pick_u_##TAG(int ktb, int nub, int c);
+DMF_DECL(f64_f64) DMF_DECL(f64_u16) DMF_DECL(f32_f32) DMF_DECL(f32_u16)
+#undef DMF_DECL
+}  // namespace dmf

@@ -1,0 +1,161 @@
+"""Drop-in mirror of the reference's demethify/deconvolution.py on top of the sm_100a kernel library.
+
+Same function names, argument order, defaults and numpy-in / numpy-out contract as the reference
+(file:line cited per function); the arithmetic of every solver step runs in libdemethify_sm100.so.
+Initial draws use numpy's legacy MT19937 stream exactly as the reference does (set_seed -> numpy.random),
+so that u0 / alpha0 are bit-identical for a given seed.
+"""
+import numpy as np
+import numpy.random as rd
+
+from . import _lib
+from .engine import DeviceProblem, FitBatch
+from .init_func import wls_intercept, constrained_nndsvd, nndsvd_initialize
+
+__all__ = ["set_seed", "cost_f_w", "projection_simplex_sort_2d", "init_BSSMF_md", "init_BSSMF_md_p",
+           "mdwbssmf_deconv", "mdwbssmf_deconv_p", "unsupervised_deconv", "last_fit_info"]
+
+_last = {}
+
+
+def last_fit_info():
+    """{'n_outer', 'cost', 'launches'} of the most recent solver call (the reference exposes no such hook;
+    needed for the identical-iteration-count parity check)."""
+    return dict(_last)
+
+
+def set_seed(seed=None):
+    """deconvolution.py:9-11 — seeds numpy's global legacy stream (int -> init_genrand, list -> init_by_array)."""
+    if seed is not None:
+        rd.seed(seed)
+
+
+def cost_f_w(y, R, alpha, d_x):
+    """deconvolution.py:15-17 — sum d_x * (y - R @ alpha)^2, one streaming pass on the GPU."""
+    R = np.asarray(R)
+    alpha = np.asarray(alpha)
+    Kt = R.shape[1]
+    # the kernels take [R_trunc | u]; any split is equivalent for the cost, use the last column as "u"
+    prob = DeviceProblem(y, d_x, R[:, :Kt - 1] if Kt > 1 else None)
+    batch = FitBatch(prob, 1, [R[:, Kt - 1:]], [alpha], mode=_lib.DMF_MODE_PARTIAL if Kt > 1 else _lib.DMF_MODE_UNSUPERVISED)
+    batch.pass_init()
+    cost = batch.states()[0].cost
+    batch.close()
+    return cost
+
+
+def projection_simplex_sort_2d(v, z=1):
+    """deconvolution.py:21-37 — column-wise Euclidean projection onto the simplex.  On the solver path this
+    runs inside the alpha-step kernel; this standalone form (used only by the SVD init on a Kt x N matrix)
+    is host-side glue."""
+    v = np.asarray(v, dtype=np.float64)
+    p, n = v.shape
+    srt = -np.sort(-v, axis=0)
+    pi = np.cumsum(srt, axis=0) - z
+    ok = (srt - pi / np.arange(1, p + 1)[:, None]) > 0
+    if not ok.any(axis=0).all():
+        raise ZeroDivisionError("division by zero")
+    rho = p - 1 - np.argmax(ok[::-1], axis=0)
+    theta = pi[rho, np.arange(n)] / (rho + 1)
+    return np.maximum(v - theta, 0)
+
+
+def _draw(init_option, meth_frequency, d_x, R_trunc, n_u):
+    M, K = R_trunc.shape
+    nb = meth_frequency.shape[1]
+    if init_option == "uniform":
+        u = rd.uniform(size=(M, n_u))
+        full = np.c_[R_trunc, u]
+        alpha = np.concatenate([wls_intercept(meth_frequency[:, k:k + 1], d_x[:, k:k + 1], full) for k in range(nb)], axis=1)
+    elif init_option == "uniform_":
+        u = rd.uniform(size=(M, n_u))
+        alpha = rd.dirichlet(np.ones(K + n_u), nb).T
+    elif init_option == "beta":
+        temp = np.ones((M, n_u))
+        u = rd.beta(temp * 0.5, temp * 0.5)
+        alpha = rd.dirichlet(np.ones(K + n_u), nb).T
+    elif init_option == "SVD":
+        W, alpha = constrained_nndsvd(meth_frequency, R_trunc, d_x, rank=n_u, flag=0)
+        u = W[:, K:]
+    elif init_option == "ICA":
+        raise NotImplementedError("--init ICA forms an M x M covariance (init_func.py:120) and is out of scope of the "
+                                  "B200 path (SURVEY.md 2.1 row 4); use uniform_, uniform, beta or SVD")
+    else:
+        raise ValueError(f"unknown init option {init_option!r}")
+    return u, alpha
+
+
+def init_BSSMF_md(init_option, meth_frequency, d_x, R_trunc, n_u, seed=None, rb_alg=wls_intercept):
+    """deconvolution.py:40-78."""
+    set_seed(seed)
+    nb = meth_frequency.shape[1]
+    if init_option != "uniform_" and n_u > nb:
+        init_option = "uniform_"
+    u, alpha = _draw(init_option, meth_frequency, d_x, R_trunc, n_u)
+    if init_option == "SVD":
+        alpha = projection_simplex_sort_2d(alpha)
+    R = np.c_[R_trunc, u]
+    if alpha[-n_u:][0].all() == 0.0:                      # :74-76
+        alpha[-n_u:][0] = 1e-10
+        alpha[:-n_u] = (1 - 1e-10) * alpha[:-n_u]
+    return u, R, alpha
+
+
+def init_BSSMF_md_p(init_option, meth_frequency, d_x, R_trunc, n_u, purity, rb_alg=wls_intercept, seed=None):
+    """deconvolution.py:228-267."""
+    set_seed(seed)
+    nb = meth_frequency.shape[1]
+    if init_option != "uniform" and n_u > nb:
+        print("The number of unknowns is greater than the number of samples, we'll go with a uniform initialisation. ")
+        init_option = "uniform"
+    if init_option != "uniform_" and n_u > nb:
+        init_option = "uniform_"
+    u, alpha = _draw(init_option, meth_frequency, d_x, R_trunc, n_u)
+    if init_option == "SVD":                               # :262
+        alpha = np.vstack((purity * projection_simplex_sort_2d(alpha[:-n_u]), projection_simplex_sort_2d(alpha[-n_u:])))
+    R = np.c_[R_trunc, u]
+    return u, R, alpha
+
+
+def _solve(mode, u, alpha, meth_frequency, d_x, R_trunc, n_u, n_iter1, n_iter2, tol, purity=None):
+    prob = DeviceProblem(meth_frequency, d_x, R_trunc)
+    batch = FitBatch(prob, n_u, [np.asarray(u).reshape(-1, n_u)], [np.asarray(alpha)], mode=mode, purity=purity)
+    states = batch.fit(n_iter1, n_iter2, tol)
+    (u_out, a_out, n_outer, cost), = batch.results(states)
+    _last.update(n_outer=n_outer, cost=cost, launches=batch.launch_count(), geometry=batch.geometry())
+    batch.close()
+    return u_out, a_out
+
+
+def mdwbssmf_deconv(u, R, alpha, meth_frequency, d_x, R_trunc, n_u, n_iter1=100000, n_iter2=50, tol=1e-3):
+    """deconvolution.py:190-223 — partial-reference accelerated projected gradient; returns (u, alpha)."""
+    return _solve(_lib.DMF_MODE_PARTIAL, u, alpha, meth_frequency, d_x, R_trunc, n_u, n_iter1, n_iter2, tol)
+
+
+def mdwbssmf_deconv_p(u, R, alpha, meth_frequency, d_x, R_trunc, n_u, purity, n_iter1=100, n_iter2=500, tol=1e-3):
+    """deconvolution.py:305-337 — purity-constrained variant (U step + Frank-Wolfe alpha step)."""
+    return _solve(_lib.DMF_MODE_PURITY, u, alpha, meth_frequency, d_x, R_trunc, n_u, n_iter1, n_iter2, tol, purity=purity)
+
+
+def unsupervised_deconv(meth_frequency, n_u, d_x, init_option, n_iter1=100000, n_iter2=20, tol=1e-3, seed=None):
+    """deconvolution.py:107-184 — reference-free variant (no R_trunc)."""
+    set_seed(seed)
+    M, nb = meth_frequency.shape
+    if init_option != "uniform_" and n_u > nb:
+        init_option = "uniform_"
+    if init_option == "uniform_":
+        u = rd.uniform(size=(M, n_u))
+        alpha = rd.dirichlet(np.ones(n_u), nb).T
+    elif init_option == "beta":
+        temp = np.ones((M, n_u))
+        u = rd.beta(temp * 0.5, temp * 0.5)
+        alpha = rd.dirichlet(np.ones(n_u), nb).T
+    elif init_option == "SVD":
+        u, alpha = nndsvd_initialize(meth_frequency, rank=n_u)
+        u = u.clip(0, 1)
+        alpha = projection_simplex_sort_2d(alpha)
+    elif init_option == "uniform":
+        raise NameError("name 'R_trunc' is not defined")   # what the reference does (deconvolution.py:117)
+    else:
+        raise NotImplementedError(f"init option {init_option!r} is not available on the B200 path")
+    return _solve(_lib.DMF_MODE_UNSUPERVISED, u, alpha, meth_frequency, d_x, None, n_u, n_iter1, n_iter2, tol)

@@ -1,0 +1,241 @@
+"""Device-side plumbing between the reference-shaped Python API and the C ABI.
+
+torch is used for device memory, streams and host<->device copies only; every arithmetic step on the
+deconvolution path is a kernel of libdemethify_sm100.so reached through `_lib` (ctypes).
+
+  DeviceProblem : X, d_x, R_trunc resident in HBM (d_x narrowed to uint16 when it is integer coverage)
+  FitBatch      : a set of independent fits of one shape (restarts, bootstrap resamples, BCV folds)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, get_precision
+
+_handles = {}
+
+
+def _handle(device_index):
+    if device_index not in _handles:
+        h = C.c_void_p()
+        _lib.check(_lib.lib().dmf_create(device_index, C.byref(h)))
+        _handles[device_index] = h
+    return _handles[device_index]
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.DmfError("demethify_b200 needs a CUDA device (B200); there is no CPU fallback")
+
+
+def current_device():
+    _require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _tdtype(precision):
+    return torch.float64 if precision == "fp64" else torch.float32
+
+
+def to_device(arr, dtype=None, device=None):
+    """Host ndarray / tensor -> contiguous device tensor (async when the source is pinned)."""
+    device = device or current_device()
+    if isinstance(arr, torch.Tensor):
+        t = arr
+    else:
+        a = np.asarray(arr)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)        # pandas .values arrive F-ordered
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.from_numpy(a)
+    t = t.to(device, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class DeviceProblem:
+    """X (M x N), d_x (M x N) and R_trunc (M x K, optional) in HBM in the layout the kernels stream."""
+
+    def __init__(self, X, D, Rk=None, precision=None, narrow_weights=True, device=None):
+        _require_cuda()
+        self.precision = precision or get_precision()
+        self.device = device or current_device()
+        self.dtype = _tdtype(self.precision)
+        self.X = to_device(X, self.dtype, self.device)
+        self.M, self.N = self.X.shape
+        self.K = 0
+        self.Rk = None
+        if Rk is not None:
+            self.Rk = to_device(Rk, self.dtype, self.device)
+            if self.Rk.ndim != 2 or self.Rk.shape[0] != self.M:
+                raise ValueError("R_trunc must be M x K")
+            self.K = self.Rk.shape[1]
+        self.set_weights(D, narrow_weights)
+
+    def set_weights(self, D, narrow=True):
+        """Upload d_x.  Integer coverage in [0, 65535] is stored as uint16 (2 B/entry instead of 8)."""
+        raw = to_device(D, None, self.device)
+        if tuple(raw.shape) != (self.M, self.N):
+            raise ValueError("d_x must have the shape of meth_frequency")
+        self.wtype = _lib.DMF_W_FLOAT
+        self.D = None
+        if narrow:
+            kind = {torch.float64: 0, torch.float32: 1, torch.int64: 2}.get(raw.dtype)
+            if kind is None:
+                raw = raw.to(torch.float64)
+                kind = 0
+            packed = torch.empty((self.M, self.N), dtype=torch.uint16, device=self.device)
+            bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().dmf_pack_weights_u16(C.c_void_p(raw.data_ptr()), kind, raw.numel(), C.c_void_p(packed.data_ptr()),
+                                                       C.c_void_p(bad.data_ptr()), _stream_ptr()))
+            if int(bad.item()) == 0:
+                self.D, self.wtype = packed, _lib.DMF_W_U16
+        if self.D is None:
+            self.D = raw.to(self.dtype).contiguous()
+
+    def with_weights(self, D_tensor, wtype):
+        """Shallow copy sharing X / R_trunc with different weights (BCV folds, ic.py:75)."""
+        other = object.__new__(DeviceProblem)
+        other.__dict__.update(self.__dict__)
+        other.D, other.wtype = D_tensor, wtype
+        return other
+
+
+class FitBatch:
+    """n_fits independent fits of one (M, N, K, n_u) shape, advanced together by single launches."""
+
+    def __init__(self, problems, n_u, U0, A0, mode=_lib.DMF_MODE_PARTIAL, purity=None, rows=None, trace_cap=0,
+                 max_ctas_per_fit=0):
+        probs = problems if isinstance(problems, (list, tuple)) else [problems]
+        self.n_fits = len(U0)
+        if len(probs) == 1:
+            probs = list(probs) * self.n_fits
+        if len(probs) != self.n_fits or len(A0) != self.n_fits:
+            raise ValueError("one problem / U0 / A0 per fit expected")
+        p0 = probs[0]
+        self.p0, self.probs = p0, probs
+        self.M, self.N, self.K, self.n_u = p0.M, p0.N, p0.K, int(n_u)
+        self.Kt = self.K + self.n_u
+        self.mode = mode
+        dev, dt = p0.device, p0.dtype
+        self.device = dev
+        if rows is not None:
+            self.M = int(rows[0].shape[0])
+        # ping-pong buffers: both slots start at the initial iterate (u_ = u.copy(), deconvolution.py:194-195)
+        self.u_slot = (self.M * self.n_u + 31) // 32 * 32          # slot stride keeps bulk copies 16-byte aligned
+        self.U = torch.zeros((self.n_fits, 2, self.u_slot), dtype=dt, device=dev)
+        self.A = torch.empty((self.n_fits, 2, self.Kt, self.N), dtype=dt, device=dev)
+        for i in range(self.n_fits):
+            u = to_device(U0[i], dt, dev).reshape(self.M, self.n_u)
+            a = to_device(A0[i], dt, dev).reshape(self.Kt, self.N)
+            self.u_view(i, 0).copy_(u); self.u_view(i, 1).copy_(u)
+            self.A[i, 0].copy_(a); self.A[i, 1].copy_(a)
+        self.purity = None
+        if mode == _lib.DMF_MODE_PURITY:
+            self.purity = to_device(np.asarray(purity, dtype=np.float64).reshape(-1), torch.float64, dev)
+            if self.purity.numel() != self.N:
+                raise ValueError("purity needs one value per sample")
+        self.rows = None
+        if rows is not None:
+            self.rows = [to_device(np.asarray(r, dtype=np.int32), torch.int32, dev) for r in rows]
+        self.trace_cap = int(trace_cap)
+        self.trace = torch.zeros((self.n_fits, max(self.trace_cap, 1)), dtype=torch.float64, device=dev) if trace_cap else None
+
+        lib = _lib.lib()
+        self.h = _handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.shape = _lib.Shape(M=self.M, N=self.N, K=self.K, n_u=self.n_u,
+                                dtype=_lib.DMF_F64 if dt == torch.float64 else _lib.DMF_F32, wtype=p0.wtype, mode=mode,
+                                n_fits=self.n_fits, max_ctas_per_fit=max_ctas_per_fit, ldx=self.N, ldd=self.N, ldr=max(self.K, 1),
+                                u_slot=self.u_slot)
+        nbytes = C.c_size_t()
+        _lib.check(lib.dmf_batch_workspace_bytes(self.h, C.byref(self.shape), C.byref(nbytes)))
+        self.ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+        descs = (_lib.FitDesc * self.n_fits)()
+        for i, p in enumerate(probs):
+            if (p.N, p.K, p.wtype, p.dtype) != (p0.N, p0.K, p0.wtype, p0.dtype):
+                raise ValueError("all problems of a batch must share shape and storage types")
+            d = descs[i]
+            d.X, d.D = p.X.data_ptr(), p.D.data_ptr()
+            d.Rk = p.Rk.data_ptr() if p.Rk is not None else None
+            d.rows = self.rows[i].data_ptr() if self.rows is not None else None
+            d.U, d.A = self.U[i].data_ptr(), self.A[i].data_ptr()
+            d.purity = self.purity.data_ptr() if self.purity is not None else None
+            d.cost_trace = self.trace[i].data_ptr() if self.trace is not None else None
+            d.trace_cap = self.trace_cap
+        ws_ptr = (self.ws.data_ptr() + 255) // 256 * 256
+        self.b = C.c_void_p()
+        _lib.check(lib.dmf_batch_create(self.h, C.byref(self.shape), descs, C.c_void_p(ws_ptr), nbytes.value, _stream_ptr(), C.byref(self.b)))
+
+    def u_view(self, i, slot):
+        return self.U[i, slot, :self.M * self.n_u].view(self.M, self.n_u)
+
+    # -- single reference-shaped steps (one launch each)
+    def pass_init(self):
+        _lib.check(_lib.lib().dmf_pass_init(self.b, _stream_ptr()))
+
+    def pass_u(self):
+        _lib.check(_lib.lib().dmf_pass_u(self.b, _stream_ptr()))
+
+    def pass_alpha(self):
+        _lib.check(_lib.lib().dmf_pass_alpha(self.b, _stream_ptr()))
+
+    def pass_fw(self, k):
+        _lib.check(_lib.lib().dmf_pass_fw(self.b, int(k), _stream_ptr()))
+
+    def pass_cost(self, tol):
+        _lib.check(_lib.lib().dmf_pass_cost(self.b, float(tol), _stream_ptr()))
+
+    def enqueue_outer(self, n_outer, n_iter2, tol):
+        _lib.check(_lib.lib().dmf_enqueue_outer(self.b, int(n_outer), int(n_iter2), float(tol), _stream_ptr()))
+
+    def fit(self, n_iter1, n_iter2, tol):
+        """Run every fit to termination (|cf - cf_0| < tol) or n_iter1 outer iterations."""
+        _lib.check(_lib.lib().dmf_fit_batched(self.b, int(n_iter1), int(n_iter2), float(tol), _stream_ptr()))
+        return self.states()
+
+    def states(self):
+        out = (_lib.FitState * self.n_fits)()
+        _lib.check(_lib.lib().dmf_batch_read_state(self.b, out, self.n_fits, _stream_ptr()))
+        return list(out)
+
+    def geometry(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().dmf_batch_geometry(self.b, C.byref(a), C.byref(b), C.byref(c)))
+        return {"ctas_per_fit": a.value, "tile_rows": b.value, "smem_bytes": c.value}
+
+    def launch_count(self):
+        n = C.c_int64()
+        _lib.check(_lib.lib().dmf_batch_launch_count(self.b, C.byref(n)))
+        return n.value
+
+    def current(self, i, states=None):
+        """Device tensors (U, alpha) holding fit i's current iterate."""
+        st = (states or self.states())[i]
+        return self.u_view(i, st.u_slot), self.A[i, st.a_slot]
+
+    def results(self, states=None):
+        """[(u ndarray Mxn_u, alpha ndarray KtxN, n_outer, cost)] as float64 host arrays."""
+        states = states or self.states()
+        out = []
+        for i, st in enumerate(states):
+            u, a = self.current(i, states)
+            out.append((u.to(torch.float64).cpu().numpy(), a.to(torch.float64).cpu().numpy(), st.n_outer, st.cost))
+        return out
+
+    def close(self):
+        if getattr(self, "b", None) is not None and self.b.value:
+            _lib.lib().dmf_batch_destroy(self.b)
+            self.b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,146 @@
+/*
+ * demethify_b200.h — C ABI of libdemethify_sm100.so, the sm_100a kernel library behind the
+ * DeMethify NMF-deconvolution hot path (X ~ [R|U]·alpha, accelerated projected gradient).
+ *
+ * The reference (cortes-ciriano-lab/DeMethify) is pure Python + numba and has NO FFI of its own
+ * (SURVEY.md §8 b1/b2); every entry point below therefore cites the reference FUNCTION whose
+ * arithmetic it replaces (file:line under demethify/), and INTEGRATION.md shows the ctypes stub a
+ * maintainer would add to demethify/deconvolution.py to bind it.
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers + sizes, caller owns every buffer (allocate with torch / cudaMalloc),
+ *     no ownership transfer, every function returns 0 on success or a DMF_E_* code
+ *     (text via dmf_last_error()).  All matrices row-major.  All base pointers 16-byte aligned.
+ *   - stream arguments are cudaStream_t passed as void* (0 = legacy default stream).
+ *   - a "batch" is a set of independent fits of identical shape (M,N,K,n_u): bootstrap resamples,
+ *     restarts, BCV folds (bootstrap.py:26, demethify.py:167-203, ic.py:67).  The n_u sweep of
+ *     ic.py:192 is one batch per n_u.  Fits never exchange data; each owns its U, alpha and state.
+ *   - floating-point reductions over CpG rows are fp64 with a fixed order (run-to-run deterministic for
+ *     a given grid), so the |cf - cf_0| < tol test of deconvolution.py:220 is reproducible.
+ */
+#ifndef DEMETHIFY_B200_H
+#define DEMETHIFY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMF_ABI_VERSION 1
+
+enum { DMF_OK = 0, DMF_E_ARG = 1, DMF_E_CUDA = 2, DMF_E_SHAPE = 3, DMF_E_STATE = 4 };
+
+/* arithmetic/storage type of X, Rk, U, alpha */
+enum { DMF_F64 = 0, DMF_F32 = 1 };
+/* storage of the coverage weights d_x: same float type as X, or narrow unsigned integers
+ * (exact for integer coverage) */
+enum { DMF_W_FLOAT = 0, DMF_W_U16 = 1 };
+/* solver variant */
+enum {
+    DMF_MODE_PARTIAL = 0,      /* mdwbssmf_deconv      deconvolution.py:190-223 */
+    DMF_MODE_PURITY = 1,       /* mdwbssmf_deconv_p    deconvolution.py:305-337 */
+    DMF_MODE_UNSUPERVISED = 2  /* unsupervised_deconv  deconvolution.py:107-184 (K = 0; U-gradient at u, :163) */
+};
+
+typedef struct dmf_shape {
+    int64_t M;      /* CpG rows                         */
+    int32_t N;      /* samples                          */
+    int32_t K;      /* known cell types (0 allowed)     */
+    int32_t n_u;    /* unknown cell types (>= 1)        */
+    int32_t dtype;  /* DMF_F64 | DMF_F32                */
+    int32_t wtype;  /* DMF_W_FLOAT | DMF_W_U16          */
+    int32_t mode;   /* DMF_MODE_*                       */
+    int32_t n_fits; /* fits in the batch                */
+    int32_t max_ctas_per_fit; /* 0 = let the library choose (multiple of the SM count overall) */
+    int64_t ldx;    /* row pitch of X  in elements (>= N) */
+    int64_t ldd;    /* row pitch of D  in elements (>= N) */
+    int64_t ldr;    /* row pitch of Rk in elements (>= K) */
+    int64_t u_slot; /* elements between the two ping-pong slots of U (>= M*n_u, u_slot*sizeof(T) % 16 == 0) */
+} dmf_shape_t;
+
+/* Per-fit buffers (host array of n_fits of these is passed to dmf_batch_create). */
+typedef struct dmf_fit_desc {
+    const void* X;         /* M x N   methylation frequencies (meth_frequency)                 */
+    const void* D;         /* M x N   coverage weights d_x                                      */
+    const void* Rk;        /* M x K   known reference profiles R_trunc (NULL when K = 0)        */
+    const int32_t* rows;   /* optional gather: fit row p reads source row rows[p] of X, D, Rk
+                              (bootstrap.py:28 resample); NULL = identity.  U stays position-indexed */
+    void* U;               /* two slots of M x n_u, shape.u_slot elements apart; BOTH hold the initial u */
+    void* A;               /* [2][Kt][N]; BOTH slots hold the initial alpha (alpha_ = alpha.copy())    */
+    const double* purity;  /* [N] internal purity vector (DMF_MODE_PURITY) else NULL            */
+    double* cost_trace;    /* optional [trace_cap] cost after every outer iteration, or NULL    */
+    int32_t trace_cap;
+    int32_t reserved;
+} dmf_fit_desc_t;
+
+/* Per-fit result block, filled by dmf_batch_read_state (host memory). */
+typedef struct dmf_fit_state {
+    double cost;       /* cost_f_w at the returned iterate                           */
+    double cost_prev;
+    double l_w, l_h;   /* current step constants (deconvolution.py:198-201,212,216)  */
+    double a1, a2;     /* extrapolation scalars (deconvolution.py:84,96)              */
+    double dmax;       /* max d_x over the fit's rows                                 */
+    int32_t n_outer;   /* outer iterations executed                                   */
+    int32_t done;      /* 1 once |cf-cf_0| < tol fired                                */
+    int32_t u_slot;    /* which slot of U / A holds the current iterate               */
+    int32_t a_slot;
+} dmf_fit_state_t;
+
+typedef struct dmf_handle_s* dmf_handle_t;
+typedef struct dmf_batch_s* dmf_batch_t;
+
+/* library / device ----------------------------------------------------------------------------- */
+int dmf_abi_version(void);
+const char* dmf_last_error(void);
+int dmf_create(int device, dmf_handle_t* out);
+int dmf_destroy(dmf_handle_t h);
+int dmf_sm_count(dmf_handle_t h, int* out);
+
+/* batch set-up --------------------------------------------------------------------------------- */
+/* bytes of device workspace a batch of this shape needs (partials, tickets, per-fit state) */
+int dmf_batch_workspace_bytes(dmf_handle_t h, const dmf_shape_t* shape, size_t* bytes);
+int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_desc_t* fits_host,
+                     void* workspace_dev, size_t workspace_bytes, void* stream, dmf_batch_t* out);
+int dmf_batch_destroy(dmf_batch_t b);
+/* launch geometry chosen for the batch (for roofline accounting) */
+int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows, int32_t* smem_bytes);
+
+/* reference-shaped single steps: ONE launch each, all live fits of the batch -------------------- */
+/* cost_f_w + ||R||_F^2 + max d_x, initialises l_w, l_h, cf (deconvolution.py:192-204 / :308-318) */
+int dmf_pass_init(dmf_batch_t b, void* stream);
+/* one inner iteration of update_u (deconvolution.py:82-89) */
+int dmf_pass_u(dmf_batch_t b, void* stream);
+/* one inner iteration of update_alpha incl. projection_simplex_sort_2d (deconvolution.py:94-101, :21-37) */
+int dmf_pass_alpha(dmf_batch_t b, void* stream);
+/* one Frank-Wolfe iteration k of frank_wolfe_nmf (deconvolution.py:285-299) */
+int dmf_pass_fw(dmf_batch_t b, int32_t k_inner, void* stream);
+/* cost_f_w + termination test |cf - cf_0| < tol (deconvolution.py:218-221) */
+int dmf_pass_cost(dmf_batch_t b, double tol, void* stream);
+
+/* whole loops --------------------------------------------------------------------------------- */
+/* enqueue n_outer outer iterations (n_iter2 U steps, n_iter2 alpha/FW steps, cost) without host sync;
+ * fits that reach termination skip their remaining launches on the device. */
+int dmf_enqueue_outer(dmf_batch_t b, int32_t n_outer, int32_t n_iter2, double tol, void* stream);
+/* mdwbssmf_deconv / mdwbssmf_deconv_p / unsupervised_deconv for every fit of the batch: init pass,
+ * then outer iterations until every fit terminated or n_iter1 is reached.  Blocks the calling thread. */
+int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol, void* stream);
+/* copy per-fit state to host (synchronises the stream) */
+int dmf_batch_read_state(dmf_batch_t b, dmf_fit_state_t* out_host, int32_t n, void* stream);
+/* number of kernel launches issued through this batch since creation */
+int dmf_batch_launch_count(dmf_batch_t b, int64_t* out);
+
+/* utilities ------------------------------------------------------------------------------------ */
+/* narrow fp64/fp32/int64 coverage to u16 with range/integrality check; *bad receives the number of
+ * entries that are not integers in [0, 65535] (device int32) */
+int dmf_pack_weights_u16(const void* src, int32_t src_kind /*0 f64, 1 f32, 2 i64*/, int64_t count,
+                         uint16_t* dst, int32_t* bad_dev, void* stream);
+/* dst[p, :] = src[rows[p], :] row gather (sklearn.utils.resample, bootstrap.py:28), elem_bytes in {1,2,4,8} */
+int dmf_gather_rows(const void* src, const int32_t* rows, int64_t n_rows, int64_t row_elems,
+                    int32_t elem_bytes, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMETHIFY_B200_H */
