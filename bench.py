@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=M_FULL, help="override M (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--profile", action="store_true", help="resident arm only (for runs under ncu): no e2e, no CPU leg")
     return ap.parse_args()
 
 
@@ -241,6 +242,10 @@ def run_b200(args, rank, world, local_rank):
     st = batch.states()[0]
     assert st.n_outer == (args.warmup + args.steps) * OUTER_PER_STEP and np.isfinite(st.cost)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_u": t_u, "ms_alpha": t_a, "ms_cost": t_c}))
+        return
     # ---- end-to-end arm: public API, host buffers in, host arrays out
     nX, nD, nR, nU, nA = hX.numpy(), hD.numpy(), hR.numpy(), hU.numpy(), hA.numpy()
     batch.close()
