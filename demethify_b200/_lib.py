@@ -17,7 +17,7 @@ DMF_MODE_PARTIAL, DMF_MODE_PURITY, DMF_MODE_UNSUPERVISED = 0, 1, 2
 class Shape(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("n_u", C.c_int32), ("dtype", C.c_int32),
                 ("wtype", C.c_int32), ("mode", C.c_int32), ("n_fits", C.c_int32), ("max_ctas_per_fit", C.c_int32),
-                ("ldx", C.c_int64), ("ldd", C.c_int64), ("ldr", C.c_int64), ("u_slot", C.c_int64)]
+                ("ldx", C.c_int64), ("ldd", C.c_int64), ("ldr", C.c_int64), ("ldu", C.c_int64), ("u_slot", C.c_int64)]
 
 
 class FitDesc(C.Structure):

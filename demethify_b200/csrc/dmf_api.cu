@@ -41,9 +41,8 @@ struct dmf_batch_s {
     Geom g;
     FitDev* fits_dev;       // in workspace
     FitState* states_dev;   // in workspace, contiguous [n_fits]
-    int ktb, nub;           // register-tile buckets
-    int c_alpha, c_u;       // columns per thread in the alpha/cost and U kernels
-    int ntc_alpha, ntc_u;
+    int ktb, c_alpha, ntc_alpha;      // alpha / cost kernels
+    int kb, nub, c_u, ntc_u;          // U kernel
     unsigned smem_alpha, smem_u, smem_cost;
     int occ;
     long long launches;
@@ -67,11 +66,17 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // ---------------------------------------------------------------------------------------------
 // Geometry.  One stage of the ring holds tile_rows rows of every streamed matrix with the global pitch.
 struct Plan {
-    int ktb, nub, c_alpha, c_u, ntc_alpha, ntc_u;
+    int ktb, c_alpha, ntc_alpha;          // alpha / cost kernels: register-row bucket, columns per thread
+    int kb, nub, c_u, rpt_max, ntc_u;     // U kernel buckets
+    int Kp, nup, rpt;
     int tile_rows, n_tiles, n_parts, n_groups, part_stride, occ;
     unsigned offX, offD, offR, offU, offUp, stage_bytes, smem_alpha, smem_u, smem_cost, row_bulk;
     size_t ws_bytes, off_fits, off_states, off_tickets, off_part, off_gpart, per_fit_tickets, per_fit_part, per_fit_gpart;
 };
+
+// U-pass instantiations (dmf_inst_body.cuh): known bucket, unknown bucket, columns/thread, rows/thread/tile
+struct UEntry { int kb, nub, c, rpt; };
+const UEntry kUTable[] = {{6, 2, 2, 4}, {8, 2, 2, 4}, {8, 8, 2, 1}, {16, 2, 2, 4}, {16, 8, 2, 1}, {16, 16, 1, 1}, {32, 2, 1, 4}, {32, 8, 1, 1}, {32, 32, 1, 1}};
 
 int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     if (s.M <= 0 || s.N <= 0 || s.K < 0 || s.n_u <= 0 || s.n_fits <= 0) return fail(DMF_E_SHAPE, "M, N, n_u, n_fits must be positive and K >= 0");
@@ -79,44 +84,54 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     if (s.mode == DMF_MODE_PURITY && s.K == 0) return fail(DMF_E_SHAPE, "purity mode requires K >= 1");
     if (s.dtype != DMF_F64 && s.dtype != DMF_F32) return fail(DMF_E_ARG, "dtype must be DMF_F64 or DMF_F32");
     if (s.wtype != DMF_W_FLOAT && s.wtype != DMF_W_U16) return fail(DMF_E_ARG, "wtype must be DMF_W_FLOAT or DMF_W_U16");
-    if (s.ldx < s.N || s.ldd < s.N || (s.K && s.ldr < s.K)) return fail(DMF_E_SHAPE, "row pitch smaller than the row");
-    const int Kt = s.K + s.n_u;
-    if (s.u_slot < s.M * s.n_u || (s.u_slot * (s.dtype == DMF_F64 ? 8 : 4)) % 16) return fail(DMF_E_SHAPE, "u_slot must be >= M*n_u and a multiple of 16 bytes");
-    if (Kt > kMaxKt) return fail(DMF_E_SHAPE, "K + n_u > 32 is not supported by this build");
-    p.ktb = Kt <= 8 ? 8 : (Kt <= 16 ? 16 : 32);
-    p.nub = s.n_u <= 2 ? 2 : (s.n_u <= 8 ? 8 : (s.n_u <= 16 && p.ktb == 16 ? 16 : 32));
-    if (p.nub > p.ktb) p.nub = p.ktb;
-    if (p.ktb == 8 && p.nub > 8) p.nub = 8;
-    // columns per thread: as few as the register budget allows, more when N needs it
-    const int c_min = (s.N + kConsumers - 1) / kConsumers;
-    if (p.ktb == 8) { p.c_alpha = c_min <= 2 ? 2 : 4; p.c_u = c_min <= 2 ? 2 : 4; }
-    else if (p.ktb == 16) { p.c_alpha = c_min <= 1 ? 1 : 2; p.c_u = c_min <= 1 ? 1 : 2; }
-    else { p.c_alpha = 1; p.c_u = 1; }
-    if (c_min > p.c_alpha) return fail(DMF_E_SHAPE, "N too large for this K + n_u in this build (N <= 1024 / 512 / 256 for Kt <= 8 / 16 / 32)");
-    p.ntc_alpha = next_pow2((s.N + p.c_alpha - 1) / p.c_alpha);
-    p.ntc_u = next_pow2((s.N + p.c_u - 1) / p.c_u);
-
+    p.Kp = s.K + (s.K & 1);
+    p.nup = s.n_u + (s.n_u & 1);
+    if (s.ldx < s.N || s.ldd < s.N || s.ldr < p.Kp || s.ldu < p.nup) return fail(DMF_E_SHAPE, "row pitch smaller than the (even-padded) row");
+    if ((s.ldx | s.ldd | s.ldu | (s.K ? s.ldr : 0)) & 1) return fail(DMF_E_SHAPE, "row pitches must be even (zero padded)");
     const size_t sT = s.dtype == DMF_F64 ? 8 : 4;
     const size_t sW = s.wtype == DMF_W_U16 ? 2 : sT;
-    const size_t px = s.ldx * sT, pd = s.ldd * sW, pr = s.K ? s.ldr * sT : 0, pu = (size_t)s.n_u * sT;
+    if (s.u_slot < s.M * s.ldu || (s.u_slot * sT) % 16) return fail(DMF_E_SHAPE, "u_slot must be >= M*ldu and a multiple of 16 bytes");
+    const int Kt = s.K + s.n_u;
+    const int rowlen = p.Kp + p.nup;
+    if (rowlen > kMaxKt || Kt > kMaxKt) return fail(DMF_E_SHAPE, "K + n_u (even padded) > 32 is not supported by this build");
+    p.ktb = rowlen <= 8 ? 8 : (rowlen <= 16 ? 16 : 32);
+    p.c_alpha = p.ktb <= 16 ? 2 : 1;
+    const UEntry* ue = nullptr;
+    for (const UEntry& e : kUTable)
+        if (e.kb >= p.Kp && e.nub >= p.nup) { ue = &e; break; }
+    if (!ue) return fail(DMF_E_SHAPE, "no U-pass instantiation for this K / n_u");
+    p.kb = ue->kb; p.nub = ue->nub; p.c_u = ue->c; p.rpt_max = ue->rpt;
+    if (s.N > kConsumers * p.c_alpha || s.N > kConsumers * p.c_u)
+        return fail(DMF_E_SHAPE, "N too large for this K + n_u in this build (N <= 512 for small K + n_u, <= 256 otherwise)");
+    p.ntc_alpha = next_pow2((s.N + p.c_alpha - 1) / p.c_alpha);
+    p.ntc_u = next_pow2((s.N + p.c_u - 1) / p.c_u);
+    const int rg_u = kConsumers / p.ntc_u;
+
+    const size_t px = s.ldx * sT, pd = s.ldd * sW, pr = s.K ? s.ldr * sT : 0, pu = (size_t)s.ldu * sT;
     // smallest row multiple that keeps every tile start 16-byte aligned
     int ra = 1;
     while (ra < 16 && ((ra * px) % 16 || (ra * pd) % 16 || (ra * pr) % 16 || (ra * pu) % 16)) ra <<= 1;
     const size_t row_bytes = px + pd + pr + 2 * pu;
-    p.occ = (p.ktb == 8) ? 2 : 1;
     const size_t smem_cap = (size_t)h->max_smem_optin;
-    const size_t budget = (p.occ == 2 ? std::min<size_t>(smem_cap, 110 * 1024) : std::min<size_t>(smem_cap, 200 * 1024)) - kCtlBytes - 8192;
-    const size_t stage_target = budget / kStages;
-    long long tr = (long long)(stage_target / row_bytes) / ra * ra;
-    if (tr < ra) {
-        // a single row group does not fit twice per SM: fall back to one CTA per SM
-        p.occ = 1;
-        const size_t b1 = std::min<size_t>(smem_cap, 200 * 1024) - kCtlBytes - 8192;
-        tr = (long long)(b1 / kStages / row_bytes) / ra * ra;
-        if (tr < ra) return fail(DMF_E_SHAPE, "one row tile does not fit in shared memory (N too large)");
+    p.occ = (p.ktb <= 8 && ((p.kb + 2 * p.nub) * p.c_u <= 24)) ? 2 : 1;   // must mirror the __launch_bounds__ of the kernels
+    auto stage_of = [&](long long tr) {
+        auto a128 = [](size_t v) { return align_up(v, 128); };
+        return a128(tr * px) + a128(tr * pd) + a128(tr * pr) + 2 * a128(tr * pu);
+    };
+    p.rpt = 0;
+    for (int attempt = 0; attempt < 2 && !p.rpt; ++attempt) {
+        const size_t budget = (p.occ == 2 ? std::min<size_t>(smem_cap, 112 * 1024) : std::min<size_t>(smem_cap, 220 * 1024)) - kCtlBytes - 4096;
+        for (int rpt = p.rpt_max; rpt >= 1; rpt >>= 1) {
+            const long long tr = (long long)rpt * rg_u;
+            if (tr % ra) continue;
+            if (stage_of(tr) * kStages + (size_t)2 * tr * s.n_u * ((p.ntc_u + 31) / 32) * 8 <= budget) { p.rpt = rpt; break; }
+        }
+        if (!p.rpt) {
+            if (p.occ == 2) p.occ = 1; else break;
+        }
     }
-    tr = std::min<long long>(tr, 512);
-    tr = std::min<long long>(tr, (long long)align_up((size_t)s.M, ra));
+    if (!p.rpt) return fail(DMF_E_SHAPE, "one row tile does not fit in shared memory (or pitches force an unsupported tile alignment)");
+    const long long tr = (long long)p.rpt * rg_u;
     p.tile_rows = (int)tr;
     p.n_tiles = (int)((s.M + tr - 1) / tr);
     auto a128 = [](size_t v) { return (unsigned)align_up(v, 128); };
@@ -181,9 +196,9 @@ int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_in
     return DMF_OK;
 }
 
-kern_t k_cost(dmf_batch_s* b) { return by_types(b->shape, g_cost, b->ktb, 0, b->c_alpha); }
+kern_t k_cost(dmf_batch_s* b, int initial) { return by_types(b->shape, g_cost, b->ktb, initial, b->c_alpha); }
 kern_t k_alpha(dmf_batch_s* b) { return by_types(b->shape, g_alpha, b->ktb, 0, b->c_alpha); }
-kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->ktb, b->nub, b->c_u); }
+kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->kb, b->nub, b->c_u); }
 
 // ---------------------------------------------------------------------------------------------
 // small utility kernels
@@ -306,19 +321,28 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->pinned = nullptr;
     Geom& g = b->g;
     g.M = s.M; g.N = s.N; g.K = s.K; g.nu = s.n_u; g.Kt = s.K + s.n_u;
-    g.ldx = s.ldx; g.ldd = s.ldd; g.ldr = s.K ? s.ldr : 0;
+    g.ldx = s.ldx; g.ldd = s.ldd; g.ldr = s.K ? s.ldr : 0; g.ldu = s.ldu;
+    g.Kp = p.Kp; g.nup = p.nup; g.rpt = p.rpt;
     g.uslot_bytes = s.u_slot * (s.dtype == DMF_F64 ? 8 : 4);
     g.tile_rows = p.tile_rows; g.n_tiles = p.n_tiles;
     g.ntc = p.ntc_alpha; g.rg = kConsumers / p.ntc_alpha;
     g.n_parts = p.n_parts; g.n_groups = p.n_groups; g.part_stride = p.part_stride;
     g.offX = p.offX; g.offD = p.offD; g.offR = p.offR; g.offU = p.offU; g.offUp = p.offUp; g.stage_bytes = p.stage_bytes;
     g.row_bulk = p.row_bulk; g.mode = s.mode; g.gather = gather ? 1 : 0;
-    b->ktb = p.ktb; b->nub = p.nub; b->c_alpha = p.c_alpha; b->c_u = p.c_u;
+    {
+        const unsigned sT = s.dtype == DMF_F64 ? 8 : 4, sW = s.wtype == DMF_W_U16 ? 2 : sT;
+        g.tile_tx[0] = (unsigned)(p.tile_rows * s.ldx * sT);
+        g.tile_tx[1] = (unsigned)(p.tile_rows * s.ldd * sW);
+        g.tile_tx[2] = s.K ? (unsigned)(p.tile_rows * s.ldr * sT) : 0u;
+        g.tile_tx[3] = g.tile_tx[4] = (unsigned)(p.tile_rows * s.ldu * sT);
+    }
+    b->ktb = p.ktb; b->c_alpha = p.c_alpha; b->kb = p.kb; b->nub = p.nub; b->c_u = p.c_u;
     b->ntc_alpha = p.ntc_alpha; b->ntc_u = p.ntc_u;
     b->smem_alpha = p.smem_alpha; b->smem_u = p.smem_u; b->smem_cost = p.smem_cost; b->occ = p.occ;
     b->fits_dev = reinterpret_cast<FitDev*>(base + p.off_fits);
     b->states_dev = reinterpret_cast<FitState*>(base + p.off_states);
-    if ((rc = set_smem(k_cost(b), b->smem_cost)) || (rc = set_smem(k_alpha(b), b->smem_alpha)) || (rc = set_smem(k_u(b), b->smem_u))) {
+    if ((rc = set_smem(k_cost(b, 0), b->smem_cost)) || (rc = set_smem(k_cost(b, 1), b->smem_cost)) || (rc = set_smem(k_alpha(b), b->smem_alpha)) ||
+        (rc = set_smem(k_u(b), b->smem_u))) {
         delete b;
         return rc;
     }
@@ -352,11 +376,11 @@ int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows,
 
 int dmf_pass_init(dmf_batch_t b, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
-    return launch(b, k_cost(b), b->ntc_alpha, b->smem_cost, kFlagInitial, 0, 0.0, (cudaStream_t)stream);
+    return launch(b, k_cost(b, 1), b->ntc_alpha, b->smem_cost, kFlagInitial, 0, 0.0, (cudaStream_t)stream);
 }
 int dmf_pass_cost(dmf_batch_t b, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
-    return launch(b, k_cost(b), b->ntc_alpha, b->smem_cost, 0, 0, tol, (cudaStream_t)stream);
+    return launch(b, k_cost(b, 0), b->ntc_alpha, b->smem_cost, 0, 0, tol, (cudaStream_t)stream);
 }
 int dmf_pass_u(dmf_batch_t b, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");

@@ -7,10 +7,11 @@
 
 namespace dmf {
 
-constexpr int kConsumers = 256;             // consumer threads per CTA (8 warps)
-constexpr int kThreads = kConsumers + 32;   // + one producer warp
+constexpr int kConsumers = 256;             // threads per CTA: 8 warps, all compute; warp 0 also feeds the TMA ring
+constexpr int kThreads = kConsumers;
 constexpr int kStages = 4;                  // smem ring depth
 constexpr int kGroup = 16;                  // CTAs per first-level reduction group
+constexpr int kMaxSrc = 5;                  // matrices streamed per stage: X, D, Rk, U, Uprev
 constexpr int kMaxKt = 32;                  // K + n_u supported by the register-tiled kernels
 
 // ------------------------------------------------------------------------------------------------
@@ -47,7 +48,9 @@ struct FitDev {
 struct Geom {
     long long M;
     int N, K, nu, Kt;
-    long long ldx, ldd, ldr;       // row pitches in elements
+    long long ldx, ldd, ldr, ldu;  // row pitches in elements (all even, zero padded)
+    int Kp, nup;                   // K and n_u rounded up to even: columns actually loaded
+    int rpt;                       // rows per thread per tile in the U pass (tile_rows = rpt * rows-groups)
     long long uslot_bytes;         // bytes between the two U slots
     int tile_rows, n_tiles;
     int ntc, rg;                   // threads per row (power of two), row groups per CTA
@@ -55,6 +58,7 @@ struct Geom {
     int part_stride;               // doubles per partial record
     unsigned offX, offD, offR, offU, offUp, stage_bytes;   // smem stage layout (bytes)
     unsigned row_bulk;             // bit0 X, bit1 D, bit2 Rk: per-row bulk copies legal in gather mode
+    unsigned tile_tx[kMaxSrc];     // bytes of one FULL tile of X, D, Rk, U, Uprev (each a multiple of 16)
     int mode;                      // DMF_MODE_*
     int gather;                    // any fit uses a row index
 };
@@ -71,13 +75,22 @@ struct PassArgs {
 constexpr int kFlagInitial = 1;   // init_cost_kernel: set-up pass (norms, max d, no termination test)
 constexpr int kFlagFW = 2;        // alpha_pass_kernel: Frank-Wolfe step instead of projected gradient
 
+struct TileSrc {
+    const char* base;      // global base of the matrix (fit-specific), nullptr = absent
+    long long pitch;       // bytes per row
+    unsigned off;          // offset inside the stage
+    unsigned char gathered;   // rows come through the fit's row index
+    unsigned char row_bulk;   // per-row bulk copy legal (pitch % 16 == 0)
+    unsigned short pad;
+};
 struct SmemCtl {
     unsigned long long full[kStages];
     unsigned long long empty[kStages];
+    TileSrc src[kMaxSrc];   // what one stage is made of (written once by thread 0)
     int flag;
     int pad;
 };
-constexpr unsigned kCtlBytes = 128;
+constexpr unsigned kCtlBytes = 256;
 static_assert(sizeof(SmemCtl) <= kCtlBytes, "control block too large");
 
 // ------------------------------------------------------------------------------------------------
@@ -124,13 +137,6 @@ __device__ __forceinline__ T wload(const void* base, long long idx) {
 
 // ------------------------------------------------------------------------------------------------
 // Tile pipeline.  One stage holds `tile_rows` rows of X, D, Rk, U(cur) and optionally U(prev).
-struct TileSrc {
-    const char* base;      // global base of the matrix (fit-specific)
-    long long pitch;       // bytes per row
-    unsigned off;          // offset inside the stage
-    bool gathered;         // rows come through the fit's row index
-    bool row_bulk;         // per-row bulk copy legal (pitch % 16 == 0)
-};
 
 // Executed by the whole producer warp.  Fills stage `sbase` with rows [r0, r0+nrows) of every source
 // and arms `full_bar` with the number of bytes that will arrive asynchronously.
@@ -183,6 +189,23 @@ __device__ __forceinline__ void produce_tile(const TileSrc* src, int nsrc, const
             }
         }
     }
+}
+
+// Full, contiguous tile: every source is ONE bulk copy whose size was fixed on the host; only lane 0 works.
+__device__ __forceinline__ void produce_full_tile(const Geom& g, const TileSrc* src, int nsrc, long long r0, char* sbase,
+                                                  uint32_t full_bar, int lane) {
+    if (lane == 0) {
+        unsigned tx = 0;
+#pragma unroll
+        for (int s = 0; s < kMaxSrc; ++s)
+            if (s < nsrc && src[s].base != nullptr) tx += g.tile_tx[s];
+        mbar_arrive_expect_tx(full_bar, tx);
+        const uint32_t dst = smem_u32(sbase);
+#pragma unroll
+        for (int s = 0; s < kMaxSrc; ++s)
+            if (s < nsrc && src[s].base != nullptr) bulk_g2s(dst + src[s].off, src[s].base + r0 * src[s].pitch, g.tile_tx[s], full_bar);
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -4,28 +4,27 @@
 namespace dmf {
 #define DMF_CAT2(a, b) a##b
 #define DMF_CAT(a, b) DMF_CAT2(a, b)
-kern_t DMF_CAT(pick_cost_, DMF_TAG)(int ktb, int, int c) {
-    if (ktb == 8 && c == 2) return init_cost_kernel<DMF_T, DMF_WT, 8, 2>;
-    if (ktb == 8 && c == 4) return init_cost_kernel<DMF_T, DMF_WT, 8, 4>;
-    if (ktb == 16 && c == 1) return init_cost_kernel<DMF_T, DMF_WT, 16, 1>;
-    if (ktb == 16 && c == 2) return init_cost_kernel<DMF_T, DMF_WT, 16, 2>;
-    if (ktb == 32 && c == 1) return init_cost_kernel<DMF_T, DMF_WT, 32, 1>;
+// cost / set-up pass: (register-row bucket, columns per thread)
+kern_t DMF_CAT(pick_cost_, DMF_TAG)(int ktb, int initial, int c) {
+#define DMF_C(KTB_, C_)                                                                              \
+    if (ktb == KTB_ && c == C_)                                                                      \
+        return initial ? (kern_t)cost_kernel<DMF_T, DMF_WT, KTB_, C_, true> : (kern_t)cost_kernel<DMF_T, DMF_WT, KTB_, C_, false>;
+    DMF_C(8, 2) DMF_C(16, 2) DMF_C(32, 1)
+#undef DMF_C
     return nullptr;
 }
 kern_t DMF_CAT(pick_alpha_, DMF_TAG)(int ktb, int, int c) {
     if (ktb == 8 && c == 2) return alpha_pass_kernel<DMF_T, DMF_WT, 8, 2>;
-    if (ktb == 8 && c == 4) return alpha_pass_kernel<DMF_T, DMF_WT, 8, 4>;
-    if (ktb == 16 && c == 1) return alpha_pass_kernel<DMF_T, DMF_WT, 16, 1>;
     if (ktb == 16 && c == 2) return alpha_pass_kernel<DMF_T, DMF_WT, 16, 2>;
     if (ktb == 32 && c == 1) return alpha_pass_kernel<DMF_T, DMF_WT, 32, 1>;
     return nullptr;
 }
-kern_t DMF_CAT(pick_u_, DMF_TAG)(int ktb, int nub, int c) {
-#define DMF_U(KTB_, NUB_, C_) \
-    if (ktb == KTB_ && nub == NUB_ && c == C_) return u_pass_kernel<DMF_T, DMF_WT, KTB_, NUB_, C_>;
-    DMF_U(8, 2, 2) DMF_U(8, 2, 4) DMF_U(8, 8, 2) DMF_U(8, 8, 4)
-    DMF_U(16, 2, 1) DMF_U(16, 2, 2) DMF_U(16, 8, 1) DMF_U(16, 8, 2) DMF_U(16, 16, 1) DMF_U(16, 16, 2)
-    DMF_U(32, 2, 1) DMF_U(32, 8, 1) DMF_U(32, 32, 1)
+// U pass: (known bucket, unknown bucket) -> fixed (columns per thread, rows per thread per tile); see kUTable in dmf_api.cu
+kern_t DMF_CAT(pick_u_, DMF_TAG)(int kb, int nub, int) {
+#define DMF_U(KB_, NUB_, C_, RPT_) \
+    if (kb == KB_ && nub == NUB_) return u_pass_kernel<DMF_T, DMF_WT, KB_, NUB_, C_, RPT_>;
+    DMF_U(6, 2, 2, 4) DMF_U(8, 2, 2, 4) DMF_U(8, 8, 2, 1) DMF_U(16, 2, 2, 4) DMF_U(16, 8, 2, 1) DMF_U(16, 16, 1, 1)
+    DMF_U(32, 2, 1, 4) DMF_U(32, 8, 1, 1) DMF_U(32, 32, 1, 1)
 #undef DMF_U
     return nullptr;
 }

@@ -1,18 +1,20 @@
 // dmf_kernels.cuh — reference-shaped streaming passes over the tall CpG dimension.
 //
 // Every kernel is ONE launch = one reference step for all live fits of a batch (grid.y = fit):
-//   init_cost_kernel : cost_f_w (+ ||R||^2, max d_x at set-up)        deconvolution.py:15-17, 192-204, 218-221
+//   cost_kernel      : cost_f_w (+ ||R||^2, max d_x at set-up)        deconvolution.py:15-17, 192-204, 218-221
 //   u_pass_kernel    : one inner iteration of update_u                deconvolution.py:82-89  (unsup. variant :157-164)
 //   alpha_pass_kernel: one inner iteration of update_alpha            deconvolution.py:94-101 + projection :21-37
 //                      or one Frank-Wolfe iteration                   deconvolution.py:285-299
 //
 // Layout: a producer warp streams row tiles of X, D, R_trunc, u (and u_prev) into a 4-stage shared-memory
 // ring with 1-D bulk copies (TMA engine) signalled through mbarriers; 256 consumer threads are arranged
-// as (row group g, column thread tc): thread tc owns C adjacent sample columns, keeps its alpha columns in
-// registers and walks the rows of the tile.  Row-wise sums (U gradient) use warp shuffles, column-wise
-// sums (alpha gradient) stay in registers across the whole CTA lifetime; cross-CTA sums go through the
-// deterministic two-level reduction of dmf_device.cuh and the LAST CTA applies the step (clip / simplex
-// projection / Frank-Wolfe vertex), updates the fit state and re-arms the tickets.
+// as (row group g, column thread tc): thread tc owns C adjacent sample columns (C = 2: every access is a
+// two-element vector load), keeps its alpha columns in registers and walks the rows of the tile.  All row
+// pitches are even and zero padded (ABI contract), so the inner loops are branch free.
+// Row-wise sums (U gradient) use a transposed warp-shuffle butterfly, column-wise sums (alpha gradient)
+// stay in registers across the whole CTA lifetime; cross-CTA sums go through the deterministic two-level
+// reduction of dmf_device.cuh and the LAST CTA applies the step (clip / simplex projection / Frank-Wolfe
+// vertex), updates the fit state and re-arms the tickets.
 #pragma once
 #include "dmf_device.cuh"
 
@@ -25,6 +27,58 @@ template <>
 __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 template <>
 __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+// ---- shared-memory loads through 32-bit shared addresses (explicit ld.shared: no 64-bit address math)
+__device__ __forceinline__ void lds2(uint32_t addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds2(uint32_t addr, float& a, float& b) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds1(uint32_t addr, double& a) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr)); }
+__device__ __forceinline__ void lds1(uint32_t addr, float& a) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(addr)); }
+// C adjacent elements (C = 1, 2, 4)
+template <typename T, int C>
+__device__ __forceinline__ void ldsC(uint32_t addr, T (&x)[C]) {
+    if (C == 1) lds1(addr, x[0]);
+    else {
+#pragma unroll
+        for (int i = 0; i < C / 2; ++i) lds2(addr + i * 2 * (uint32_t)sizeof(T), x[2 * i], x[(2 * i + 1) % C]);
+    }
+}
+// C adjacent weights, converted to T
+template <typename T, typename WT, int C>
+struct WLoad {   // WT == T
+    static __device__ __forceinline__ void ld(uint32_t addr, T (&d)[C]) { ldsC<T, C>(addr, d); }
+};
+template <typename T>
+struct WLoad<T, uint16_t, 1> {
+    static __device__ __forceinline__ void ld(uint32_t addr, T (&d)[1]) {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+        d[0] = (T)v;
+    }
+};
+template <typename T>
+struct WLoad<T, uint16_t, 2> {
+    static __device__ __forceinline__ void ld(uint32_t addr, T (&d)[2]) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        d[0] = (T)(v & 0xffffu);
+        d[1] = (T)(v >> 16);
+    }
+};
+template <typename T>
+struct WLoad<T, uint16_t, 4> {
+    static __device__ __forceinline__ void ld(uint32_t addr, T (&d)[4]) {
+        uint32_t v, w;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(w) : "r"(addr));
+        d[0] = (T)(v & 0xffffu);
+        d[1] = (T)(v >> 16);
+        d[2] = (T)(w & 0xffffu);
+        d[3] = (T)(w >> 16);
+    }
+};
 
 // sum of one double per consumer thread, fixed order; result valid in consumer thread 0
 __device__ __forceinline__ double consumer_block_sum(double v, double* scratch /* >= 8 doubles */, int ctid) {
@@ -54,17 +108,15 @@ __device__ __forceinline__ double consumer_block_max(double v, double* scratch, 
     return s;
 }
 
-// Common CTA set-up: barriers, tile sources.  Returns number of tiles this CTA owns.
+// Common CTA set-up: barriers and the tile share of this CTA.
 struct CtaCtx {
     SmemCtl* ctl;
-    char* stages;
     int n_my;
     int warp, lane, ctid;
 };
 
 __device__ __forceinline__ void cta_setup(const Geom& g, unsigned char* smem, CtaCtx& c) {
     c.ctl = reinterpret_cast<SmemCtl*>(smem);
-    c.stages = reinterpret_cast<char*>(smem) + kCtlBytes;
     c.warp = threadIdx.x >> 5;
     c.lane = threadIdx.x & 31;
     c.ctid = threadIdx.x;   // consumers are threads [0, kConsumers)
@@ -78,91 +130,130 @@ __device__ __forceinline__ void cta_setup(const Geom& g, unsigned char* smem, Ct
         }
         mbar_fence_init();
     }
-    __syncthreads();
 }
 
-__device__ __forceinline__ void producer_loop(const Geom& g, const FitDev& f, const CtaCtx& c, const TileSrc* src, int nsrc) {
-    for (int it = 0; it < c.n_my; ++it) {
-        const int s = it % kStages;
-        const unsigned n = (unsigned)(it / kStages);
-        mbar_wait(smem_u32(&c.ctl->empty[s]), (n & 1u) ^ 1u);
-        const long long tile = blockIdx.x + (long long)it * gridDim.x;
-        const long long r0 = tile * g.tile_rows;
-        const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
-        produce_tile(src, nsrc, f.rows, r0, nrows, c.stages + (size_t)s * g.stage_bytes, smem_u32(&c.ctl->full[s]), c.lane);
+// Producer duty is rotated over the warps (tile t is requested by warp t mod 8, between its own tiles), so no
+// single warp lags behind; kStages - 1 tiles stay in flight per CTA.
+__device__ __forceinline__ void produce_it(const Geom& g, const FitDev& f, const CtaCtx& c, unsigned char* stages, int nsrc, int it) {
+    if (it >= c.n_my || c.warp != (it & (kConsumers / 32 - 1))) return;
+    const int s = it % kStages;
+    const unsigned n = (unsigned)(it / kStages);
+    mbar_wait(smem_u32(&c.ctl->empty[s]), (n & 1u) ^ 1u);
+    const long long tile = blockIdx.x + (long long)it * gridDim.x;
+    const long long r0 = tile * g.tile_rows;
+    const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
+    char* sbase = reinterpret_cast<char*>(stages) + (size_t)s * g.stage_bytes;
+    if (nrows == g.tile_rows && f.rows == nullptr)
+        produce_full_tile(g, c.ctl->src, nsrc, r0, sbase, smem_u32(&c.ctl->full[s]), c.lane);
+    else
+        produce_tile(c.ctl->src, nsrc, f.rows, r0, nrows, sbase, smem_u32(&c.ctl->full[s]), c.lane);
+}
+
+// Register row [R_trunc row (Kp entries, zero padded) | u row (ldu entries, zero padded)] is fetched as
+// NCH two-element chunks; chunk i lives at  stage + off[i] + row * pitch[i].  Chunks beyond the real row
+// alias chunk 0 (their alpha rows are zero, so they contribute nothing).
+template <int NCH>
+struct ChunkMap {
+    unsigned off[NCH];
+    unsigned pitch[NCH];
+};
+template <typename T, int NCH>
+__device__ __forceinline__ void make_chunk_map(const Geom& g, ChunkMap<NCH>& m) {
+    const int nR = g.Kp >> 1, nU = (int)(g.ldu >> 1);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        if (i < nR) { m.off[i] = g.offR + i * 2 * (unsigned)sizeof(T); m.pitch[i] = (unsigned)(g.ldr * sizeof(T)); }
+        else if (i < nR + nU) { m.off[i] = g.offU + (i - nR) * 2 * (unsigned)sizeof(T); m.pitch[i] = (unsigned)(g.ldu * sizeof(T)); }
+        else if (nR > 0) { m.off[i] = g.offR; m.pitch[i] = (unsigned)(g.ldr * sizeof(T)); }
+        else { m.off[i] = g.offU; m.pitch[i] = (unsigned)(g.ldu * sizeof(T)); }
     }
+}
+// alpha row that register-row entry i multiplies (-1: padding)
+__device__ __forceinline__ int alpha_row_of(const Geom& g, int i) {
+    if (i < g.Kp) return i < g.K ? i : -1;
+    const int q = i - g.Kp;
+    return q < g.nu ? g.K + q : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
 // cost / set-up pass
-template <typename T, typename WT, int KTB, int C>
-__global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) init_cost_kernel(const PassArgs a) {
+template <typename T, typename WT, int KTB, int C, bool INITIAL>
+__global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(const PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NCH = KTB / 2;
     const Geom& g = a.g;
     const FitDev f = a.fits[blockIdx.y];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
     cta_setup(g, smem, c);
-    const bool initial = (a.flags & kFlagInitial) != 0;
+    unsigned char* stages = smem + kCtlBytes;
+    const uint32_t stages32 = smem_u32(stages);
     const int ucur = st->u_cur, acur = st->a_cur;
     const T* Acur = reinterpret_cast<const T*>(f.A) + (size_t)acur * g.Kt * g.N;
     const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
 
     double cost = 0.0, ssq_r = 0.0, ssq_u = 0.0, dmx = 0.0;
-    if (c.warp == kConsumers / 32) {
-        TileSrc src[4];
-        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, true, (g.row_bulk & 1u) != 0};
-        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, true, (g.row_bulk & 2u) != 0};
-        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, true, (g.row_bulk & 4u) != 0};
-        src[3] = {Ucur, g.nu * (long long)sizeof(T), g.offU, false, false};
-        producer_loop(g, f, c, src, 4);
-    } else {
+    constexpr int NSRC = 4;
+    if (threadIdx.x == 0) {
+        TileSrc* src = c.ctl->src;
+        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
+        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
+        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
+        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+    }
+    __syncthreads();
+    for (int it = 0; it < kStages - 1; ++it) produce_it(g, f, c, stages, NSRC, it);
+    {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
-        const int j0 = tc * C;
+        const bool colvalid = C * tc < g.N;
+        const int j0 = colvalid ? C * tc : 0;
         T at[KTB][C];
 #pragma unroll
-        for (int k = 0; k < KTB; ++k)
+        for (int k = 0; k < KTB; ++k) {
+            const int ar = alpha_row_of(g, k);
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) at[k][cc] = (k < g.Kt && j0 + cc < g.N) ? Acur[(size_t)k * g.N + j0 + cc] : (T)0;
+            for (int cc = 0; cc < C; ++cc) at[k][cc] = (ar >= 0 && j0 + cc < g.N) ? Acur[(size_t)ar * g.N + j0 + cc] : (T)0;
+        }
+        ChunkMap<NCH> cm;
+        make_chunk_map<T, NCH>(g, cm);
+        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
+        const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
         for (int it = 0; it < c.n_my; ++it) {
+            produce_it(g, f, c, stages, NSRC, it + kStages - 1);
             const int s = it % kStages;
             mbar_wait(smem_u32(&c.ctl->full[s]), (unsigned)(it / kStages) & 1u);
-            const char* sb = c.stages + (size_t)s * g.stage_bytes;
-            const T* sX = reinterpret_cast<const T*>(sb + g.offX);
-            const void* sD = sb + g.offD;
-            const T* sR = reinterpret_cast<const T*>(sb + g.offR);
-            const T* sU = reinterpret_cast<const T*>(sb + g.offU);
+            const uint32_t sb = stages32 + (uint32_t)s * g.stage_bytes;
             const long long r0 = (blockIdx.x + (long long)it * gridDim.x) * g.tile_rows;
             const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
-            for (int r = gr; r < nrows; r += g.rg) {
-                T rrow[KTB];
+            if (colvalid) {
+                for (int r = gr; r < nrows; r += g.rg) {
+                    T rrow[KTB];
 #pragma unroll
-                for (int k = 0; k < KTB; ++k) {
-                    T v = (T)0;
-                    if (k < g.K) v = sR[(size_t)r * g.ldr + k];
-                    else if (k < g.Kt) v = sU[r * g.nu + (k - g.K)];
-                    rrow[k] = v;
-                }
-                if (initial && tc == 0) {
+                    for (int i = 0; i < NCH; ++i) lds2(sb + cm.off[i] + r * cm.pitch[i], rrow[2 * i], rrow[2 * i + 1]);
+                    if (INITIAL && tc == 0) {
 #pragma unroll
-                    for (int k = 0; k < KTB; ++k) {
-                        const double v = (double)rrow[k];
-                        if (k < g.K) ssq_r = fma(v, v, ssq_r);
-                        else ssq_u = fma(v, v, ssq_u);
+                        for (int k = 0; k < KTB; ++k) {
+                            const double v = (double)rrow[k];
+                            const int ar = alpha_row_of(g, k);
+                            if (ar >= 0 && ar < g.K) ssq_r = fma(v, v, ssq_r);
+                            else if (ar >= g.K) ssq_u = fma(v, v, ssq_u);
+                        }
                     }
-                }
+                    T x[C], d[C], p[C];
+                    ldsC<T, C>(sb + xoff + r * xpitch, x);
+                    WLoad<T, WT, C>::ld(sb + doff + r * dpitch, d);
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) {
-                    if (j0 + cc < g.N) {
-                        const T x = sX[(size_t)r * g.ldx + j0 + cc];
-                        const T d = wload<T, WT>(sD, (long long)r * g.ldd + j0 + cc);
-                        T pred = (T)0;
+                    for (int cc = 0; cc < C; ++cc) p[cc] = (T)0;
 #pragma unroll
-                        for (int k = 0; k < KTB; ++k) pred = fma_t<T>(rrow[k], at[k][cc], pred);
-                        const double res = (double)(x - pred);
-                        cost = fma((double)d * res, res, cost);
-                        dmx = fmax(dmx, (double)d);
+                    for (int k = 0; k < KTB; ++k)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) p[cc] = fma_t<T>(rrow[k], at[k][cc], p[cc]);
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        const double e = (double)(x[cc] - p[cc]);
+                        cost = fma((double)d[cc] * e, e, cost);
+                        if (INITIAL) dmx = fmax(dmx, (double)d[cc]);
                     }
                 }
             }
@@ -172,13 +263,16 @@ __global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) init_cost_k
     }
     __syncthreads();
     // CTA partial record: [cost, ssq_rk, ssq_u, dmax]
-    double* scratch = reinterpret_cast<double*>(c.stages);
+    double* scratch = reinterpret_cast<double*>(stages);
     double* rec = scratch + 16;
     if (c.warp < kConsumers / 32) {
         const double s0 = consumer_block_sum(cost, scratch, c.ctid);
-        const double s1 = consumer_block_sum(ssq_r, scratch, c.ctid);
-        const double s2 = consumer_block_sum(ssq_u, scratch, c.ctid);
-        const double s3 = consumer_block_max(dmx, scratch, c.ctid);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (INITIAL) {
+            s1 = consumer_block_sum(ssq_r, scratch, c.ctid);
+            s2 = consumer_block_sum(ssq_u, scratch, c.ctid);
+            s3 = consumer_block_max(dmx, scratch, c.ctid);
+        }
         if (c.ctid == 0) {
             double* p = f.part + (size_t)blockIdx.x * g.part_stride;
             p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
@@ -188,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) init_cost_k
     if (!hier_reduce(g, f, rec, 3, &c.ctl->flag)) return;
     if (threadIdx.x == 0) {
         const double cf = rec[0];
-        if (initial) {
+        if (INITIAL) {
             double dm = 0.0;
             for (int p = 0; p < g.n_parts; ++p) dm = fmax(dm, __ldcg(&f.part[(size_t)p * g.part_stride + 3]));
             st->dmax = dm;
@@ -227,149 +321,206 @@ __global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) init_cost_k
 }
 
 // ------------------------------------------------------------------------------------------------
+// Segmented reduction of NV doubles per lane over aligned groups of L lanes (L power of two <= 32).
+// Transposed butterfly: while more than one value is left, each step halves the number of values a lane
+// carries (small offsets first), then plain xor-adds cover the remaining offsets.  Deterministic.
+// On return lane l holds the group totals of slots  slot_base + i,  i < count.
+template <int NV>
+__device__ __forceinline__ void seg_reduce(double (&v)[NV], int L, int lane, int& slot_base, int& count) {
+    int n = NV;
+    slot_base = 0;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int o = 1 << s;
+        if (o < L) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int half = NV >> (s + 1);          // compile-time: values kept when every earlier step ran
+            if (half >= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < (NV >> (s + 1)); ++i) {
+                    const double send = up ? v[i] : v[i + half];
+                    const double keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+                n = half;
+                slot_base += up ? half : 0;
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+            }
+        }
+    }
+    count = n;
+}
+
 // U pass: u <- clip(u_t + ((d o (x - Rk a_k - u_g a_u)) a_u^T) / l_w, 0, 1),  u_t = u + beta (u - u_prev)
 // (u_g = u_t in update_u:88, u_g = u in unsupervised_deconv:163)
-template <typename T, typename WT, int KTB, int NUB, int C>
-__global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) u_pass_kernel(const PassArgs a) {
+template <typename T, typename WT, int KB, int NUB, int C, int RPT>
+__global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) u_pass_kernel(const PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NV = RPT * NUB;
     const Geom& g = a.g;
     const FitDev f = a.fits[blockIdx.y];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
     cta_setup(g, smem, c);
+    unsigned char* stages = smem + kCtlBytes;
+    const uint32_t stages32 = smem_u32(stages);
     const int ucur = st->u_cur, acur = st->a_cur;
     const double a_prev = st->a1, l_w = st->l_w, l_w_old = st->l_w_old;
     const double a_next = next_momentum(a_prev);
     const T beta = (T)extrap_beta(a_prev, a_next, l_w_old, l_w);
     const T lw = (T)l_w;
     const T* Acur = reinterpret_cast<const T*>(f.A) + (size_t)acur * g.Kt * g.N;
-    const size_t uslot = (size_t)g.uslot_bytes;
-    const char* Ucur = f.U + (size_t)ucur * uslot;
-    char* Uprev = f.U + (size_t)(ucur ^ 1) * uslot;      // read as u_prev, overwritten with the new u
+    const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
+    char* Uprev = f.U + (size_t)(ucur ^ 1) * g.uslot_bytes;      // read as u_prev, overwritten with the new u
     const bool at_current = (g.mode == 2);
 
     double ssq_u = 0.0;
-    if (c.warp == kConsumers / 32) {
-        TileSrc src[5];
-        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, true, (g.row_bulk & 1u) != 0};
-        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, true, (g.row_bulk & 2u) != 0};
-        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, true, (g.row_bulk & 4u) != 0};
-        src[3] = {Ucur, g.nu * (long long)sizeof(T), g.offU, false, false};
-        src[4] = {Uprev, g.nu * (long long)sizeof(T), g.offUp, false, false};
-        producer_loop(g, f, c, src, 5);
-    } else {
+    constexpr int NSRC = 5;
+    if (threadIdx.x == 0) {
+        TileSrc* src = c.ctl->src;
+        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
+        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
+        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
+        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+        src[4] = {Uprev, g.ldu * (long long)sizeof(T), g.offUp, 0, 0, 0};
+    }
+    __syncthreads();
+    for (int it = 0; it < kStages - 1; ++it) produce_it(g, f, c, stages, NSRC, it);
+    {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
-        const int j0 = tc * C;
-        const int lanes_per_row = min(g.ntc, 32);
-        const int warps_per_row = (g.ntc + 31) / 32;
-        T at[KTB][C];    // all alpha rows of my columns (prediction)
-        T au[NUB][C];    // unknown block again (gradient), compile-time indexed
+        const bool colvalid = C * tc < g.N;
+        const int j0 = colvalid ? C * tc : 0;
+        const int L = min(g.ntc, 32);
+        const int wpr = (g.ntc + 31) / 32;           // warps per row
+        const int wir = tc >> 5;                      // my warp's index within the row
+        T ak[KB][C];     // known block of alpha, my columns
+        T au[NUB][C];    // unknown block (zero for padding columns: they add nothing to the row sums)
 #pragma unroll
-        for (int k = 0; k < KTB; ++k)
+        for (int k = 0; k < KB; ++k)
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) at[k][cc] = (k < g.Kt && j0 + cc < g.N) ? Acur[(size_t)k * g.N + j0 + cc] : (T)0;
+            for (int cc = 0; cc < C; ++cc) ak[k][cc] = (k < g.K && colvalid && j0 + cc < g.N) ? Acur[(size_t)k * g.N + j0 + cc] : (T)0;
 #pragma unroll
         for (int q = 0; q < NUB; ++q)
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) au[q][cc] = (q < g.nu && j0 + cc < g.N) ? Acur[(size_t)(g.K + q) * g.N + j0 + cc] : (T)0;
-        // cross-warp combine buffer (only when a row spans several warps): [2][tile_rows][warps_per_row][nu]
-        double* red = reinterpret_cast<double*>(c.stages + (size_t)kStages * g.stage_bytes);
-        const int rows_padded = ((g.tile_rows + g.rg - 1) / g.rg) * g.rg;
+            for (int cc = 0; cc < C; ++cc) au[q][cc] = (q < g.nu && colvalid && j0 + cc < g.N) ? Acur[(size_t)(g.K + q) * g.N + j0 + cc] : (T)0;
+        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
+        const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
+        const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
+        const int nRch = g.Kp >> 1, nUch = (int)(g.ldu >> 1);
+        // cross-warp combine buffer (rows spanning several warps): [2][tile_rows][nu][wpr]
+        double* red = reinterpret_cast<double*>(stages + (size_t)kStages * g.stage_bytes);
 
         for (int it = 0; it < c.n_my; ++it) {
+            produce_it(g, f, c, stages, NSRC, it + kStages - 1);
             const int s = it % kStages;
             mbar_wait(smem_u32(&c.ctl->full[s]), (unsigned)(it / kStages) & 1u);
-            const char* sb = c.stages + (size_t)s * g.stage_bytes;
-            const T* sX = reinterpret_cast<const T*>(sb + g.offX);
-            const void* sD = sb + g.offD;
-            const T* sR = reinterpret_cast<const T*>(sb + g.offR);
-            const T* sU = reinterpret_cast<const T*>(sb + g.offU);
-            const T* sUp = reinterpret_cast<const T*>(sb + g.offUp);
+            const uint32_t sb = stages32 + (uint32_t)s * g.stage_bytes;
             const long long r0 = (blockIdx.x + (long long)it * gridDim.x) * g.tile_rows;
             const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
-            double* redt = red + (size_t)(it & 1) * g.tile_rows * warps_per_row * g.nu;
-            T* Uout = reinterpret_cast<T*>(Uprev) + (size_t)r0 * g.nu;
+            double* redt = red + (size_t)(it & 1) * g.tile_rows * g.nu * wpr;
+            T* Uout = reinterpret_cast<T*>(Uprev) + (size_t)r0 * g.ldu;
 
-            for (int rb = 0; rb < rows_padded; rb += g.rg) {
-                const int r = rb + gr;
-                const bool live = r < nrows;
-                T rrow[KTB];     // [Rk row | u_g row]
-                T ut[NUB];
+            double gp[NV];
+            T utk[RPT][NUB];
+#pragma unroll
+            for (int rb = 0; rb < RPT; ++rb) {
+                const int r = gr + rb * g.rg;
+                const bool live = (rb < g.rpt) && (r < nrows);
+                const int rr = live ? r : 0;                      // dead rows recompute row 0; their slots are never stored
+                T rk[KB], ug[NUB];
+#pragma unroll
+                for (int i = 0; i < KB / 2; ++i) {
+                    const int ii = i < nRch ? i : 0;
+                    lds2(sb + g.offR + ii * 2 * (unsigned)sizeof(T) + rr * rpitch, rk[2 * i], rk[2 * i + 1]);
+                }
+#pragma unroll
+                for (int i = 0; i < NUB / 2; ++i) {
+                    const int ii = i < nUch ? i : 0;
+                    T u0, u1, p0, p1;
+                    lds2(sb + g.offU + ii * 2 * (unsigned)sizeof(T) + rr * upitch, u0, u1);
+                    lds2(sb + g.offUp + ii * 2 * (unsigned)sizeof(T) + rr * upitch, p0, p1);
+                    utk[rb][2 * i] = u0 + beta * (u0 - p0);
+                    utk[rb][2 * i + 1] = u1 + beta * (u1 - p1);
+                    ug[2 * i] = at_current ? u0 : utk[rb][2 * i];
+                    ug[2 * i + 1] = at_current ? u1 : utk[rb][2 * i + 1];
+                }
+                T x[C], d[C], pk[C], pu[C];
+                ldsC<T, C>(sb + xoff + rr * xpitch, x);
+                WLoad<T, WT, C>::ld(sb + doff + rr * dpitch, d);
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) pk[cc] = pu[cc] = (T)0;
+                if (g.K > 0) {
+#pragma unroll
+                    for (int k = 0; k < KB; ++k)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) pk[cc] = fma_t<T>(rk[k], ak[k][cc], pk[cc]);
+                }
+#pragma unroll
+                for (int q = 0; q < NUB; ++q)
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) pu[cc] = fma_t<T>(ug[q], au[q][cc], pu[cc]);
+                T w[C];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) w[cc] = d[cc] * ((x[cc] - pk[cc]) - pu[cc]);   // (X - R_trunc a_k) - u a_u, :88
 #pragma unroll
                 for (int q = 0; q < NUB; ++q) {
-                    T v = (T)0;
-                    if (live && q < g.nu) {
-                        const T u = sU[r * g.nu + q], up = sUp[r * g.nu + q];
-                        v = u + beta * (u - up);
-                    }
-                    ut[q] = v;
+                    T acc = w[0] * au[q][0];
+#pragma unroll
+                    for (int cc = 1; cc < C; ++cc) acc = fma_t<T>(w[cc], au[q][cc], acc);
+                    gp[rb * NUB + q] = (double)acc;
                 }
+            }
+            // row sums over the column threads
+            int slot_base, count;
+            seg_reduce<NV>(gp, L, c.lane, slot_base, count);
+            const bool owner = ((c.lane & (L - 1)) & ~(NV - 1)) == 0;     // lanes sharing a slot set: one writes
+            if (wpr == 1) {
 #pragma unroll
-                for (int k = 0; k < KTB; ++k) {
-                    T v = (T)0;
-                    if (live) {
-                        if (k < g.K) v = sR[(size_t)r * g.ldr + k];
-                        else if (k < g.Kt) v = at_current ? sU[r * g.nu + (k - g.K)] : (T)0;
-                    }
-                    rrow[k] = v;
-                }
-                T gp[NUB];
+                for (int i = 0; i < NV; ++i) {
+                    if (i < count) {
+                        const int slot = slot_base + i;
+                        const int rb = slot / NUB, q = slot - rb * NUB;
+                        const int r = gr + rb * g.rg;
+                        if (owner && rb < g.rpt && r < nrows && q < g.nu) {
+                            T utq = (T)0;
 #pragma unroll
-                for (int q = 0; q < NUB; ++q) gp[q] = (T)0;
+                            for (int b2 = 0; b2 < RPT; ++b2)
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) {
-                    if (live && j0 + cc < g.N) {
-                        const T x = sX[(size_t)r * g.ldx + j0 + cc];
-                        const T d = wload<T, WT>(sD, (long long)r * g.ldd + j0 + cc);
-                        T pk = (T)0;     // R_trunc @ alpha_known   (and u @ alpha_unk in the unsupervised variant)
-#pragma unroll
-                        for (int k = 0; k < KTB; ++k) pk = fma_t<T>(rrow[k], at[k][cc], pk);
-                        T res = x - pk;
-                        if (!at_current) {
-                            T pu = (T)0;  // u_temp @ alpha_unk
-#pragma unroll
-                            for (int q = 0; q < NUB; ++q) pu = fma_t<T>(ut[q], au[q][cc], pu);
-                            res = res - pu;
-                        }
-                        const T w = d * res;
-#pragma unroll
-                        for (int q = 0; q < NUB; ++q) gp[q] = fma_t<T>(w, au[q][cc], gp[q]);
-                    }
-                }
-                // row sum over the column threads of this row
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) {
-                    if (q < g.nu) {
-                        double v = (double)gp[q];
-                        for (int o = lanes_per_row >> 1; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        gp[q] = (T)v;
-                        if (warps_per_row > 1 && live && (c.lane == 0)) redt[((size_t)r * warps_per_row + (tc >> 5)) * g.nu + q] = v;
-                    }
-                }
-                if (warps_per_row == 1 && live && (tc == 0)) {
-#pragma unroll
-                    for (int q = 0; q < NUB; ++q) {
-                        if (q < g.nu) {
-                            T un = ut[q] + gp[q] / lw;
+                                for (int q2 = 0; q2 < NUB; ++q2)
+                                    if (b2 == rb && q2 == q) utq = utk[b2][q2];
+                            T un = utq + (T)gp[i] / lw;
                             un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
-                            Uout[(size_t)r * g.nu + q] = un;
+                            Uout[(size_t)r * g.ldu + q] = un;
                             ssq_u = fma((double)un, (double)un, ssq_u);
                         }
                     }
                 }
-            }
-            if (warps_per_row > 1) {
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (i < count) {
+                        const int slot = slot_base + i;
+                        const int rb = slot / NUB, q = slot - rb * NUB;
+                        const int r = gr + rb * g.rg;
+                        if (owner && rb < g.rpt && r < nrows && q < g.nu) redt[((size_t)r * g.nu + q) * wpr + wir] = gp[i];
+                    }
+                }
                 consumer_bar();
+                const T* sU = reinterpret_cast<const T*>(stages + (size_t)s * g.stage_bytes + g.offU);
+                const T* sUp = reinterpret_cast<const T*>(stages + (size_t)s * g.stage_bytes + g.offUp);
                 for (int e = c.ctid; e < nrows * g.nu; e += kConsumers) {
                     const int r = e / g.nu, q = e - r * g.nu;
                     double v = 0.0;
-                    for (int w = 0; w < warps_per_row; ++w) v += redt[((size_t)r * warps_per_row + w) * g.nu + q];
-                    const T u = sU[r * g.nu + q], up = sUp[r * g.nu + q];
+                    for (int w2 = 0; w2 < wpr; ++w2) v += redt[(size_t)e * wpr + w2];
+                    const T u = sU[(size_t)r * g.ldu + q], up = sUp[(size_t)r * g.ldu + q];
                     const T utq = u + beta * (u - up);
                     T un = utq + (T)v / lw;
                     un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
-                    Uout[(size_t)r * g.nu + q] = un;
+                    Uout[(size_t)r * g.ldu + q] = un;
                     ssq_u = fma((double)un, (double)un, ssq_u);
                 }
             }
@@ -378,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) u_pass_kern
         }
     }
     __syncthreads();
-    double* scratch = reinterpret_cast<double*>(c.stages);
+    double* scratch = reinterpret_cast<double*>(stages);
     double* rec = scratch + 16;
     if (c.warp < kConsumers / 32) {
         const double s0 = consumer_block_sum(ssq_u, scratch, c.ctid);
@@ -420,14 +571,17 @@ __device__ __forceinline__ bool project_simplex(double* v, int p) {
 
 // alpha pass: G = R^T (d o (x - R a_eval)); last CTA applies the projected-gradient or Frank-Wolfe step
 template <typename T, typename WT, int KTB, int C>
-__global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) alpha_pass_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kernel(const PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NCH = KTB / 2;
     const Geom& g = a.g;
     const FitDev f = a.fits[blockIdx.y];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
     cta_setup(g, smem, c);
+    unsigned char* stages = smem + kCtlBytes;
+    const uint32_t stages32 = smem_u32(stages);
     const bool fw = (a.flags & kFlagFW) != 0;
     const int ucur = st->u_cur, acur = st->a_cur;
     const double a_prev = st->a2, l_h = st->l_h, l_h_old = st->l_h_old;
@@ -439,65 +593,72 @@ __global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) alpha_pass_
     const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
 
     const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
-    const int j0 = tc * C;
+    const bool colvalid = (c.ctid < kConsumers) && (C * tc < g.N);
+    const int j0 = colvalid ? C * tc : 0;
     T G[KTB][C];
 #pragma unroll
     for (int k = 0; k < KTB; ++k)
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) G[k][cc] = (T)0;
 
-    if (c.warp == kConsumers / 32) {
-        TileSrc src[4];
-        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, true, (g.row_bulk & 1u) != 0};
-        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, true, (g.row_bulk & 2u) != 0};
-        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, true, (g.row_bulk & 4u) != 0};
-        src[3] = {Ucur, g.nu * (long long)sizeof(T), g.offU, false, false};
-        producer_loop(g, f, c, src, 4);
-    } else {
+    constexpr int NSRC = 4;
+    if (threadIdx.x == 0) {
+        TileSrc* src = c.ctl->src;
+        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
+        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
+        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
+        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+    }
+    __syncthreads();
+    for (int it = 0; it < kStages - 1; ++it) produce_it(g, f, c, stages, NSRC, it);
+    {
         T at[KTB][C];    // evaluation point: alpha_temp (PG) or alpha (FW)
 #pragma unroll
-        for (int k = 0; k < KTB; ++k)
+        for (int k = 0; k < KTB; ++k) {
+            const int ar = alpha_row_of(g, k);
 #pragma unroll
             for (int cc = 0; cc < C; ++cc) {
                 T v = (T)0;
-                if (k < g.Kt && j0 + cc < g.N) {
-                    const T ac = Acur[(size_t)k * g.N + j0 + cc];
+                if (ar >= 0 && colvalid && j0 + cc < g.N) {
+                    const T ac = Acur[(size_t)ar * g.N + j0 + cc];
                     v = ac;
-                    if (!fw) v = ac + beta * (ac - Aprev[(size_t)k * g.N + j0 + cc]);
+                    if (!fw) v = ac + beta * (ac - Aprev[(size_t)ar * g.N + j0 + cc]);
                 }
                 at[k][cc] = v;
             }
+        }
+        ChunkMap<NCH> cm;
+        make_chunk_map<T, NCH>(g, cm);
+        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
+        const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
         for (int it = 0; it < c.n_my; ++it) {
+            produce_it(g, f, c, stages, NSRC, it + kStages - 1);
             const int s = it % kStages;
             mbar_wait(smem_u32(&c.ctl->full[s]), (unsigned)(it / kStages) & 1u);
-            const char* sb = c.stages + (size_t)s * g.stage_bytes;
-            const T* sX = reinterpret_cast<const T*>(sb + g.offX);
-            const void* sD = sb + g.offD;
-            const T* sR = reinterpret_cast<const T*>(sb + g.offR);
-            const T* sU = reinterpret_cast<const T*>(sb + g.offU);
+            const uint32_t sb = stages32 + (uint32_t)s * g.stage_bytes;
             const long long r0 = (blockIdx.x + (long long)it * gridDim.x) * g.tile_rows;
             const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
-            for (int r = gr; r < nrows; r += g.rg) {
-                T rrow[KTB];
+            if (colvalid) {
+                for (int r = gr; r < nrows; r += g.rg) {
+                    T rrow[KTB];
 #pragma unroll
-                for (int k = 0; k < KTB; ++k) {
-                    T v = (T)0;
-                    if (k < g.K) v = sR[(size_t)r * g.ldr + k];
-                    else if (k < g.Kt) v = sU[r * g.nu + (k - g.K)];
-                    rrow[k] = v;
-                }
+                    for (int i = 0; i < NCH; ++i) lds2(sb + cm.off[i] + r * cm.pitch[i], rrow[2 * i], rrow[2 * i + 1]);
+                    T x[C], d[C], p[C];
+                    ldsC<T, C>(sb + xoff + r * xpitch, x);
+                    WLoad<T, WT, C>::ld(sb + doff + r * dpitch, d);
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) {
-                    if (j0 + cc < g.N) {
-                        const T x = sX[(size_t)r * g.ldx + j0 + cc];
-                        const T d = wload<T, WT>(sD, (long long)r * g.ldd + j0 + cc);
-                        T pred = (T)0;
+                    for (int cc = 0; cc < C; ++cc) p[cc] = (T)0;
 #pragma unroll
-                        for (int k = 0; k < KTB; ++k) pred = fma_t<T>(rrow[k], at[k][cc], pred);
-                        const T w = d * (x - pred);
+                    for (int k = 0; k < KTB; ++k)
 #pragma unroll
-                        for (int k = 0; k < KTB; ++k) G[k][cc] = fma_t<T>(rrow[k], w, G[k][cc]);
-                    }
+                        for (int cc = 0; cc < C; ++cc) p[cc] = fma_t<T>(rrow[k], at[k][cc], p[cc]);
+                    T w[C];
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) w[cc] = d[cc] * (x[cc] - p[cc]);
+#pragma unroll
+                    for (int k = 0; k < KTB; ++k)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) G[k][cc] = fma_t<T>(rrow[k], w[cc], G[k][cc]);
                 }
             }
             __syncwarp();
@@ -506,19 +667,21 @@ __global__ void __launch_bounds__(kThreads, (KTB * C <= 16) ? 2 : 1) alpha_pass_
     }
     __syncthreads();
     // combine the row groups of this CTA in fixed order, then publish the CTA partial [Kt][N]
-    double* scratch = reinterpret_cast<double*>(c.stages);
+    double* scratch = reinterpret_cast<double*>(stages);
     const int KN = g.Kt * g.N;
     if (c.warp < kConsumers / 32) {
         for (int gg = 0; gg < g.rg; ++gg) {
-            if (gr == gg) {
+            if (gr == gg && colvalid) {
 #pragma unroll
-                for (int k = 0; k < KTB; ++k)
+                for (int k = 0; k < KTB; ++k) {
+                    const int ar = alpha_row_of(g, k);
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc)
-                        if (k < g.Kt && j0 + cc < g.N) {
-                            double* p = &scratch[(size_t)k * g.N + j0 + cc];
+                        if (ar >= 0 && j0 + cc < g.N) {
+                            double* p = &scratch[(size_t)ar * g.N + j0 + cc];
                             *p = (gg == 0) ? (double)G[k][cc] : (*p + (double)G[k][cc]);
                         }
+                }
             }
             consumer_bar();
         }

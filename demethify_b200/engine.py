@@ -42,6 +42,19 @@ def _tdtype(precision):
     return torch.float64 if precision == "fp64" else torch.float32
 
 
+def _even(n):
+    return n + (n & 1)
+
+
+def _pad_cols(t, width):
+    """Zero-pad a 2-D device tensor on the right to `width` columns (ABI: even pitches, zero padding)."""
+    if t.shape[1] == width:
+        return t.contiguous()
+    out = torch.zeros((t.shape[0], width), dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]].copy_(t)
+    return out
+
+
 def to_device(arr, dtype=None, device=None):
     """Host ndarray / tensor -> contiguous device tensor (async when the source is pinned)."""
     device = device or current_device()
@@ -68,15 +81,18 @@ class DeviceProblem:
         self.precision = precision or get_precision()
         self.device = device or current_device()
         self.dtype = _tdtype(self.precision)
-        self.X = to_device(X, self.dtype, self.device)
-        self.M, self.N = self.X.shape
+        X = to_device(X, self.dtype, self.device)
+        self.M, self.N = X.shape
+        self.ldx = _even(self.N)
+        self.X = _pad_cols(X, self.ldx)
         self.K = 0
         self.Rk = None
         if Rk is not None:
-            self.Rk = to_device(Rk, self.dtype, self.device)
-            if self.Rk.ndim != 2 or self.Rk.shape[0] != self.M:
+            Rk = to_device(Rk, self.dtype, self.device)
+            if Rk.ndim != 2 or Rk.shape[0] != self.M:
                 raise ValueError("R_trunc must be M x K")
-            self.K = self.Rk.shape[1]
+            self.K = Rk.shape[1]
+            self.Rk = _pad_cols(Rk, _even(self.K))
         self.set_weights(D, narrow_weights)
 
     def set_weights(self, D, narrow=True):
@@ -91,14 +107,15 @@ class DeviceProblem:
             if kind is None:
                 raw = raw.to(torch.float64)
                 kind = 0
-            packed = torch.empty((self.M, self.N), dtype=torch.uint16, device=self.device)
+            raw = _pad_cols(raw, self.ldx)
+            packed = torch.empty((self.M, self.ldx), dtype=torch.uint16, device=self.device)
             bad = torch.zeros(1, dtype=torch.int32, device=self.device)
             _lib.check(_lib.lib().dmf_pack_weights_u16(C.c_void_p(raw.data_ptr()), kind, raw.numel(), C.c_void_p(packed.data_ptr()),
                                                        C.c_void_p(bad.data_ptr()), _stream_ptr()))
             if int(bad.item()) == 0:
                 self.D, self.wtype = packed, _lib.DMF_W_U16
         if self.D is None:
-            self.D = raw.to(self.dtype).contiguous()
+            self.D = _pad_cols(raw.to(self.dtype), self.ldx)
 
     def with_weights(self, D_tensor, wtype):
         """Shallow copy sharing X / R_trunc with different weights (BCV folds, ic.py:75)."""
@@ -129,7 +146,8 @@ class FitBatch:
         if rows is not None:
             self.M = int(rows[0].shape[0])
         # ping-pong buffers: both slots start at the initial iterate (u_ = u.copy(), deconvolution.py:194-195)
-        self.u_slot = (self.M * self.n_u + 31) // 32 * 32          # slot stride keeps bulk copies 16-byte aligned
+        self.ldu = _even(self.n_u)
+        self.u_slot = (self.M * self.ldu + 31) // 32 * 32          # slot stride keeps bulk copies 16-byte aligned
         self.U = torch.zeros((self.n_fits, 2, self.u_slot), dtype=dt, device=dev)
         self.A = torch.empty((self.n_fits, 2, self.Kt, self.N), dtype=dt, device=dev)
         for i in range(self.n_fits):
@@ -152,8 +170,8 @@ class FitBatch:
         self.h = _handle(dev.index if dev.index is not None else torch.cuda.current_device())
         self.shape = _lib.Shape(M=self.M, N=self.N, K=self.K, n_u=self.n_u,
                                 dtype=_lib.DMF_F64 if dt == torch.float64 else _lib.DMF_F32, wtype=p0.wtype, mode=mode,
-                                n_fits=self.n_fits, max_ctas_per_fit=max_ctas_per_fit, ldx=self.N, ldd=self.N, ldr=max(self.K, 1),
-                                u_slot=self.u_slot)
+                                n_fits=self.n_fits, max_ctas_per_fit=max_ctas_per_fit, ldx=p0.ldx, ldd=p0.ldx, ldr=_even(self.K),
+                                ldu=self.ldu, u_slot=self.u_slot)
         nbytes = C.c_size_t()
         _lib.check(lib.dmf_batch_workspace_bytes(self.h, C.byref(self.shape), C.byref(nbytes)))
         self.ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
@@ -174,7 +192,7 @@ class FitBatch:
         _lib.check(lib.dmf_batch_create(self.h, C.byref(self.shape), descs, C.c_void_p(ws_ptr), nbytes.value, _stream_ptr(), C.byref(self.b)))
 
     def u_view(self, i, slot):
-        return self.U[i, slot, :self.M * self.n_u].view(self.M, self.n_u)
+        return self.U[i, slot, :self.M * self.ldu].view(self.M, self.ldu)[:, :self.n_u]
 
     # -- single reference-shaped steps (one launch each)
     def pass_init(self):
@@ -226,7 +244,7 @@ class FitBatch:
         out = []
         for i, st in enumerate(states):
             u, a = self.current(i, states)
-            out.append((u.to(torch.float64).cpu().numpy(), a.to(torch.float64).cpu().numpy(), st.n_outer, st.cost))
+            out.append((u.to(torch.float64).contiguous().cpu().numpy(), a.to(torch.float64).cpu().numpy(), st.n_outer, st.cost))
         return out
 
     def close(self):

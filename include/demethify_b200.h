@@ -54,10 +54,13 @@ typedef struct dmf_shape {
     int32_t mode;   /* DMF_MODE_*                       */
     int32_t n_fits; /* fits in the batch                */
     int32_t max_ctas_per_fit; /* 0 = let the library choose (multiple of the SM count overall) */
-    int64_t ldx;    /* row pitch of X  in elements (>= N) */
-    int64_t ldd;    /* row pitch of D  in elements (>= N) */
-    int64_t ldr;    /* row pitch of Rk in elements (>= K) */
-    int64_t u_slot; /* elements between the two ping-pong slots of U (>= M*n_u, u_slot*sizeof(T) % 16 == 0) */
+    /* Row pitches in elements.  ALL PITCHES MUST BE EVEN and the padding entries MUST BE ZERO: the kernels
+     * fetch every matrix as aligned two-element vectors and rely on zero padding instead of bounds tests. */
+    int64_t ldx;    /* row pitch of X  (>= N, even)      */
+    int64_t ldd;    /* row pitch of D  (>= N, even)      */
+    int64_t ldr;    /* row pitch of Rk (>= K, even)      */
+    int64_t ldu;    /* row pitch of U  (>= n_u, even)    */
+    int64_t u_slot; /* elements between the two ping-pong slots of U (>= M*ldu, u_slot*sizeof(T) % 16 == 0) */
 } dmf_shape_t;
 
 /* Per-fit buffers (host array of n_fits of these is passed to dmf_batch_create). */
@@ -67,7 +70,7 @@ typedef struct dmf_fit_desc {
     const void* Rk;        /* M x K   known reference profiles R_trunc (NULL when K = 0)        */
     const int32_t* rows;   /* optional gather: fit row p reads source row rows[p] of X, D, Rk
                               (bootstrap.py:28 resample); NULL = identity.  U stays position-indexed */
-    void* U;               /* two slots of M x n_u, shape.u_slot elements apart; BOTH hold the initial u */
+    void* U;               /* two slots of M x n_u (pitch ldu), shape.u_slot elements apart; BOTH hold the initial u */
     void* A;               /* [2][Kt][N]; BOTH slots hold the initial alpha (alpha_ = alpha.copy())    */
     const double* purity;  /* [N] internal purity vector (DMF_MODE_PURITY) else NULL            */
     double* cost_trace;    /* optional [trace_cap] cost after every outer iteration, or NULL    */
