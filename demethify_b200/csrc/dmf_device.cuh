@@ -9,7 +9,7 @@ namespace dmf {
 
 constexpr int kConsumers = 256;             // threads per CTA: 8 warps, all compute; warp 0 also feeds the TMA ring
 constexpr int kThreads = kConsumers;
-constexpr int kStages = 4;                  // smem ring depth
+constexpr int kStages = 5;                  // smem ring depth (kStages - 2 tiles requested ahead)
 constexpr int kGroup = 16;                  // CTAs per first-level reduction group
 constexpr int kMaxSrc = 5;                  // matrices streamed per stage: X, D, Rk, U, Uprev
 constexpr int kMaxKt = 32;                  // K + n_u supported by the register-tiled kernels

@@ -111,7 +111,8 @@ __device__ __forceinline__ double consumer_block_max(double v, double* scratch, 
 // Common CTA set-up: barriers and the tile share of this CTA.
 struct CtaCtx {
     SmemCtl* ctl;
-    int n_my;
+    int n_my;          // tiles this CTA owns (global tiles blockIdx.x, blockIdx.x + gridDim.x, ...)
+    int last_rows;     // rows in the last global tile
     int warp, lane, ctid;
 };
 
@@ -119,9 +120,10 @@ __device__ __forceinline__ void cta_setup(const Geom& g, unsigned char* smem, Ct
     c.ctl = reinterpret_cast<SmemCtl*>(smem);
     c.warp = threadIdx.x >> 5;
     c.lane = threadIdx.x & 31;
-    c.ctid = threadIdx.x;   // consumers are threads [0, kConsumers)
+    c.ctid = threadIdx.x;
     const int first = blockIdx.x;
     c.n_my = (g.n_tiles > first) ? (g.n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    c.last_rows = (int)(g.M - (long long)(g.n_tiles - 1) * g.tile_rows);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
@@ -132,21 +134,50 @@ __device__ __forceinline__ void cta_setup(const Geom& g, unsigned char* smem, Ct
     }
 }
 
+// Rolling view of the stage ring (all 32-bit): tile counter, stage, barrier parity, stage address, global tile.
+struct Ring {
+    int it, s, gtile;
+    unsigned parity;
+    uint32_t sb;
+    __device__ __forceinline__ void init(uint32_t stages32) { it = 0; s = 0; parity = 0; sb = stages32; gtile = blockIdx.x; }
+    __device__ __forceinline__ void advance(const Geom& g, uint32_t stages32) {
+        ++it;
+        gtile += gridDim.x;
+        if (++s == kStages) { s = 0; parity ^= 1u; sb = stages32; }
+        else sb += g.stage_bytes;
+    }
+    __device__ __forceinline__ int rows(const Geom& g, const CtaCtx& c) const { return gtile == g.n_tiles - 1 ? c.last_rows : g.tile_rows; }
+};
+
 // Producer duty is rotated over the warps (tile t is requested by warp t mod 8, between its own tiles), so no
-// single warp lags behind; kStages - 1 tiles stay in flight per CTA.
-__device__ __forceinline__ void produce_it(const Geom& g, const FitDev& f, const CtaCtx& c, unsigned char* stages, int nsrc, int it) {
-    if (it >= c.n_my || c.warp != (it & (kConsumers / 32 - 1))) return;
-    const int s = it % kStages;
-    const unsigned n = (unsigned)(it / kStages);
-    mbar_wait(smem_u32(&c.ctl->empty[s]), (n & 1u) ^ 1u);
-    const long long tile = blockIdx.x + (long long)it * gridDim.x;
-    const long long r0 = tile * g.tile_rows;
-    const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
-    char* sbase = reinterpret_cast<char*>(stages) + (size_t)s * g.stage_bytes;
-    if (nrows == g.tile_rows && f.rows == nullptr)
-        produce_full_tile(g, c.ctl->src, nsrc, r0, sbase, smem_u32(&c.ctl->full[s]), c.lane);
-    else
-        produce_tile(c.ctl->src, nsrc, f.rows, r0, nrows, sbase, smem_u32(&c.ctl->full[s]), c.lane);
+// single warp lags behind.  Requests run kAhead = kStages - 2 tiles ahead of consumption: the stage being
+// refilled was released a full tile ago, so the requesting warp practically never waits on `empty`.
+constexpr int kAhead = kStages - 2;
+__device__ __forceinline__ void produce_next(const Geom& g, const FitDev& f, const CtaCtx& c, Ring& pr, uint32_t stages32, int nsrc) {
+    if (pr.it < c.n_my && c.warp == (pr.it & (kConsumers / 32 - 1))) {
+        mbar_wait(smem_u32(&c.ctl->empty[pr.s]), pr.parity ^ 1u);
+        const int nrows = pr.rows(g, c);
+        const uint32_t full = smem_u32(&c.ctl->full[pr.s]);
+        if (nrows == g.tile_rows && f.rows == nullptr) {
+            if (c.lane == 0) {
+                const TileSrc* src = c.ctl->src;
+                unsigned tx = 0;
+#pragma unroll
+                for (int k = 0; k < kMaxSrc; ++k)
+                    if (k < nsrc && src[k].base != nullptr) tx += g.tile_tx[k];
+                mbar_arrive_expect_tx(full, tx);
+#pragma unroll
+                for (int k = 0; k < kMaxSrc; ++k)
+                    if (k < nsrc && src[k].base != nullptr)
+                        bulk_g2s(pr.sb + src[k].off, src[k].base + (unsigned long long)pr.gtile * g.tile_tx[k], g.tile_tx[k], full);
+            }
+            __syncwarp();
+        } else {
+            produce_tile(c.ctl->src, nsrc, f.rows, (long long)pr.gtile * g.tile_rows, nrows,
+                         reinterpret_cast<char*>(__cvta_shared_to_generic(pr.sb)), full, c.lane);
+        }
+    }
+    pr.advance(g, stages32);
 }
 
 // Register row [R_trunc row (Kp entries, zero padded) | u row (ldu entries, zero padded)] is fetched as
@@ -159,7 +190,7 @@ struct ChunkMap {
 };
 template <typename T, int NCH>
 __device__ __forceinline__ void make_chunk_map(const Geom& g, ChunkMap<NCH>& m) {
-    const int nR = g.Kp >> 1, nU = (int)(g.ldu >> 1);
+    const int nR = g.Kp >> 1, nU = g.nup >> 1;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         if (i < nR) { m.off[i] = g.offR + i * 2 * (unsigned)sizeof(T); m.pitch[i] = (unsigned)(g.ldr * sizeof(T)); }
@@ -203,7 +234,10 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
         src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
     }
     __syncthreads();
-    for (int it = 0; it < kStages - 1; ++it) produce_it(g, f, c, stages, NSRC, it);
+    Ring pr, cr;
+    pr.init(stages32);
+    cr.init(stages32);
+    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
         const bool colvalid = C * tc < g.N;
@@ -219,13 +253,11 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
         make_chunk_map<T, NCH>(g, cm);
         const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
         const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
-        for (int it = 0; it < c.n_my; ++it) {
-            produce_it(g, f, c, stages, NSRC, it + kStages - 1);
-            const int s = it % kStages;
-            mbar_wait(smem_u32(&c.ctl->full[s]), (unsigned)(it / kStages) & 1u);
-            const uint32_t sb = stages32 + (uint32_t)s * g.stage_bytes;
-            const long long r0 = (blockIdx.x + (long long)it * gridDim.x) * g.tile_rows;
-            const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
+        for (; cr.it < c.n_my; cr.advance(g, stages32)) {
+            produce_next(g, f, c, pr, stages32, NSRC);
+            mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
+            const uint32_t sb = cr.sb;
+            const int nrows = cr.rows(g, c);
             if (colvalid) {
                 for (int r = gr; r < nrows; r += g.rg) {
                     T rrow[KTB];
@@ -243,12 +275,19 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
                     T x[C], d[C], p[C];
                     ldsC<T, C>(sb + xoff + r * xpitch, x);
                     WLoad<T, WT, C>::ld(sb + doff + r * dpitch, d);
+                    // two independent chains per column (even / odd entries) halve the dependent-FMA latency
+                    T pe[C], po[C];
 #pragma unroll
-                    for (int cc = 0; cc < C; ++cc) p[cc] = (T)0;
+                    for (int cc = 0; cc < C; ++cc) { pe[cc] = rrow[0] * at[0][cc]; po[cc] = rrow[1] * at[1][cc]; }
 #pragma unroll
-                    for (int k = 0; k < KTB; ++k)
+                    for (int k = 2; k < KTB; k += 2)
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) p[cc] = fma_t<T>(rrow[k], at[k][cc], p[cc]);
+                        for (int cc = 0; cc < C; ++cc) {
+                            pe[cc] = fma_t<T>(rrow[k], at[k][cc], pe[cc]);
+                            po[cc] = fma_t<T>(rrow[k + 1], at[k + 1][cc], po[cc]);
+                        }
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) p[cc] = pe[cc] + po[cc];
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) {
                         const double e = (double)(x[cc] - p[cc]);
@@ -258,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
                 }
             }
             __syncwarp();
-            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[s]));
+            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
         }
     }
     __syncthreads();
@@ -333,8 +372,6 @@ __device__ __forceinline__ void seg_reduce(double (&v)[NV], int L, int lane, int
     for (int s = 0; s < 5; ++s) {
         const int o = 1 << s;
         if (o < L) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int half = NV >> (s + 1);          // compile-time: values kept when every earlier step ran
             if (half >= 1) {
                 const bool up = (lane & o) != 0;
@@ -389,7 +426,10 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
         src[4] = {Uprev, g.ldu * (long long)sizeof(T), g.offUp, 0, 0, 0};
     }
     __syncthreads();
-    for (int it = 0; it < kStages - 1; ++it) produce_it(g, f, c, stages, NSRC, it);
+    Ring pr, cr;
+    pr.init(stages32);
+    cr.init(stages32);
+    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
         const bool colvalid = C * tc < g.N;
@@ -410,19 +450,17 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
         const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
         const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
         const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
-        const int nRch = g.Kp >> 1, nUch = (int)(g.ldu >> 1);
+        const int nRch = g.Kp >> 1, nUch = g.nup >> 1;
         // cross-warp combine buffer (rows spanning several warps): [2][tile_rows][nu][wpr]
         double* red = reinterpret_cast<double*>(stages + (size_t)kStages * g.stage_bytes);
 
-        for (int it = 0; it < c.n_my; ++it) {
-            produce_it(g, f, c, stages, NSRC, it + kStages - 1);
-            const int s = it % kStages;
-            mbar_wait(smem_u32(&c.ctl->full[s]), (unsigned)(it / kStages) & 1u);
-            const uint32_t sb = stages32 + (uint32_t)s * g.stage_bytes;
-            const long long r0 = (blockIdx.x + (long long)it * gridDim.x) * g.tile_rows;
-            const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
-            double* redt = red + (size_t)(it & 1) * g.tile_rows * g.nu * wpr;
-            T* Uout = reinterpret_cast<T*>(Uprev) + (size_t)r0 * g.ldu;
+        for (; cr.it < c.n_my; cr.advance(g, stages32)) {
+            produce_next(g, f, c, pr, stages32, NSRC);
+            mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
+            const uint32_t sb = cr.sb;
+            const int nrows = cr.rows(g, c);
+            double* redt = red + (size_t)(cr.it & 1) * g.tile_rows * g.nu * wpr;
+            T* Uout = reinterpret_cast<T*>(Uprev) + (size_t)cr.gtile * g.tile_rows * g.ldu;
 
             double gp[NV];
             T utk[RPT][NUB];
@@ -451,14 +489,18 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
                 T x[C], d[C], pk[C], pu[C];
                 ldsC<T, C>(sb + xoff + rr * xpitch, x);
                 WLoad<T, WT, C>::ld(sb + doff + rr * dpitch, d);
+                T pk1[C];
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) pk[cc] = pu[cc] = (T)0;
-                if (g.K > 0) {
+                for (int cc = 0; cc < C; ++cc) { pk[cc] = rk[0] * ak[0][cc]; pk1[cc] = rk[1] * ak[1][cc]; pu[cc] = (T)0; }
 #pragma unroll
-                    for (int k = 0; k < KB; ++k)
+                for (int k = 2; k < KB; k += 2)
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) pk[cc] = fma_t<T>(rk[k], ak[k][cc], pk[cc]);
-                }
+                    for (int cc = 0; cc < C; ++cc) {
+                        pk[cc] = fma_t<T>(rk[k], ak[k][cc], pk[cc]);
+                        pk1[cc] = fma_t<T>(rk[k + 1], ak[k + 1][cc], pk1[cc]);
+                    }
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) pk[cc] = pk[cc] + pk1[cc];
 #pragma unroll
                 for (int q = 0; q < NUB; ++q)
 #pragma unroll
@@ -509,11 +551,15 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
                         if (owner && rb < g.rpt && r < nrows && q < g.nu) redt[((size_t)r * g.nu + q) * wpr + wir] = gp[i];
                     }
                 }
-                consumer_bar();
-                const T* sU = reinterpret_cast<const T*>(stages + (size_t)s * g.stage_bytes + g.offU);
-                const T* sUp = reinterpret_cast<const T*>(stages + (size_t)s * g.stage_bytes + g.offUp);
-                for (int e = c.ctid; e < nrows * g.nu; e += kConsumers) {
-                    const int r = e / g.nu, q = e - r * g.nu;
+                // only the warps of this row group meet: named barrier 1 + gr, ntc threads
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + gr), "r"(g.ntc) : "memory");
+                const T* sU = reinterpret_cast<const T*>(stages + (size_t)cr.s * g.stage_bytes + g.offU);
+                const T* sUp = reinterpret_cast<const T*>(stages + (size_t)cr.s * g.stage_bytes + g.offUp);
+                for (int e2 = tc; e2 < g.rpt * g.nu; e2 += g.ntc) {
+                    const int rb = e2 / g.nu, q = e2 - rb * g.nu;
+                    const int r = gr + rb * g.rg;
+                    if (r >= nrows) continue;
+                    const int e = r * g.nu + q;
                     double v = 0.0;
                     for (int w2 = 0; w2 < wpr; ++w2) v += redt[(size_t)e * wpr + w2];
                     const T u = sU[(size_t)r * g.ldu + q], up = sUp[(size_t)r * g.ldu + q];
@@ -525,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
                 }
             }
             __syncwarp();
-            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[s]));
+            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
         }
     }
     __syncthreads();
@@ -610,7 +656,10 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
         src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
     }
     __syncthreads();
-    for (int it = 0; it < kStages - 1; ++it) produce_it(g, f, c, stages, NSRC, it);
+    Ring pr, cr;
+    pr.init(stages32);
+    cr.init(stages32);
+    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         T at[KTB][C];    // evaluation point: alpha_temp (PG) or alpha (FW)
 #pragma unroll
@@ -631,13 +680,11 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
         make_chunk_map<T, NCH>(g, cm);
         const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
         const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
-        for (int it = 0; it < c.n_my; ++it) {
-            produce_it(g, f, c, stages, NSRC, it + kStages - 1);
-            const int s = it % kStages;
-            mbar_wait(smem_u32(&c.ctl->full[s]), (unsigned)(it / kStages) & 1u);
-            const uint32_t sb = stages32 + (uint32_t)s * g.stage_bytes;
-            const long long r0 = (blockIdx.x + (long long)it * gridDim.x) * g.tile_rows;
-            const int nrows = (int)min((long long)g.tile_rows, g.M - r0);
+        for (; cr.it < c.n_my; cr.advance(g, stages32)) {
+            produce_next(g, f, c, pr, stages32, NSRC);
+            mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
+            const uint32_t sb = cr.sb;
+            const int nrows = cr.rows(g, c);
             if (colvalid) {
                 for (int r = gr; r < nrows; r += g.rg) {
                     T rrow[KTB];
@@ -646,12 +693,19 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
                     T x[C], d[C], p[C];
                     ldsC<T, C>(sb + xoff + r * xpitch, x);
                     WLoad<T, WT, C>::ld(sb + doff + r * dpitch, d);
+                    // two independent chains per column (even / odd entries) halve the dependent-FMA latency
+                    T pe[C], po[C];
 #pragma unroll
-                    for (int cc = 0; cc < C; ++cc) p[cc] = (T)0;
+                    for (int cc = 0; cc < C; ++cc) { pe[cc] = rrow[0] * at[0][cc]; po[cc] = rrow[1] * at[1][cc]; }
 #pragma unroll
-                    for (int k = 0; k < KTB; ++k)
+                    for (int k = 2; k < KTB; k += 2)
 #pragma unroll
-                        for (int cc = 0; cc < C; ++cc) p[cc] = fma_t<T>(rrow[k], at[k][cc], p[cc]);
+                        for (int cc = 0; cc < C; ++cc) {
+                            pe[cc] = fma_t<T>(rrow[k], at[k][cc], pe[cc]);
+                            po[cc] = fma_t<T>(rrow[k + 1], at[k + 1][cc], po[cc]);
+                        }
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) p[cc] = pe[cc] + po[cc];
                     T w[C];
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) w[cc] = d[cc] * (x[cc] - p[cc]);
@@ -662,7 +716,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
                 }
             }
             __syncwarp();
-            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[s]));
+            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
         }
     }
     __syncthreads();
