@@ -32,6 +32,13 @@ class FitState(C.Structure):
                 ("done", C.c_int32), ("u_slot", C.c_int32), ("a_slot", C.c_int32)]
 
 
+class WlsDesc(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("K2", C.c_int32), ("dtype", C.c_int32),
+                ("wtype", C.c_int32), ("y_is_dx", C.c_int32), ("reserved", C.c_int32), ("ldx", C.c_int64), ("ldd", C.c_int64),
+                ("ldr", C.c_int64), ("ldr2", C.c_int64), ("X", C.c_void_p), ("D", C.c_void_p), ("R1", C.c_void_p),
+                ("R2", C.c_void_p), ("out", C.c_void_p)]
+
+
 EXPORTS = {
     "dmf_abi_version": (C.c_int, []),
     "dmf_last_error": (C.c_char_p, []),
@@ -52,6 +59,8 @@ EXPORTS = {
     "dmf_fit_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_batch_read_state": (C.c_int, [C.c_void_p, C.POINTER(FitState), C.c_int32, C.c_void_p]),
     "dmf_batch_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "dmf_wls_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(WlsDesc), C.POINTER(C.c_size_t)]),
+    "dmf_wls_fit": (C.c_int, [C.c_void_p, C.POINTER(WlsDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dmf_pack_weights_u16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmf_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
 }

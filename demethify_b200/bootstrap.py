@@ -1,0 +1,120 @@
+"""Mirror of the reference's demethify/bootstrap.py: bootstrap confidence intervals.
+
+The reference fits the resamples one after another (bootstrap.py:26-46); here all resamples of a wave are ONE
+batched launch set (FitBatch with a per-fit row index: the kernels gather rows of the shared X, d_x, R_trunc, while
+every fit owns its position-indexed u).  Seeds, resampling indices, init draws and the percentile arithmetic follow
+the reference exactly: seed_i = seed_{i-1} + i, sklearn.utils.resample == RandomState(seed).randint.
+"""
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from .deconvolution import init_BSSMF_md, init_BSSMF_md_p
+from .engine import DeviceProblem, FitBatch, device_free_bytes
+from .init_func import wls_all_samples
+
+__all__ = ["bt_ci", "bootstrap_seeds", "resample_indices", "bootstrap_fits"]
+
+
+def bootstrap_seeds(seed, n_bootstrap):
+    """bootstrap.py:27 — the seed accumulates: seed, seed+1, seed+3, seed+6, ..."""
+    if isinstance(seed, (list, tuple, np.ndarray)):
+        # `--seed S` reaches bt_ci as [S] in the reference and `seed + i` raises TypeError
+        raise TypeError("can only concatenate list (not \"int\") to list")
+    out, s = [], seed
+    for i in range(n_bootstrap):
+        s = s + i if s is not None else None
+        out.append(s)
+    return out
+
+
+def resample_indices(seed, M):
+    """sklearn.utils.resample(X, counts, ref, random_state=seed) (bootstrap.py:28) draws
+    RandomState(seed).randint(0, M, size=(M,)) once and indexes every array with it."""
+    return np.random.RandomState(seed).randint(0, M, size=(M,))
+
+
+def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, purity, seed, prob=None,
+                   keep_u=True):
+    """All resample fits -> (alphas (B, Kt, N), us (B, M, n_u) or None, n_outer list).
+    `purity` is the internal vector (already divided by 100, bootstrap.py:18) or None."""
+    meth_f = np.asarray(meth_f)
+    M, N = meth_f.shape
+    seeds = bootstrap_seeds(seed, n_bootstrap)
+    prob = prob or DeviceProblem(meth_f, counts, ref)
+    alphas = np.zeros((n_bootstrap, prob.K + n_u, N))
+    if n_u == 0:
+        for b, s in enumerate(seeds):          # bootstrap.py:40-43: per-sample NNLS on the resampled rows
+            idx = resample_indices(s, M)
+            alphas[b] = wls_all_samples(prob.gathered(idx), None, None, y_is_dx=True)
+        return alphas, None, [0] * n_bootstrap
+    us = np.zeros((n_bootstrap, M, n_u)) if keep_u else None
+    n_outer = []
+    data_dependent_init = init_option in ("uniform", "SVD")
+    # fits per wave: bounded by device memory (two u slots + partials per fit)
+    per_fit = 2 * M * (n_u + (n_u & 1)) * (8 if prob.precision == "fp64" else 4) + 64 * (prob.K + n_u) * N * 8 + 4096
+    wave = int(max(1, min(n_bootstrap, (device_free_bytes(prob.device) // 2) // max(per_fit, 1), 4096)))
+    for w0 in range(0, n_bootstrap, wave):
+        chunk = seeds[w0:w0 + wave]
+        rows, U0, A0, inv = [], [], [], []
+        for s in chunk:
+            idx = resample_indices(s, M)
+            if data_dependent_init:
+                Xb, Db, Rb = meth_f[idx], np.asarray(counts)[idx], np.asarray(ref)[idx]
+            else:      # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
+                Xb, Db, Rb = meth_f, counts, ref
+            if purity is not None:
+                u0, _, a0 = init_BSSMF_md_p(init_option, Xb, Db, Rb, n_u, purity, seed=s)
+            else:
+                u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
+            # visit the resampled rows in source order (HBM locality); u is position-indexed, so permute it along
+            order = np.argsort(idx, kind="stable")
+            rows.append(idx[order])
+            U0.append(u0[order])
+            A0.append(a0)
+            inv.append(order)
+        mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
+        batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows)
+        states = batch.fit(n_iter1, n_iter2, tol)
+        for k, (u, a, n_o, _cost) in enumerate(batch.results(states)):
+            alphas[w0 + k] = a
+            if keep_u:
+                us[w0 + k][inv[k]] = u           # back to the resampled-position order of the reference (Q6)
+            n_outer.append(n_o)
+        batch.close()
+    return alphas, us, n_outer
+
+
+def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, header, outdir, samples,
+          purity, seed):
+    """bootstrap.py:10-93 — same arguments, same two CSV files, same return value (list of DataFrames)."""
+    supervised = n_u == 0
+    a = 1 - confidence_level / 100
+    lower_percentile = 100 * (a / 2)
+    upper_percentile = 100 * (1 - (a / 2))
+    pur = None
+    if purity:
+        pur = np.array(purity) / 100.0                      # bootstrap.py:18 (NOT 1 - p/100)
+    alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed)
+    lo = np.percentile(alphas, lower_percentile, axis=0)    # (Kt, N); bootstrap.py:53-54
+    hi = np.percentile(alphas, upper_percentile, axis=0)
+    results = []
+    unknown_header = [] if supervised else ["unknown_cell_" + str(i + 1) for i in range(n_u)]
+    cell_types = list(header) + unknown_header
+    n_ct = np.asarray(ref).shape[1] + n_u
+    cols = {}
+    for i in range(np.asarray(meth_f).shape[1]):
+        cols[f"Sample_{i + 1}"] = [(float(lo[k, i]), float(hi[k, i])) for k in range(n_ct)]
+    proportions_df = pd.DataFrame(cols, index=cell_types)
+    proportions_df.columns = samples
+    proportions_df.index.name = "Cell Type"
+    proportions_df.to_csv(outdir + "/confidence_interval_celltypes_proportions.csv", index=True)
+    results.append(proportions_df)
+    if not supervised:
+        ulo = np.percentile(us, lower_percentile, axis=0)   # (M, n_u); bootstrap.py:77-78
+        uhi = np.percentile(us, upper_percentile, axis=0)
+        ref_cols = {unknown_header[k]: [(float(ulo[j, k]), float(uhi[j, k])) for j in range(us.shape[1])] for k in range(n_u)}
+        ref_estimate_df = pd.DataFrame(ref_cols)
+        ref_estimate_df.to_csv(outdir + "/confidence_interval_methylation_estimate.csv", index=False)
+        results.append(ref_estimate_df)
+    return results

@@ -486,3 +486,137 @@ int dmf_gather_rows(const void* src, const int32_t* rows, int64_t n_rows, int64_
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// wls_intercept for all samples (dmf_wls.cuh)
+#include "dmf_wls.cuh"
+
+namespace {
+
+struct WlsPlan {
+    int slab, ntc, rg, tile_rows, n_tiles, n_parts, n_groups, part_stride, Kz, nblk;
+    unsigned offX, offD, offR, offU, stage_bytes, smem;
+    size_t off_fit, off_tickets, off_part, off_gpart, off_mom, off_status, ws_bytes;
+};
+
+int make_wls_plan(const dmf_handle_s* h, const dmf_wls_desc_t& d, WlsPlan& p) {
+    if (d.M <= 0 || d.N <= 0 || d.K < 0 || d.K2 < 0 || d.K + d.K2 <= 0) return fail(DMF_E_SHAPE, "wls: M, N positive and K + K2 >= 1 required");
+    if (d.K + d.K2 > kMaxKt) return fail(DMF_E_SHAPE, "wls: more than 32 regressors are not supported by this build");
+    if (d.dtype != DMF_F64 && d.dtype != DMF_F32) return fail(DMF_E_ARG, "dtype must be DMF_F64 or DMF_F32");
+    if (d.wtype != DMF_W_FLOAT && d.wtype != DMF_W_U16) return fail(DMF_E_ARG, "wtype must be DMF_W_FLOAT or DMF_W_U16");
+    if (d.ldx < d.N || d.ldd < d.N || (d.K && d.ldr < d.K) || (d.K2 && d.ldr2 < d.K2)) return fail(DMF_E_SHAPE, "wls: row pitch smaller than the row");
+    if ((d.ldx | d.ldd | (d.K ? d.ldr : 0) | (d.K2 ? d.ldr2 : 0)) & 1) return fail(DMF_E_SHAPE, "wls: row pitches must be even (zero padded)");
+    const size_t sT = d.dtype == DMF_F64 ? 8 : 4, sW = d.wtype == DMF_W_U16 ? 2 : sT;
+    p.slab = std::min<int>(d.N, kConsumers);            // sample columns per launch (one column per thread)
+    p.ntc = next_pow2(p.slab);
+    p.rg = kConsumers / p.ntc;
+    const size_t px = d.ldx * sT, pd = d.ldd * sW, pr = d.K ? d.ldr * sT : 0, pu = d.K2 ? d.ldr2 * sT : 0;
+    int ra = 1;
+    while (ra < 16 && ((ra * px) % 16 || (ra * pd) % 16 || (ra * pr) % 16 || (ra * pu) % 16)) ra <<= 1;
+    const size_t budget = std::min<size_t>((size_t)h->max_smem_optin, 200 * 1024) - kCtlBytes - 2048;
+    auto a128 = [](size_t v) { return align_up(v, 128); };
+    long long tr = 0;
+    for (long long cand = (long long)p.rg * 8; cand >= 1; cand >>= 1) {
+        if (cand % ra) continue;
+        if ((a128(cand * px) + a128(cand * pd) + a128(cand * pr) + a128(cand * pu)) * kStages <= budget) { tr = cand; break; }
+    }
+    if (!tr) return fail(DMF_E_SHAPE, "wls: one row tile does not fit in shared memory");
+    p.tile_rows = (int)tr;
+    p.n_tiles = (int)((d.M + tr - 1) / tr);
+    p.offX = 0;
+    p.offD = (unsigned)a128(tr * px);
+    p.offR = p.offD + (unsigned)a128(tr * pd);
+    p.offU = p.offR + (unsigned)a128(tr * pr);
+    p.stage_bytes = p.offU + (unsigned)a128(tr * pu);
+    p.n_parts = std::min(p.n_tiles, h->sm_count);
+    p.n_groups = (p.n_parts + kGroup - 1) / kGroup;
+    p.part_stride = kWlsBlock * kWlsBlock * p.slab;
+    p.Kz = d.K + d.K2 + 2;
+    p.nblk = (p.Kz + kWlsBlock - 1) / kWlsBlock;
+    p.smem = (unsigned)std::max<size_t>(kCtlBytes + (size_t)kStages * p.stage_bytes, kCtlBytes + (size_t)p.part_stride * 8 + 256);
+    if (p.smem > (unsigned)h->max_smem_optin) return fail(DMF_E_SHAPE, "wls: shared-memory plan exceeds the device limit");
+    p.off_fit = 0;
+    p.off_tickets = 256;
+    p.off_part = align_up(p.off_tickets + sizeof(unsigned) * (p.n_groups + 1), 256);
+    p.off_gpart = align_up(p.off_part + (size_t)p.n_parts * p.part_stride * 8, 256);
+    p.off_mom = align_up(p.off_gpart + (size_t)p.n_groups * p.part_stride * 8, 256);
+    p.off_status = align_up(p.off_mom + (size_t)p.Kz * p.Kz * p.slab * 8, 256);
+    p.ws_bytes = p.off_status + 256;
+    return DMF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmf_wls_workspace_bytes(dmf_handle_t h, const dmf_wls_desc_t* d, size_t* bytes) {
+    if (!h || !d || !bytes) return fail(DMF_E_ARG, "NULL argument");
+    WlsPlan p;
+    int rc = make_wls_plan(h, *d, p);
+    if (rc) return rc;
+    *bytes = p.ws_bytes;
+    return DMF_OK;
+}
+
+int dmf_wls_fit(dmf_handle_t h, const dmf_wls_desc_t* dd, void* ws, size_t ws_bytes, void* stream) {
+    if (!h || !dd || !ws) return fail(DMF_E_ARG, "NULL argument");
+    const dmf_wls_desc_t& d = *dd;
+    if (!d.X || !d.D || !d.out || (d.K && !d.R1) || (d.K2 && !d.R2)) return fail(DMF_E_ARG, "wls: NULL matrix");
+    WlsPlan p;
+    int rc = make_wls_plan(h, d, p);
+    if (rc) return rc;
+    if (ws_bytes < p.ws_bytes) return fail(DMF_E_ARG, "wls: workspace too small");
+    if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(DMF_E_ARG, "workspace must be 256-byte aligned");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = static_cast<char*>(ws);
+    const size_t sT = d.dtype == DMF_F64 ? 8 : 4, sW = d.wtype == DMF_W_U16 ? 2 : sT;
+    wls_kern_t kern = d.dtype == DMF_F64 ? (d.wtype == DMF_W_U16 ? pick_wls_f64_u16() : pick_wls_f64_f64())
+                                         : (d.wtype == DMF_W_U16 ? pick_wls_f32_u16() : pick_wls_f32_f32());
+    CUDA_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    CUDA_TRY(cudaMemsetAsync(base + p.off_tickets, 0, p.off_part - p.off_tickets, st));
+    CUDA_TRY(cudaMemsetAsync(base + p.off_status, 0, 256, st));
+    for (int j0 = 0; j0 < d.N; j0 += p.slab) {
+        const int ns = std::min(p.slab, d.N - j0);
+        FitDev f;
+        memset(&f, 0, sizeof(f));
+        f.X = static_cast<const char*>(d.X) + (size_t)j0 * sT;
+        f.D = static_cast<const char*>(d.D) + (size_t)j0 * sW;
+        f.Rk = static_cast<const char*>(d.R1);
+        f.U = const_cast<char*>(static_cast<const char*>(d.R2));
+        f.part = reinterpret_cast<double*>(base + p.off_part);
+        f.gpart = reinterpret_cast<double*>(base + p.off_gpart);
+        f.tickets = reinterpret_cast<unsigned*>(base + p.off_tickets);
+        CUDA_TRY(cudaMemcpyAsync(base + p.off_fit, &f, sizeof(f), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // `f` is a stack temporary
+        WlsArgs a;
+        memset(&a, 0, sizeof(a));
+        Geom& g = a.g;
+        g.M = d.M; g.N = ns; g.K = d.K; g.nu = d.K2; g.Kt = d.K + d.K2;
+        g.ldx = d.ldx; g.ldd = d.ldd; g.ldr = d.K ? d.ldr : 0; g.ldu = d.K2 ? d.ldr2 : 0;
+        g.tile_rows = p.tile_rows; g.n_tiles = p.n_tiles; g.ntc = next_pow2(ns); g.rg = kConsumers / g.ntc;
+        // rows of a tile are walked with stride rg: a narrower last slab only changes the thread mapping
+        g.n_parts = p.n_parts; g.n_groups = p.n_groups; g.part_stride = p.part_stride;
+        g.offX = p.offX; g.offD = p.offD; g.offR = p.offR; g.offU = p.offU; g.offUp = p.offU; g.stage_bytes = p.stage_bytes;
+        g.tile_tx[0] = (unsigned)(p.tile_rows * d.ldx * sT);
+        g.tile_tx[1] = (unsigned)(p.tile_rows * d.ldd * sW);
+        g.tile_tx[2] = d.K ? (unsigned)(p.tile_rows * d.ldr * sT) : 0u;
+        g.tile_tx[3] = d.K2 ? (unsigned)(p.tile_rows * d.ldr2 * sT) : 0u;
+        g.tile_tx[4] = 0;
+        a.fits = reinterpret_cast<const FitDev*>(base + p.off_fit);
+        a.mom = reinterpret_cast<double*>(base + p.off_mom);
+        a.Kfull = d.K + d.K2;
+        a.y_is_dx = d.y_is_dx;
+        for (int bi = 0; bi < p.nblk; ++bi)
+            for (int bj = bi; bj < p.nblk; ++bj) {
+                a.bi = bi; a.bj = bj;
+                kern<<<dim3(p.n_parts, 1, 1), kThreads, p.smem, st>>>(a);
+                CUDA_TRY(cudaGetLastError());
+            }
+        wls_nnls_kernel<<<(ns + 63) / 64, 64, 0, st>>>(a.mom, a.Kfull, ns, d.M, d.out + j0, (long long)d.N, reinterpret_cast<int*>(base + p.off_status));
+        CUDA_TRY(cudaGetLastError());
+    }
+    return DMF_OK;
+}
+
+}  // extern "C"

@@ -3,10 +3,13 @@
 #include "dmf_device.cuh"
 namespace dmf {
 typedef void (*kern_t)(const PassArgs);
+struct WlsArgs;
+typedef void (*wls_kern_t)(const WlsArgs);
 #define DMF_DECL(TAG)                                      \
     kern_t pick_cost_##TAG(int ktb, int nub, int c);       \
     kern_t pick_alpha_##TAG(int ktb, int nub, int c);      \
-    kern_t pick_u_##TAG(int ktb, int nub, int c);
+    kern_t pick_u_##TAG(int ktb, int nub, int c);          \
+    wls_kern_t pick_wls_##TAG();
 DMF_DECL(f64_f64) DMF_DECL(f64_u16) DMF_DECL(f32_f32) DMF_DECL(f32_u16)
 #undef DMF_DECL
 }  // namespace dmf

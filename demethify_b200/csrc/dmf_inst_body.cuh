@@ -1,6 +1,7 @@
 // dmf_inst_body.cuh — included by dmf_inst_<tag>.cu with DMF_T, DMF_WT and DMF_TAG defined.
 #include "dmf_inst.h"
 #include "dmf_kernels.cuh"
+#include "dmf_wls.cuh"
 namespace dmf {
 #define DMF_CAT2(a, b) a##b
 #define DMF_CAT(a, b) DMF_CAT2(a, b)
@@ -28,4 +29,5 @@ kern_t DMF_CAT(pick_u_, DMF_TAG)(int kb, int nub, int) {
 #undef DMF_U
     return nullptr;
 }
+wls_kern_t DMF_CAT(pick_wls_, DMF_TAG)() { return wls_moments_kernel<DMF_T, DMF_WT>; }
 }  // namespace dmf

@@ -10,7 +10,7 @@ import numpy.random as rd
 
 from . import _lib
 from .engine import DeviceProblem, FitBatch
-from .init_func import wls_intercept, constrained_nndsvd, nndsvd_initialize
+from .init_func import wls_intercept, wls_all_samples, constrained_nndsvd, nndsvd_initialize
 
 __all__ = ["set_seed", "cost_f_w", "projection_simplex_sort_2d", "init_BSSMF_md", "init_BSSMF_md_p",
            "mdwbssmf_deconv", "mdwbssmf_deconv_p", "unsupervised_deconv", "last_fit_info"]
@@ -65,8 +65,7 @@ def _draw(init_option, meth_frequency, d_x, R_trunc, n_u):
     nb = meth_frequency.shape[1]
     if init_option == "uniform":
         u = rd.uniform(size=(M, n_u))
-        full = np.c_[R_trunc, u]
-        alpha = np.concatenate([wls_intercept(meth_frequency[:, k:k + 1], d_x[:, k:k + 1], full) for k in range(nb)], axis=1)
+        alpha = wls_all_samples(meth_frequency, d_x, R_trunc, extra=u)      # per-sample wls_intercept on [R_trunc | u], :49-52
     elif init_option == "uniform_":
         u = rd.uniform(size=(M, n_u))
         alpha = rd.dirichlet(np.ones(K + n_u), nb).T

@@ -1,0 +1,171 @@
+"""`demethify` command line — drop-in for the reference's demethify/demethify.py:main (same flags, same output files:
+celltypes_proportions.csv, methylation_profile_estimate.csv, confidence_interval_*.csv, log.log), running the
+deconvolution on the B200 kernel library.  Additive flag: --precision {fp64,fp32}.  Plotting is imported lazily
+(matplotlib / seaborn / colorcet are optional)."""
+import argparse
+import os
+import sys
+import warnings
+from time import time
+
+import numpy as np
+import pandas as pd
+
+from . import set_precision
+from .bootstrap import bt_ci
+from .deconvolution import (cost_f_w, init_BSSMF_md, init_BSSMF_md_p, mdwbssmf_deconv, mdwbssmf_deconv_p, unsupervised_deconv)
+from .ic import evaluate_best_ic
+from .init_func import wls_all_samples
+
+warnings.filterwarnings("ignore")
+
+LOGO = r"""
+    ____                      __  __    _ ____
+   / __ \___  ____ ___  ___  / /_/ /_  (_) __/_  __
+  / / / / _ \/ __ `__ \/ _ \/ __/ __ \/ / /_/ / / /
+ / /_/ /  __/ / / / / /  __/ /_/ / / / / __/ /_/ /
+/_____/\___/_/ /_/ /_/\___/\__/_/ /_/_/_/  \__, /   (B200)
+                                          /____/
+"""
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="DeMethify - Partial reference-based Methylation Deconvolution (B200 path)")
+    p.add_argument("--methfreq", nargs="+", type=str, required=True, help="Methylation frequency file path (values between 0 and 1)")
+    p.add_argument("--ref", nargs="?", type=str, help="Methylation reference matrix file path")
+    p.add_argument("--iterations", nargs=2, type=int, help="Numbers of iterations for outer and inner loops (default without purity = 10000, 20, with purity= 100, 500)")
+    p.add_argument("--nbunknown", nargs=1, type=int, help="Number of unknown cell types to estimate ")
+    p.add_argument("--purity", nargs="+", type=float, help="The purities of the samples in percent [0,100], if known")
+    p.add_argument("--termination", nargs=1, type=float, default=1e-2, help="Termination condition for cost function (default = 1e-2)")
+    p.add_argument("--init", nargs="?", default="uniform_", help="Initialisation option, the default is uniform_, and the options are: uniform, uniform_, beta, SVD, ICA. ")
+    p.add_argument("--outdir", nargs="?", required=True, help="Output directory")
+    p.add_argument("--fillna", action="store_true", help="Replace every NA by 0 in the given data")
+    p.add_argument("--ic", nargs="+", help="Select number of unknown cell types by minimising a criterion (AIC, BIC, CCC, BCV, minka)")
+    p.add_argument("--confidence", nargs=2, type=int, help="Outputs bootstrap confidence intervals, takes confidence level and boostrap iteration numbers as input.")
+    p.add_argument("--plot", action="store_true", help="Plot cell type proportions estimates for each sample, eventually with confidence intervals. ")
+    p.add_argument("--restart", nargs=1, type=int, help="Number of random restarts among which to select the one with the lowest cost/highest loglikelihood")
+    p.add_argument("--seed", nargs=1, type=int, default=1, help="Set a seed integer number for random number generation for reproducibility. ")
+    p.add_argument("--noprint", action="store_true", help="Doesnt show the logo.")
+    p.add_argument("--bedmethyl", action="store_true", help="Flag to indicate that the input will be bedmethyl files, modkit style")
+    p.add_argument("--precision", choices=["fp64", "fp32"], default="fp64", help="(B200 path) arithmetic of the solver kernels")
+    return p
+
+
+def read_inputs(args):
+    """demethify.py:103-143 — bedmethyl (tab separated, percent_modified in percent) or csv (fraction) readers."""
+    ref, header = None, []
+    sep = "\t" if args.bedmethyl else ","
+    if args.ref:
+        ref_df = pd.read_csv(args.ref, sep=sep)
+        if args.bedmethyl:
+            ref_df = ref_df.iloc[:, 3:]
+        if args.fillna:
+            ref_df = ref_df.fillna(0)
+        header = list(ref_df.columns)
+        ref = ref_df.values
+    freqs, cov = [], []
+    for path in args.methfreq:
+        t = pd.read_csv(path, sep=sep)
+        if not args.bedmethyl and t.shape[1] == 1:
+            t["valid_coverage"] = 1
+        if args.fillna:
+            t = t.fillna(0)
+        freqs.append(t["percent_modified"].values / 100 if args.bedmethyl else t["percent_modified"].values)
+        cov.append(t["valid_coverage"].values)
+    return np.column_stack(freqs), np.column_stack(cov), ref, header
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    set_precision(args.precision)
+    args.restart = 1 if args.restart is None else args.restart[0]
+    if not args.iterations:
+        args.iterations = [100, 500] if args.purity else [10000, 20]
+    if isinstance(args.termination, list):
+        args.termination = args.termination[0]
+    purity = None
+    if args.purity:
+        purity = np.array(args.purity)
+        if np.any((purity >= 0) & (purity <= 1)):
+            print("Purity is between 0 and 1, are you sure that it's a percentage?")
+        elif np.any((purity < 0) & (purity > 100)):
+            sys.stderr.write("Error: Invalid value for purity, not within [0,100] bounds.")
+            sys.exit(1)
+        purity = 1 - (purity / 100.0)                         # demethify.py:77
+    nb_r = 5
+    if args.ic:
+        if args.nbunknown:
+            sys.stderr.write("Error: --ic cannot be used with --nbunknown.\n")
+            sys.exit(1)
+        if len(args.ic) > 1:
+            nb_r = int(args.ic[1])
+        args.ic = args.ic[0]
+    if not args.noprint:
+        print(LOGO)
+    outdir = os.path.join(os.getcwd(), args.outdir)
+    if not os.path.exists(outdir):
+        print(f"Creating directory {outdir} to store results")
+        os.mkdir(outdir)
+    if args.nbunknown is None:
+        args.nbunknown = [0]
+    n_u = args.nbunknown[0]
+    meth_f, counts, ref, header = read_inputs(args)
+    args.methfreq = [name.split("/")[-1] for name in args.methfreq]
+    it1, it2, tol = args.iterations[0], args.iterations[1], args.termination
+
+    t0 = time()
+    bt_results = None
+    if args.confidence:
+        bt_results = bt_ci(args.confidence[0], args.confidence[1], n_u, meth_f, counts, ref, args.init, it1, it2, tol, header, outdir,
+                           args.methfreq, args.purity, args.seed)
+    list_ic, ic_n_u = None, None
+    ref_estimate = None
+    if args.ic:
+        ref_estimate, proportions, ic_n_u, list_ic = evaluate_best_ic(meth_f, ref, counts, args.init, args.ic, args.seed, iter1=it1,
+                                                                      iter2=it2, tol=tol, n_restarts=nb_r)
+        unknown_header = ["unknown_cell_" + str(i + 1) for i in range(ic_n_u)]
+        header = header + unknown_header
+    elif not args.ref:
+        # demethify.py:167-174: every restart re-seeds with the same seed, so all restarts are the same fit
+        ref_estimate, proportions = unsupervised_deconv(meth_f, n_u, counts, args.init, n_iter1=it1, n_iter2=it2, tol=tol, seed=args.seed)
+        unknown_header = ["unknown_cell_" + str(i + 1) for i in range(n_u)]
+        header = unknown_header
+    elif n_u > 0 and meth_f.shape[1] >= 1:
+        if args.purity:
+            u, R, alpha = init_BSSMF_md_p(args.init, meth_f, counts, ref, n_u, purity, seed=args.seed)
+            ref_estimate, proportions = mdwbssmf_deconv_p(u, R, alpha, meth_f, counts, ref, n_u, purity, n_iter1=it1, n_iter2=it2, tol=tol)
+        else:
+            u, R, alpha = init_BSSMF_md(args.init, meth_f, counts, ref, n_u, seed=args.seed)
+            ref_estimate, proportions = mdwbssmf_deconv(u, R, alpha, meth_f, counts, ref, n_u, n_iter1=it1, n_iter2=it2, tol=tol)
+        unknown_header = ["unknown_cell_" + str(i + 1) for i in range(n_u)]
+        header = header + unknown_header
+    elif n_u == 0 and meth_f.shape[1] >= 1:
+        proportions = wls_all_samples(meth_f, counts, ref, y_is_dx=True)          # demethify.py:209-213
+        unknown_header = []
+    else:
+        sys.exit(f'Invalid number of unknown value! : "{args.nbunknown}" ')
+    if ref_estimate is not None:
+        pd.DataFrame(ref_estimate).to_csv(outdir + "/methylation_profile_estimate.csv", index=False, header=unknown_header)
+    time_tot = time() - t0
+
+    proportions = pd.DataFrame(proportions)
+    proportions.index = header
+    proportions.columns = args.methfreq
+    proportions.index.name = "Cell types"
+    proportions.to_csv(outdir + "/celltypes_proportions.csv", index=True)
+    print("All demethified! Results in " + outdir)
+    with open(os.path.join(outdir, "log.log"), "w+") as f:
+        f.write("Total execution time = " + str(time_tot) + " s" + "\n")
+        if args.ic:
+            f.write("Number of unknowns that minimises " + args.ic + " : " + str(ic_n_u))
+    if args.plot:
+        try:
+            from .plotting import plot_proportions
+        except ImportError as e:
+            sys.stderr.write(f"--plot needs matplotlib / seaborn / colorcet ({e}); results were written without plots\n")
+        else:
+            plot_proportions(proportions, bt_results[0] if bt_results else pd.DataFrame(), outdir, list_ic)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,11 @@ def _tdtype(precision):
     return torch.float64 if precision == "fp64" else torch.float32
 
 
+def device_free_bytes(device):
+    free, _total = torch.cuda.mem_get_info(device)
+    return int(free)
+
+
 def _even(n):
     return n + (n & 1)
 
@@ -116,6 +121,33 @@ class DeviceProblem:
                 self.D, self.wtype = packed, _lib.DMF_W_U16
         if self.D is None:
             self.D = _pad_cols(raw.to(self.dtype), self.ldx)
+
+    def masked(self, mask):
+        """Problem with weights d_x * mask (BCV training folds, ic.py:75): zero weight == entry left out, so X is shared."""
+        m = to_device(np.ascontiguousarray(mask), None, self.device)
+        if self.D.dtype == torch.uint16:        # 0/1 multiply through the int16 view (bit-exact for every u16 value)
+            m = _pad_cols(m.to(torch.int16), self.ldx)
+            return self.with_weights((self.D.view(torch.int16) * m).view(torch.uint16), self.wtype)
+        m = _pad_cols(m.to(self.D.dtype), self.ldx)
+        return self.with_weights(self.D * m, self.wtype)
+
+    def gathered(self, idx):
+        """New problem holding rows idx of X, d_x, R_trunc (row gather kernel of the library; bootstrap.py:28)."""
+        rows = to_device(np.asarray(idx, dtype=np.int32), torch.int32, self.device)
+        other = object.__new__(DeviceProblem)
+        other.__dict__.update(self.__dict__)
+        n = rows.numel()
+        lib = _lib.lib()
+
+        def take(t):
+            out = torch.empty((n, t.shape[1]), dtype=t.dtype, device=t.device)
+            _lib.check(lib.dmf_gather_rows(C.c_void_p(t.data_ptr()), C.c_void_p(rows.data_ptr()), n, t.shape[1], t.element_size(),
+                                           C.c_void_p(out.data_ptr()), _stream_ptr()))
+            return out
+        other.X, other.D = take(self.X), take(self.D)
+        other.Rk = take(self.Rk) if self.Rk is not None else None
+        other.M = n
+        return other
 
     def with_weights(self, D_tensor, wtype):
         """Shallow copy sharing X / R_trunc with different weights (BCV folds, ic.py:75)."""

@@ -134,6 +134,28 @@ int dmf_batch_read_state(dmf_batch_t b, dmf_fit_state_t* out_host, int32_t n, vo
 /* number of kernel launches issued through this batch since creation */
 int dmf_batch_launch_count(dmf_batch_t b, int64_t* out);
 
+/* reference-based fit ---------------------------------------------------------------------------- */
+/* wls_intercept (init_func.py:8-14) for every sample column at once:
+ *   out[:, j] = c_j / max(sum c_j, 1e-10),  c_j = argmin_{c >= 0, b} sum_m D[m,j] (y[m,j] - [R1|R2][m,:] c - b)^2
+ * with y = X (y_is_dx = 0; the `uniform` / SVD inits, deconvolution.py:51, init_func.py:23) or y = D o X
+ * (y_is_dx = 1; the nbunknown = 0 path, demethify.py:212 and bootstrap.py:42).  R2 (M x K2, pitch ldr2) is an
+ * optional second block of regressors (the unknown profiles u in deconvolution.py:51), NULL when K2 = 0.
+ * Same pitch rules as dmf_shape_t (even, zero padded).  out is a DEVICE buffer of (K + K2) x N doubles. */
+typedef struct dmf_wls_desc {
+    int64_t M;
+    int32_t N, K, K2;
+    int32_t dtype, wtype;
+    int32_t y_is_dx, reserved;
+    int64_t ldx, ldd, ldr, ldr2;
+    const void* X;
+    const void* D;
+    const void* R1;
+    const void* R2;
+    double* out;
+} dmf_wls_desc_t;
+int dmf_wls_workspace_bytes(dmf_handle_t h, const dmf_wls_desc_t* d, size_t* bytes);
+int dmf_wls_fit(dmf_handle_t h, const dmf_wls_desc_t* d, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* utilities ------------------------------------------------------------------------------------ */
 /* narrow fp64/fp32/int64 coverage to u16 with range/integrality check; *bad receives the number of
  * entries that are not integers in [0, 65535] (device int32) */

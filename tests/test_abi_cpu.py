@@ -32,13 +32,14 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_layouts_match_header(built, tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "demethify_b200.h"\nint main(){printf("%zu %zu %zu\\n",'
-                   'sizeof(dmf_shape_t),sizeof(dmf_fit_desc_t),sizeof(dmf_fit_state_t));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "demethify_b200.h"\nint main(){printf("%zu %zu %zu ",'
+                   'sizeof(dmf_shape_t),sizeof(dmf_fit_desc_t),sizeof(dmf_fit_state_t));'
+                   'printf("%zu\\n",sizeof(dmf_wls_desc_t));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     import ctypes as C
-    assert sizes == [C.sizeof(built.Shape), C.sizeof(built.FitDesc), C.sizeof(built.FitState)]
+    assert sizes == [C.sizeof(built.Shape), C.sizeof(built.FitDesc), C.sizeof(built.FitState), C.sizeof(built.WlsDesc)]
 
 
 def test_no_cpu_fallback_without_gpu(built):
