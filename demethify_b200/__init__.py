@@ -19,3 +19,22 @@ def set_precision(mode):
 
 def get_precision():
     return _PRECISION
+
+
+_ENGINE = "auto"
+
+
+def set_engine(mode):
+    """How the inner iterations run on the device (include/demethify_b200.h, DMF_ENGINE_*):
+    'stream' = one streaming pass over X, d_x per reference inner iteration;
+    'gram'   = two streaming passes per OUTER iteration build per-row / per-sample sufficient statistics and the
+               n_iter2 inner iterations run on those (n_u <= 4);
+    'auto'   = 'gram' where the library supports the shape, else 'stream' (default)."""
+    global _ENGINE
+    if mode not in ("auto", "gram", "stream"):
+        raise ValueError("engine must be 'auto', 'gram' or 'stream'")
+    _ENGINE = mode
+
+
+def get_engine():
+    return _ENGINE

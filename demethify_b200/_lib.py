@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, "libdemethify_sm100.so")
 DMF_F64, DMF_F32 = 0, 1
 DMF_W_FLOAT, DMF_W_U16 = 0, 1
 DMF_MODE_PARTIAL, DMF_MODE_PURITY, DMF_MODE_UNSUPERVISED = 0, 1, 2
+DMF_ENGINE_STREAM, DMF_ENGINE_GRAM = 0, 1
+ABI_VERSION = 2
 
 
 class Shape(C.Structure):
@@ -55,6 +57,14 @@ EXPORTS = {
     "dmf_pass_alpha": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dmf_pass_fw": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "dmf_pass_cost": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "dmf_batch_set_engine": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dmf_batch_get_engine": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "dmf_gram_rowgram": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
+    "dmf_gram_u_inner": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dmf_gram_panels": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dmf_gram_alpha_inner": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dmf_gram_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dmf_gram_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_enqueue_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_fit_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_batch_read_state": (C.c_int, [C.c_void_p, C.POINTER(FitState), C.c_int32, C.c_void_p]),
@@ -83,7 +93,7 @@ def lib():
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)        # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.dmf_abi_version() != 1:
+        if handle.dmf_abi_version() != ABI_VERSION:
             raise DmfError("libdemethify_sm100.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -47,6 +47,12 @@ struct dmf_batch_s {
     int occ;
     long long launches;
     FitState* pinned;       // host staging for state polling
+    // Gram-form engine (dmf_gram.cuh)
+    int engine;             // DMF_ENGINE_*
+    int gram_ok;            // this shape has Gram-engine instantiations
+    Geom gg;                // tile geometry of the Gram-engine streaming passes (no u_prev in the stage)
+    int kb_g, nub_g, c_g, ntc_g, pb_g, c_p, ntc_p, ktb_in;
+    unsigned smem_rg, smem_panel;
 };
 
 namespace {
@@ -60,6 +66,10 @@ kern_t by_types(const dmf_shape_t& s, kern_t (*f[4])(int, int, int), int a, int 
 kern_t (*g_cost[4])(int, int, int) = {pick_cost_f64_f64, pick_cost_f64_u16, pick_cost_f32_f32, pick_cost_f32_u16};
 kern_t (*g_alpha[4])(int, int, int) = {pick_alpha_f64_f64, pick_alpha_f64_u16, pick_alpha_f32_f32, pick_alpha_f32_u16};
 kern_t (*g_u[4])(int, int, int) = {pick_u_f64_f64, pick_u_f64_u16, pick_u_f32_f32, pick_u_f32_u16};
+kern_t (*g_rowgram[4])(int, int, int) = {pick_rowgram_f64_f64, pick_rowgram_f64_u16, pick_rowgram_f32_f32, pick_rowgram_f32_u16};
+kern_t (*g_panel[4])(int, int, int) = {pick_panel_f64_f64, pick_panel_f64_u16, pick_panel_f32_f32, pick_panel_f32_u16};
+kern_t (*g_uinner[4])(int, int, int) = {pick_uinner_f64_f64, pick_uinner_f64_u16, pick_uinner_f32_f32, pick_uinner_f32_u16};
+kern_t (*g_ainner[4])(int, int, int) = {pick_ainner_f64_f64, pick_ainner_f64_u16, pick_ainner_f32_f32, pick_ainner_f32_u16};
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -72,7 +82,15 @@ struct Plan {
     int tile_rows, n_tiles, n_parts, n_groups, part_stride, occ;
     unsigned offX, offD, offR, offU, offUp, stage_bytes, smem_alpha, smem_u, smem_cost, row_bulk;
     size_t ws_bytes, off_fits, off_states, off_tickets, off_part, off_gpart, per_fit_tickets, per_fit_part, per_fit_gpart;
+    // Gram engine
+    int gram_ok, kb_g, nub_g, c_g, rpt_g_max, rpt_g, ntc_g, occ_g, pb_g, c_p, ntc_p, ktb_in;
+    int tile_rows_g, n_tiles_g, n_parts_g, n_groups_g, wpr_g, ng_g;
+    unsigned g_offX, g_offD, g_offR, g_offU, g_stage_bytes, smem_rg, smem_panel;
+    size_t off_rowgram, off_gram, off_gbx, off_red, per_fit_rowgram, per_fit_gram, per_fit_gbx, per_fit_red;
 };
+
+constexpr int pow2ceil_h(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+constexpr int ng_of_h(int nub) { return nub + nub * (nub + 1) / 2; }
 
 // U-pass instantiations (dmf_inst_body.cuh): known bucket, unknown bucket, columns/thread, rows/thread/tile
 struct UEntry { int kb, nub, c, rpt; };
@@ -160,16 +178,84 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     p.smem_cost = (unsigned)std::max(pipe, (size_t)kCtlBytes + 512);
     if (std::max(p.smem_alpha, p.smem_u) > smem_cap) return fail(DMF_E_SHAPE, "shared-memory plan exceeds the device limit");
 
+    // ---- Gram-form engine (dmf_gram.cuh): n_u <= 4, own tile geometry (no u_prev in the stage, rows per thread from kGramTable)
+    p.gram_ok = 0;
+    p.n_parts_g = p.n_groups_g = 0;
+    p.per_fit_rowgram = p.per_fit_gram = p.per_fit_gbx = p.per_fit_red = 0;
+    if (s.n_u <= 4) {
+        p.kb_g = s.K == 0 ? 0 : (p.Kp <= 6 ? 6 : (p.Kp <= 16 ? 16 : 32));
+        p.nub_g = s.n_u == 1 ? 1 : (s.n_u == 2 ? 2 : 4);
+        p.c_g = p.kb_g <= 16 ? 2 : 1;
+        p.rpt_g_max = p.nub_g == 1 ? 4 : (p.nub_g == 2 ? 3 : 2);
+        p.ng_g = ng_of_h(p.nub_g);
+        p.pb_g = rowlen <= 8 ? 8 : 16;
+        p.c_p = p.pb_g == 8 ? 2 : 1;
+        p.ktb_in = Kt <= 8 ? 8 : (Kt <= 16 ? 16 : 32);
+        if (s.N <= kConsumers * p.c_g && s.N <= kConsumers * p.c_p) {
+            p.ntc_g = next_pow2((s.N + p.c_g - 1) / p.c_g);
+            p.ntc_p = next_pow2((s.N + p.c_p - 1) / p.c_p);
+            p.wpr_g = (p.ntc_g + 31) / 32;
+            const int rg_g = kConsumers / p.ntc_g;
+            // must mirror the __launch_bounds__ of rowgram_kernel / gram_panel_kernel
+            const int occ_rg = ((p.kb_g + 2 * p.nub_g) * p.c_g + 2 * pow2ceil_h(p.rpt_g_max * p.ng_g) <= 56) ? 2 : 1;
+            const int occ_pn = (2 * (p.pb_g + 1) * p.c_p <= 40) ? 2 : 1;
+            p.occ_g = std::min(occ_rg, occ_pn);
+            auto a128g = [](size_t v) { return align_up(v, 128); };
+            auto stage_g = [&](long long tr) { return a128g(tr * px) + a128g(tr * pd) + a128g(tr * pr) + a128g(tr * pu); };
+            const size_t epi_panel = kCtlBytes + (size_t)(p.pb_g + 1) * s.N * 8 + 256;
+            p.rpt_g = 0;
+            for (int attempt = 0; attempt < 2 && !p.rpt_g; ++attempt) {
+                const size_t budget = (p.occ_g == 2 ? std::min<size_t>(smem_cap, 112 * 1024) : std::min<size_t>(smem_cap, 220 * 1024)) - kCtlBytes - 1024;
+                for (int rpt = p.rpt_g_max; rpt >= 1; --rpt) {
+                    const long long trg = (long long)rpt * rg_g;
+                    if (trg % ra) continue;
+                    if (stage_g(trg) * kStages <= budget && epi_panel <= budget + kCtlBytes) { p.rpt_g = rpt; break; }
+                }
+                if (!p.rpt_g) {
+                    if (p.occ_g == 2) p.occ_g = 1; else break;
+                }
+            }
+            if (p.rpt_g) {
+                const long long trg = (long long)p.rpt_g * rg_g;
+                p.tile_rows_g = (int)trg;
+                p.n_tiles_g = (int)((s.M + trg - 1) / trg);
+                p.g_offX = 0;
+                p.g_offD = (unsigned)a128g(p.g_offX + trg * px);
+                p.g_offR = (unsigned)a128g(p.g_offD + trg * pd);
+                p.g_offU = (unsigned)a128g(p.g_offR + trg * pr);
+                p.g_stage_bytes = (unsigned)a128g(p.g_offU + trg * pu);
+                long long per_fit_g = std::max<long long>(1, (long long)h->sm_count * p.occ_g / s.n_fits);
+                if (s.max_ctas_per_fit > 0) per_fit_g = std::min<long long>(per_fit_g, s.max_ctas_per_fit);
+                p.n_parts_g = (int)std::min<long long>(per_fit_g, p.n_tiles_g);
+                p.n_groups_g = (p.n_parts_g + kGroup - 1) / kGroup;
+                const size_t pipe_g = kCtlBytes + (size_t)kStages * p.g_stage_bytes;
+                p.smem_rg = (unsigned)std::max(pipe_g, (size_t)kCtlBytes + 512);
+                p.smem_panel = (unsigned)std::max(pipe_g, epi_panel);
+                p.part_stride = std::max(p.part_stride, (int)align_up((size_t)2 * (p.pb_g + 1) * s.N, 2));
+                p.per_fit_rowgram = align_up((size_t)s.M * p.wpr_g * p.ng_g * 8, 256);
+                p.per_fit_gram = align_up((size_t)Kt * Kt * s.N * 8, 256);
+                p.per_fit_gbx = align_up((size_t)Kt * s.N * 8, 256);
+                p.per_fit_red = align_up((size_t)p.part_stride * 8, 256);
+                p.gram_ok = 1;
+            }
+        }
+    }
+    const int parts_max = std::max(p.n_parts, p.n_parts_g), groups_max = std::max(p.n_groups, p.n_groups_g);
+
     // workspace layout
     p.off_fits = 0;
     p.off_states = align_up(p.off_fits + sizeof(FitDev) * s.n_fits, 256);
-    p.per_fit_tickets = align_up(sizeof(unsigned) * (p.n_groups + 1), 128);
-    p.per_fit_part = align_up((size_t)p.n_parts * p.part_stride * 8, 128);
-    p.per_fit_gpart = align_up((size_t)p.n_groups * p.part_stride * 8, 128);
+    p.per_fit_tickets = align_up(sizeof(unsigned) * (groups_max + 1), 128);
+    p.per_fit_part = align_up((size_t)parts_max * p.part_stride * 8, 128);
+    p.per_fit_gpart = align_up((size_t)groups_max * p.part_stride * 8, 128);
     p.off_tickets = align_up(p.off_states + sizeof(FitState) * s.n_fits, 256);
     p.off_part = align_up(p.off_tickets + p.per_fit_tickets * s.n_fits, 256);
     p.off_gpart = align_up(p.off_part + p.per_fit_part * s.n_fits, 256);
-    p.ws_bytes = align_up(p.off_gpart + p.per_fit_gpart * s.n_fits, 256);
+    p.off_rowgram = align_up(p.off_gpart + p.per_fit_gpart * s.n_fits, 256);
+    p.off_gram = p.off_rowgram + p.per_fit_rowgram * s.n_fits;
+    p.off_gbx = p.off_gram + p.per_fit_gram * s.n_fits;
+    p.off_red = p.off_gbx + p.per_fit_gbx * s.n_fits;
+    p.ws_bytes = align_up(p.off_red + p.per_fit_red * s.n_fits, 256);
     return DMF_OK;
 }
 
@@ -189,6 +275,7 @@ int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_in
     a.k_inner = k_inner;
     a.flags = flags;
     a.tol = tol;
+    a.ca0 = a.cb0 = a.with_x = a.pad = 0;
     dim3 grid(b->g.n_parts, b->shape.n_fits, 1);
     k<<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -199,6 +286,30 @@ int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_in
 kern_t k_cost(dmf_batch_s* b, int initial) { return by_types(b->shape, g_cost, b->ktb, initial, b->c_alpha); }
 kern_t k_alpha(dmf_batch_s* b) { return by_types(b->shape, g_alpha, b->ktb, 0, b->c_alpha); }
 kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->kb, b->nub, b->c_u); }
+kern_t k_rowgram(dmf_batch_s* b, int initial) { return by_types(b->shape, g_rowgram, b->kb_g, b->nub_g, initial); }
+kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, 0, 0); }
+kern_t k_uinner(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 0, 0); }
+kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in, 0, 0); }
+
+// Gram-engine launch: geometry gg; ntc selects the thread mapping of the kernel; grid_x CTAs per fit (0: one CTA per fit on grid.x)
+int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_inner, double tol, int ca0, int cb0, int with_x,
+             bool per_fit_grid, cudaStream_t st) {
+    if (!k) return fail(DMF_E_SHAPE, "no Gram-engine kernel instantiation for this shape");
+    PassArgs a;
+    a.g = b->gg;
+    a.g.ntc = ntc;
+    a.g.rg = kConsumers / ntc;
+    a.fits = b->fits_dev;
+    a.k_inner = k_inner;
+    a.flags = flags;
+    a.tol = tol;
+    a.ca0 = ca0; a.cb0 = cb0; a.with_x = with_x; a.pad = 0;
+    dim3 grid = per_fit_grid ? dim3(b->shape.n_fits, 1, 1) : dim3(b->gg.n_parts, b->shape.n_fits, 1);
+    k<<<grid, kThreads, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    return DMF_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // small utility kernels
@@ -312,6 +423,10 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         f.gpart = reinterpret_cast<double*>(base + p.off_gpart + p.per_fit_gpart * i);
         f.tickets = reinterpret_cast<unsigned*>(base + p.off_tickets + p.per_fit_tickets * i);
         f.st = reinterpret_cast<FitState*>(base + p.off_states) + i;
+        f.rowgram = p.gram_ok ? reinterpret_cast<double*>(base + p.off_rowgram + p.per_fit_rowgram * i) : nullptr;
+        f.gram = p.gram_ok ? reinterpret_cast<double*>(base + p.off_gram + p.per_fit_gram * i) : nullptr;
+        f.gbx = p.gram_ok ? reinterpret_cast<double*>(base + p.off_gbx + p.per_fit_gbx * i) : nullptr;
+        f.red = p.gram_ok ? reinterpret_cast<double*>(base + p.off_red + p.per_fit_red * i) : nullptr;
         f.pad = 0;
     }
     dmf_batch_s* b = new dmf_batch_s;
@@ -341,6 +456,30 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->smem_alpha = p.smem_alpha; b->smem_u = p.smem_u; b->smem_cost = p.smem_cost; b->occ = p.occ;
     b->fits_dev = reinterpret_cast<FitDev*>(base + p.off_fits);
     b->states_dev = reinterpret_cast<FitState*>(base + p.off_states);
+    b->gram_ok = p.gram_ok;
+    b->engine = p.gram_ok ? DMF_ENGINE_GRAM : DMF_ENGINE_STREAM;
+    if (p.gram_ok) {
+        Geom& q = b->gg;
+        q = g;
+        q.rpt = p.rpt_g;
+        q.tile_rows = p.tile_rows_g; q.n_tiles = p.n_tiles_g;
+        q.ntc = p.ntc_g; q.rg = kConsumers / p.ntc_g;
+        q.n_parts = p.n_parts_g; q.n_groups = p.n_groups_g;
+        q.offX = p.g_offX; q.offD = p.g_offD; q.offR = p.g_offR; q.offU = p.g_offU; q.offUp = p.g_offU; q.stage_bytes = p.g_stage_bytes;
+        const unsigned sT = s.dtype == DMF_F64 ? 8 : 4, sW = s.wtype == DMF_W_U16 ? 2 : sT;
+        q.tile_tx[0] = (unsigned)(p.tile_rows_g * s.ldx * sT);
+        q.tile_tx[1] = (unsigned)(p.tile_rows_g * s.ldd * sW);
+        q.tile_tx[2] = s.K ? (unsigned)(p.tile_rows_g * s.ldr * sT) : 0u;
+        q.tile_tx[3] = (unsigned)(p.tile_rows_g * s.ldu * sT);
+        q.tile_tx[4] = 0;
+        b->kb_g = p.kb_g; b->nub_g = p.nub_g; b->c_g = p.c_g; b->ntc_g = p.ntc_g; b->pb_g = p.pb_g; b->c_p = p.c_p; b->ntc_p = p.ntc_p;
+        b->ktb_in = p.ktb_in; b->smem_rg = p.smem_rg; b->smem_panel = p.smem_panel;
+        if ((rc = set_smem(k_rowgram(b, 0), b->smem_rg)) || (rc = set_smem(k_rowgram(b, 1), b->smem_rg)) || (rc = set_smem(k_panel(b), b->smem_panel)) ||
+            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0))) {
+            delete b;
+            return rc;
+        }
+    }
     if ((rc = set_smem(k_cost(b, 0), b->smem_cost)) || (rc = set_smem(k_cost(b, 1), b->smem_cost)) || (rc = set_smem(k_alpha(b), b->smem_alpha)) ||
         (rc = set_smem(k_u(b), b->smem_u))) {
         delete b;
@@ -397,9 +536,69 @@ int dmf_pass_fw(dmf_batch_t b, int32_t k_inner, void* stream) {
     return launch(b, k_alpha(b), b->ntc_alpha, b->smem_alpha, kFlagFW, k_inner, 0.0, (cudaStream_t)stream);
 }
 
+int dmf_batch_set_engine(dmf_batch_t b, int32_t engine) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (engine != DMF_ENGINE_STREAM && engine != DMF_ENGINE_GRAM) return fail(DMF_E_ARG, "engine must be DMF_ENGINE_STREAM or DMF_ENGINE_GRAM");
+    if (engine == DMF_ENGINE_GRAM && !b->gram_ok) return fail(DMF_E_SHAPE, "the Gram-form engine supports n_u <= 4 (and needs its tile to fit in shared memory)");
+    b->engine = engine;
+    return DMF_OK;
+}
+int dmf_batch_get_engine(dmf_batch_t b, int32_t* engine) {
+    if (!b || !engine) return fail(DMF_E_ARG, "NULL argument");
+    *engine = b->engine;
+    return DMF_OK;
+}
+
+int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    return launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, false, (cudaStream_t)stream);
+}
+int dmf_gram_u_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    return launch_g(b, k_uinner(b), b->ntc_g, 0, 0, n_iter2, 0.0, 0, 0, 0, false, (cudaStream_t)stream);
+}
+int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    const int nR = b->gg.Kp >> 1, nU = b->gg.nup >> 1, nb = b->pb_g / 2;
+    const int ca_lo = known_block ? 0 : nR, ca_hi = known_block ? nR : nR + nU;
+    const int cb_hi = known_block ? nR : nR + nU;
+    int rc;
+    for (int ca = ca_lo; ca < ca_hi; ++ca)
+        for (int cb = 0; cb < cb_hi; cb += nb)
+            if ((rc = launch_g(b, k_panel(b), b->ntc_p, b->smem_panel, 0, 0, 0.0, ca, cb, cb == 0 ? 1 : 0, false, (cudaStream_t)stream))) return rc;
+    return DMF_OK;
+}
+int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    return launch_g(b, k_ainner(b), b->ntc_p, 0, b->shape.mode == DMF_MODE_PURITY ? kFlagFW : 0, n_iter2, 0.0, 0, 0, 0, true, (cudaStream_t)stream);
+}
+int dmf_gram_init(dmf_batch_t b, void* stream) {
+    int rc = dmf_gram_rowgram(b, 1, 0.0, stream);
+    if (rc) return rc;
+    return b->shape.K ? dmf_gram_panels(b, 1, stream) : DMF_OK;
+}
+int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
+    int rc;
+    if (n_iter2 > 0) {
+        if ((rc = dmf_gram_u_inner(b, n_iter2, stream))) return rc;
+        if ((rc = dmf_gram_panels(b, 0, stream))) return rc;
+        if ((rc = dmf_gram_alpha_inner(b, n_iter2, stream))) return rc;
+    }
+    return dmf_gram_rowgram(b, 0, tol, stream);
+}
+
 int dmf_enqueue_outer(dmf_batch_t b, int32_t n_outer, int32_t n_iter2, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     int rc;
+    if (b->engine == DMF_ENGINE_GRAM) {
+        for (int o = 0; o < n_outer; ++o)
+            if ((rc = dmf_gram_outer(b, n_iter2, tol, stream))) return rc;
+        return DMF_OK;
+    }
     for (int o = 0; o < n_outer; ++o) {
         for (int i = 0; i < n_iter2; ++i)
             if ((rc = dmf_pass_u(b, stream))) return rc;
@@ -429,7 +628,7 @@ int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol,
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (n_iter1 < 0 || n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = dmf_pass_init(b, stream);
+    int rc = b->engine == DMF_ENGINE_GRAM ? dmf_gram_init(b, stream) : dmf_pass_init(b, stream);
     if (rc) return rc;
     // Outer iterations are enqueued in chunks; after each chunk the per-fit `done` flags come back through
     // pinned memory.  Terminated fits skip their launches on the device, so over-enqueueing is harmless.

@@ -41,6 +41,10 @@ struct FitDev {
     double* gpart;       // [n_groups][part_stride] per-group partial sums
     unsigned* tickets;   // [n_groups + 1]
     FitState* st;
+    double* rowgram;     // Gram engine: [M][warps per row][NG] per-row statistics of the U step
+    double* gram;        // Gram engine: [Kt][Kt][N] per-sample G_j = R^T diag(d_.j) R
+    double* gbx;         // Gram engine: [Kt][N]     per-sample R^T (d_.j o x_.j)
+    double* red;         // Gram engine: [part_stride] totals of the last cross-CTA reduction
     int trace_cap;
     int pad;
 };
@@ -68,9 +72,12 @@ struct Geom {
 struct PassArgs {
     Geom g;
     const FitDev* fits;
-    int k_inner;      // Frank-Wolfe iteration index
+    int k_inner;      // Frank-Wolfe iteration index (reference-shaped pass) / n_iter2 (Gram-engine inner kernels)
     int flags;        // kFlag*
     double tol;
+    int ca0, cb0;     // gram_panel_kernel: first chunk (pair of padded register-row entries) of the za / zb blocks
+    int with_x;       // gram_panel_kernel: also emit R^T (d o x) for the za block
+    int pad;
 };
 constexpr int kFlagInitial = 1;   // init_cost_kernel: set-up pass (norms, max d, no termination test)
 constexpr int kFlagFW = 2;        // alpha_pass_kernel: Frank-Wolfe step instead of projected gradient

@@ -1,0 +1,578 @@
+// dmf_gram.cuh — "Gram-form" engine: the same outer iteration as deconvolution.py:206-221 / :320-335, restated so that
+// the n_iter2 inner iterations of update_u (:82-89) and update_alpha (:94-101) / frank_wolfe_nmf (:285-299) run on
+// small sufficient statistics instead of re-streaming X and d_x 2 * n_iter2 times:
+//
+//   U step   (alpha frozen)  gradient row m:  (d o (c - u_g a_u)) a_u^T  =  b_m - H_m u_g        c = x - R_trunc a_k
+//                            b_m[q]    = sum_j d_mj c_mj a_u[q,j]          (n_u values per row)
+//                            H_m[q,q'] = sum_j d_mj a_u[q,j] a_u[q',j]     (n_u (n_u+1)/2 values per row)
+//   alpha step (R frozen)    gradient col j:  R^T (d o (x - R a_t))      =  bx_j - G_j a_t
+//                            G_j = R^T diag(d_.j) R  (Kt x Kt),  bx_j = R^T (d_.j o x_.j)
+//
+//   rowgram_kernel     ONE streaming pass: b_m, H_m for every row + cost_f_w of the current iterate (direct form,
+//                      so the |cf - cf_0| < tol test sees the same number as the reference-shaped cost pass)
+//   u_inner_kernel     n_iter2 update_u iterations per row on (b_m, H_m): row-local, no streaming of X
+//   gram_panel_kernel  ONE streaming pass: the blocks of G_j, bx_j that involve u (the known x known block and
+//                      the known part of bx are invariant and computed once at set-up)
+//   alpha_inner_kernel n_iter2 update_alpha (with simplex projection) or Frank-Wolfe iterations per sample on (G_j, bx_j)
+//
+// An outer iteration is 2 streaming passes + 2 small kernels instead of 2 n_iter2 + 1 streaming passes.  The sums are
+// re-associated with respect to the reference (fp64, fixed order), which moves alpha by ~1e-15; the termination test
+// uses the directly computed cost.  Parity is pinned by the same golden vectors as the reference-shaped passes.
+#pragma once
+#include "dmf_kernels.cuh"
+
+namespace dmf {
+
+__host__ __device__ constexpr int ng_of(int nub) { return nub + nub * (nub + 1) / 2; }
+__host__ __device__ constexpr int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+__host__ __device__ constexpr int tri_index(int q, int q2, int nub) { return q * nub - q * (q - 1) / 2 + (q2 - q); }   // q <= q2
+
+// ------------------------------------------------------------------------------------------------
+// shared by cost_kernel-style epilogues: CTA partial [cost, ssq_rk, ssq_u, dmax] -> fit state
+template <bool INITIAL>
+__device__ __forceinline__ void cost_state_update(const Geom& g, const FitDev& f, FitState* st, const double* rec, const void* Acur_v,
+                                                  bool f32, double tol) {
+    const double cf = rec[0];
+    if (INITIAL) {
+        double dm = 0.0;
+        for (int p = 0; p < g.n_parts; ++p) dm = fmax(dm, __ldcg(&f.part[(size_t)p * g.part_stride + 3]));
+        st->dmax = dm;
+        st->dmax2 = dm * dm;
+        st->ssq_rk = rec[1];
+        st->ssq_u = rec[2];
+        double sa = 0.0;                       // ||alpha[-n_u:]||_F^2, deconvolution.py:198
+        for (int q = 0; q < g.nu; ++q)
+            for (int j = 0; j < g.N; ++j) {
+                const size_t idx = (size_t)(g.K + q) * g.N + j;
+                const double v = f32 ? (double)reinterpret_cast<const float*>(Acur_v)[idx] : reinterpret_cast<const double*>(Acur_v)[idx];
+                sa = fma(v, v, sa);
+            }
+        const double na = sqrt(sa), nr = sqrt(rec[1] + rec[2]);
+        st->l_w = (na * na) * st->dmax2;
+        st->l_w_old = st->l_w;
+        st->l_h = (nr * nr) * st->dmax2;
+        st->l_h_old = st->l_h;
+        st->a1 = 1.0;
+        st->a2 = 1.0;
+        st->cf = cf;
+        st->cf_prev = cf;
+        st->n_outer = 0;
+        if (f.trace && f.trace_cap > 0) f.trace[0] = cf;
+    } else {
+        const double prev = st->cf;
+        st->cf_prev = prev;
+        st->cf = cf;
+        const int n = st->n_outer + 1;
+        st->n_outer = n;
+        if (f.trace && n < f.trace_cap) f.trace[n] = cf;
+        if (fabs(cf - prev) < tol) st->done = 1;      // deconvolution.py:220
+        if (!(cf == cf)) st->done = 3;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rowgram pass.  Thread (row group gr, column thread tc) owns C adjacent columns and RPT rows of the tile; the per-row
+// values [b (NUB) | H upper triangle] are summed over the column threads of a warp with the transposed butterfly and
+// written per warp:  rowgram[row][warp-in-row][NG]  (u_inner_kernel adds the <= 8 per-warp partials in fixed order).
+template <typename T, typename WT, int KB, int NUB, int C, int RPT, bool INITIAL>
+__global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(RPT * ng_of(NUB)) <= 56) ? 2 : 1) rowgram_kernel(const PassArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NG = ng_of(NUB);
+    constexpr int NVP = pow2ceil(RPT * NG);
+    const Geom& g = a.g;
+    const FitDev f = a.fits[blockIdx.y];
+    FitState* st = f.st;
+    if (st->done) return;
+    CtaCtx c;
+    cta_setup(g, smem, c);
+    unsigned char* stages = smem + kCtlBytes;
+    const uint32_t stages32 = smem_u32(stages);
+    const int ucur = st->u_cur, acur = st->a_cur;
+    const T* Acur = reinterpret_cast<const T*>(f.A) + (size_t)acur * g.Kt * g.N;
+    const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
+
+    double cost = 0.0, ssq_r = 0.0, ssq_u = 0.0, dmx = 0.0;
+    constexpr int NSRC = 4;
+    if (threadIdx.x == 0) {
+        TileSrc* src = c.ctl->src;
+        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
+        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
+        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
+        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+    }
+    __syncthreads();
+    Ring pr, cr;
+    pr.init(stages32);
+    cr.init(stages32);
+    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    {
+        const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
+        const bool colvalid = C * tc < g.N;
+        const int j0 = colvalid ? C * tc : 0;
+        const int L = min(g.ntc, 32);
+        const int wpr = (g.ntc + 31) / 32;
+        const int wir = tc >> 5;
+        T ak[KB > 0 ? KB : 1][C];
+        T au[NUB][C];
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) ak[k][cc] = (k < g.K && colvalid && j0 + cc < g.N) ? Acur[(size_t)k * g.N + j0 + cc] : (T)0;
+#pragma unroll
+        for (int q = 0; q < NUB; ++q)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) au[q][cc] = (q < g.nu && colvalid && j0 + cc < g.N) ? Acur[(size_t)(g.K + q) * g.N + j0 + cc] : (T)0;
+        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
+        const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
+        const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
+        const int nRch = g.Kp >> 1, nUch = g.nup >> 1;
+        double* RG = f.rowgram;
+
+        for (; cr.it < c.n_my; cr.advance(g, stages32)) {
+            produce_next(g, f, c, pr, stages32, NSRC);
+            mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
+            const uint32_t sb = cr.sb;
+            const int nrows = cr.rows(g, c);
+            const long long grow0 = (long long)cr.gtile * g.tile_rows;
+
+            double gp[NVP];
+#pragma unroll
+            for (int i = 0; i < NVP; ++i) gp[i] = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < RPT; ++rb) {
+                const int r = gr + rb * g.rg;
+                const bool live = (rb < g.rpt) && (r < nrows);
+                const int rr = live ? r : 0;                      // dead rows recompute row 0; never stored, never counted
+                T rk[KB > 0 ? KB : 1], uc[NUB > 1 ? NUB : 2];
+#pragma unroll
+                for (int i = 0; i < KB / 2; ++i) {
+                    const int ii = i < nRch ? i : 0;
+                    lds2(sb + g.offR + ii * 2 * (unsigned)sizeof(T) + rr * rpitch, rk[2 * i], rk[2 * i + 1]);
+                }
+#pragma unroll
+                for (int i = 0; i < (NUB + 1) / 2; ++i) {
+                    const int ii = i < nUch ? i : 0;
+                    lds2(sb + g.offU + ii * 2 * (unsigned)sizeof(T) + rr * upitch, uc[2 * i], uc[2 * i + 1]);
+                }
+                if (INITIAL && tc == 0 && live) {
+#pragma unroll
+                    for (int k = 0; k < KB; ++k)
+                        if (k < g.K) ssq_r = fma((double)rk[k], (double)rk[k], ssq_r);
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q)
+                        if (q < g.nu) ssq_u = fma((double)uc[q], (double)uc[q], ssq_u);
+                }
+                T x[C], d[C], cres[C];
+                ldsC<T, C>(sb + xoff + rr * xpitch, x);
+                WLoad<T, WT, C>::ld(sb + doff + rr * dpitch, d);
+                if (KB > 0) {
+                    T pk[C], pk1[C];
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) { pk[cc] = rk[0] * ak[0][cc]; pk1[cc] = rk[KB > 1 ? 1 : 0] * ak[KB > 1 ? 1 : 0][cc]; }
+#pragma unroll
+                    for (int k = 2; k < KB; k += 2)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) {
+                            pk[cc] = fma_t<T>(rk[k], ak[k][cc], pk[cc]);
+                            pk1[cc] = fma_t<T>(rk[k + 1], ak[k + 1][cc], pk1[cc]);
+                        }
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) cres[cc] = x[cc] - (pk[cc] + pk1[cc]);     // c = x - R_trunc a_k
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) cres[cc] = x[cc];
+                }
+                // cost of the current iterate: d * ((x - R_trunc a_k) - u a_u)^2
+                if (live && colvalid) {
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        T pu = (T)0;
+#pragma unroll
+                        for (int q = 0; q < NUB; ++q) pu = fma_t<T>(uc[q], au[q][cc], pu);
+                        const double e = (double)(cres[cc] - pu);
+                        cost = fma((double)d[cc] * e, e, cost);
+                        if (INITIAL) dmx = fmax(dmx, (double)d[cc]);
+                    }
+                }
+                // b[q] and H[q][q'] partial sums over my columns (padding columns have au = 0)
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    double bq = 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) bq = fma((double)(d[cc] * cres[cc]), (double)au[q][cc], bq);
+                    gp[rb * NG + q] = bq;
+#pragma unroll
+                    for (int q2 = q; q2 < NUB; ++q2) {
+                        double h = 0.0;
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) h = fma((double)(d[cc] * au[q][cc]), (double)au[q2][cc], h);
+                        gp[rb * NG + NUB + tri_index(q, q2, NUB) - 0] = h;
+                    }
+                }
+            }
+            int slot_base, count;
+            seg_reduce<NVP>(gp, L, c.lane, slot_base, count);
+            const bool owner = ((c.lane & (L - 1)) & ~(NVP - 1)) == 0;
+#pragma unroll
+            for (int i = 0; i < NVP; ++i) {
+                if (i < count) {
+                    const int slot = slot_base + i;
+                    const int rb = slot / NG, v = slot - rb * NG;
+                    const int r = gr + rb * g.rg;
+                    if (owner && rb < RPT && rb < g.rpt && r < nrows) RG[((size_t)(grow0 + r) * wpr + wir) * NG + v] = gp[i];
+                }
+            }
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
+        }
+    }
+    __syncthreads();
+    double* scratch = reinterpret_cast<double*>(stages);
+    double* rec = scratch + 16;
+    if (c.warp < kConsumers / 32) {
+        const double s0 = consumer_block_sum(cost, scratch, c.ctid);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (INITIAL) {
+            s1 = consumer_block_sum(ssq_r, scratch, c.ctid);
+            s2 = consumer_block_sum(ssq_u, scratch, c.ctid);
+            s3 = consumer_block_max(dmx, scratch, c.ctid);
+        }
+        if (c.ctid == 0) {
+            double* p = f.part + (size_t)blockIdx.x * g.part_stride;
+            p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
+        }
+    }
+    if (!hier_reduce(g, f, rec, 3, &c.ctl->flag)) return;
+    if (threadIdx.x == 0) cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol);
+}
+
+// ------------------------------------------------------------------------------------------------
+// n_iter2 iterations of update_u (deconvolution.py:82-89; gradient at u for the unsupervised variant, :163) per row,
+// on the row's (b, H).  One thread per row; both U slots are rewritten (u and u_ persist across outer iterations).
+template <typename T, int NUB>
+__global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
+    constexpr int NG = ng_of(NUB);
+    __shared__ double scratch[16];
+    __shared__ double rec[2];
+    __shared__ int flag;
+    const Geom& g = a.g;
+    const FitDev f = a.fits[blockIdx.y];
+    FitState* st = f.st;
+    if (st->done) return;
+    const int n2 = a.k_inner;
+    const int ucur = st->u_cur;
+    const double l_w = st->l_w, a_in = st->a1, lwo_in = st->l_w_old;
+    const T lw = (T)l_w;
+    T* Uc = reinterpret_cast<T*>(f.U + (size_t)ucur * g.uslot_bytes);
+    T* Up = reinterpret_cast<T*>(f.U + (size_t)(ucur ^ 1) * g.uslot_bytes);
+    const bool at_current = (g.mode == 2);
+    const int wpr = (g.ntc + 31) / 32;
+    const double* RG = f.rowgram;
+    double ssq = 0.0;
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < g.M; row += (long long)gridDim.x * blockDim.x) {
+        double v[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) v[i] = 0.0;
+        for (int w = 0; w < wpr; ++w) {
+            const double* p = RG + ((size_t)row * wpr + w) * NG;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) v[i] += __ldcg(p + i);
+        }
+        T u[NUB], up[NUB];
+#pragma unroll
+        for (int q = 0; q < NUB; ++q) {
+            u[q] = q < g.nu ? Uc[(size_t)row * g.ldu + q] : (T)0;
+            up[q] = q < g.nu ? Up[(size_t)row * g.ldu + q] : (T)0;
+        }
+        double am = a_in, lwo = lwo_in;
+        for (int it = 0; it < n2; ++it) {
+            const double a0 = am;
+            am = next_momentum(a0);
+            const T beta = (T)extrap_beta(a0, am, lwo, l_w);
+            lwo = l_w;
+            T ut[NUB], ug[NUB];
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                ut[q] = u[q] + beta * (u[q] - up[q]);
+                ug[q] = at_current ? u[q] : ut[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                double s = 0.0;
+#pragma unroll
+                for (int q2 = 0; q2 < NUB; ++q2) {
+                    const double h = v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))];
+                    s = fma(h, (double)ug[q2], s);
+                }
+                const double gq = v[q] - s;
+                T un = ut[q] + (T)gq / lw;
+                un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
+                up[q] = u[q];
+                u[q] = un;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NUB; ++q)
+            if (q < g.nu) {
+                Uc[(size_t)row * g.ldu + q] = u[q];
+                Up[(size_t)row * g.ldu + q] = up[q];
+                ssq = fma((double)u[q], (double)u[q], ssq);
+            }
+    }
+    const double s0 = consumer_block_sum(ssq, scratch, threadIdx.x);
+    if (threadIdx.x == 0) f.part[(size_t)blockIdx.x * g.part_stride] = s0;
+    if (!hier_reduce(g, f, rec, 1, &flag)) return;
+    if (threadIdx.x == 0) {
+        double am = a_in;
+        for (int it = 0; it < n2; ++it) am = next_momentum(am);
+        st->a1 = am;
+        if (n2 > 0) st->l_w_old = l_w;                       // deconvolution.py:89
+        st->ssq_u = rec[0];
+        const double nr = sqrt(st->ssq_rk + rec[0]);
+        st->l_h = (nr * nr) * st->dmax2;                     // deconvolution.py:212
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-sample Gram panel:  acc[p][q][j] = sum_m d_mj za_p(m) zb_q(m),  accx[p][j] = sum_m d_mj za_p(m) x_mj
+// za = PA consecutive entries of the padded register row [R_trunc (Kp) | u (nup)] starting at chunk a.ca0 (chunks of two),
+// zb = PB entries starting at chunk a.cb0.  The last CTA scatters the totals (and their mirror images) into
+// gram[Kt][Kt][N] and, when a.with_x, gbx[Kt][N].
+template <typename T, typename WT, int PA, int PB, int C>
+__global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) gram_panel_kernel(const PassArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NA = PA / 2, NB = PB / 2;
+    const Geom& g = a.g;
+    const FitDev f = a.fits[blockIdx.y];
+    FitState* st = f.st;
+    if (st->done) return;
+    CtaCtx c;
+    cta_setup(g, smem, c);
+    unsigned char* stages = smem + kCtlBytes;
+    const uint32_t stages32 = smem_u32(stages);
+    const int ucur = st->u_cur;
+    const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
+    const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
+    const bool colvalid = C * tc < g.N;
+    const int j0 = colvalid ? C * tc : 0;
+    double acc[PA][PB][C], accx[PA][C];
+#pragma unroll
+    for (int p = 0; p < PA; ++p)
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            accx[p][cc] = 0.0;
+#pragma unroll
+            for (int q = 0; q < PB; ++q) acc[p][q][cc] = 0.0;
+        }
+    constexpr int NSRC = 4;
+    if (threadIdx.x == 0) {
+        TileSrc* src = c.ctl->src;
+        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
+        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
+        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
+        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+    }
+    __syncthreads();
+    Ring pr, cr;
+    pr.init(stages32);
+    cr.init(stages32);
+    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    const int nR = g.Kp >> 1, nU = g.nup >> 1;
+    {
+        // chunk -> (offset, pitch) inside a stage; chunks beyond the row alias chunk 0 (their totals are dropped)
+        unsigned aoff[NA], apitch[NA], boff[NB], bpitch[NB];
+        auto locate = [&](int ch, unsigned& off, unsigned& pitch) {
+            if (ch >= nR + nU) ch = 0;
+            if (ch < nR) { off = g.offR + ch * 2 * (unsigned)sizeof(T); pitch = (unsigned)(g.ldr * sizeof(T)); }
+            else { off = g.offU + (ch - nR) * 2 * (unsigned)sizeof(T); pitch = (unsigned)(g.ldu * sizeof(T)); }
+        };
+#pragma unroll
+        for (int i = 0; i < NA; ++i) locate(a.ca0 + i, aoff[i], apitch[i]);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) locate(a.cb0 + i, boff[i], bpitch[i]);
+        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
+        const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
+        for (; cr.it < c.n_my; cr.advance(g, stages32)) {
+            produce_next(g, f, c, pr, stages32, NSRC);
+            mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
+            const uint32_t sb = cr.sb;
+            const int nrows = cr.rows(g, c);
+            if (colvalid) {
+                for (int r = gr; r < nrows; r += g.rg) {
+                    T za[PA], zb[PB], x[C], d[C];
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) lds2(sb + aoff[i] + r * apitch[i], za[2 * i], za[2 * i + 1]);
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) lds2(sb + boff[i] + r * bpitch[i], zb[2 * i], zb[2 * i + 1]);
+                    ldsC<T, C>(sb + xoff + r * xpitch, x);
+                    WLoad<T, WT, C>::ld(sb + doff + r * dpitch, d);
+#pragma unroll
+                    for (int p = 0; p < PA; ++p)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) {
+                            const double t = (double)d[cc] * (double)za[p];
+                            accx[p][cc] = fma(t, (double)x[cc], accx[p][cc]);
+#pragma unroll
+                            for (int q = 0; q < PB; ++q) acc[p][q][cc] = fma(t, (double)zb[q], acc[p][q][cc]);
+                        }
+                }
+            }
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
+        }
+    }
+    __syncthreads();
+    // CTA partial record [p][q (PB + 1, last = x)][N]: row groups are combined in fixed order, one p at a time
+    double* scratch = reinterpret_cast<double*>(stages);
+    double* part = f.part + (size_t)blockIdx.x * g.part_stride;
+    const int QN = (PB + 1) * g.N;
+#pragma unroll
+    for (int p = 0; p < PA; ++p) {
+        for (int gg = 0; gg < g.rg; ++gg) {
+            if (gr == gg && colvalid) {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc)
+                    if (j0 + cc < g.N) {
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) {
+                            double* ptr = &scratch[(size_t)q * g.N + j0 + cc];
+                            *ptr = (gg == 0) ? acc[p][q][cc] : (*ptr + acc[p][q][cc]);
+                        }
+                        double* ptr = &scratch[(size_t)PB * g.N + j0 + cc];
+                        *ptr = (gg == 0) ? accx[p][cc] : (*ptr + accx[p][cc]);
+                    }
+            }
+            __syncthreads();
+        }
+        for (int e = threadIdx.x; e < QN; e += blockDim.x) part[(size_t)p * QN + e] = scratch[e];
+        __syncthreads();
+    }
+    const int n = PA * QN;
+    if (!hier_reduce(g, f, f.red, n, &c.ctl->flag)) return;
+    __threadfence();
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int p = e / QN, rem = e - p * QN;
+        const int q = rem / g.N, j = rem - q * g.N;
+        const int ia = alpha_row_of(g, 2 * a.ca0 + p);
+        if (ia < 0) continue;
+        const double v = f.red[e];
+        if (q == PB) {
+            if (a.with_x) f.gbx[(size_t)ia * g.N + j] = v;
+        } else {
+            const int ib = alpha_row_of(g, 2 * a.cb0 + q);
+            if (ib < 0) continue;
+            f.gram[((size_t)ia * g.Kt + ib) * g.N + j] = v;
+            f.gram[((size_t)ib * g.Kt + ia) * g.N + j] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// n_iter2 iterations of update_alpha (deconvolution.py:94-101 with projection :21-37) or of frank_wolfe_nmf (:285-299)
+// per sample column on (G_j, bx_j).  One CTA per fit, one thread per sample.  alpha and alpha_ both persist.
+template <typename T, int KTB>
+__global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a) {
+    __shared__ double colred[kThreads];
+    __shared__ int s_bad;
+    const Geom& g = a.g;
+    const FitDev f = a.fits[blockIdx.x];
+    FitState* st = f.st;
+    if (st->done) return;
+    const bool fw = (a.flags & kFlagFW) != 0;
+    const int n2 = a.k_inner, Kt = g.Kt;
+    const int acur = st->a_cur;
+    const double l_h = st->l_h, a_in = st->a2, lho_in = st->l_h_old;
+    T* Acur = reinterpret_cast<T*>(f.A) + (size_t)acur * g.Kt * g.N;
+    T* Aprev = reinterpret_cast<T*>(f.A) + (size_t)(acur ^ 1) * g.Kt * g.N;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    double sa_thread = 0.0;
+    for (int j = threadIdx.x; j < g.N; j += blockDim.x) {
+        double G[KTB][KTB], b[KTB], ac[KTB], ap[KTB];
+#pragma unroll(KTB <= 8 ? KTB : 1)
+        for (int k = 0; k < KTB; ++k) {
+            b[k] = k < Kt ? f.gbx[(size_t)k * g.N + j] : 0.0;
+            ac[k] = k < Kt ? (double)Acur[(size_t)k * g.N + j] : 0.0;
+            ap[k] = k < Kt ? (double)Aprev[(size_t)k * g.N + j] : 0.0;
+#pragma unroll(KTB <= 8 ? KTB : 1)
+            for (int l = 0; l < KTB; ++l) G[k][l] = (k < Kt && l < Kt) ? f.gram[((size_t)k * Kt + l) * g.N + j] : 0.0;
+        }
+        if (!fw) {
+            double am = a_in, lho = lho_in;
+            bool bad = false;
+            for (int it = 0; it < n2 && !bad; ++it) {
+                const double a0 = am;
+                am = next_momentum(a0);
+                const double beta = (double)(T)extrap_beta(a0, am, lho, l_h);
+                lho = l_h;
+                double at[KTB], v[kMaxKt];
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                for (int k = 0; k < KTB; ++k) at[k] = (double)(T)(ac[k] + beta * (ac[k] - ap[k]));
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                for (int k = 0; k < KTB; ++k) {
+                    double s = 0.0;
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                    for (int l = 0; l < KTB; ++l) s = fma(G[k][l], at[l], s);
+                    v[k] = (double)(T)(at[k] + (double)(T)((b[k] - s) / l_h));
+                }
+                if (!project_simplex(v, Kt)) { bad = true; break; }
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                for (int k = 0; k < KTB; ++k) { ap[k] = ac[k]; ac[k] = k < Kt ? (double)(T)v[k] : 0.0; }
+            }
+            if (bad) s_bad = 1;
+        } else {
+            const double pj = f.purity[j];
+            for (int it = 0; it < n2; ++it) {
+                const double gamma = 2.0 / (double)(it + 2);
+                int i1 = 0, i2 = 0;
+                double m1 = 0.0, m2 = 0.0;
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                for (int k = 0; k < KTB; ++k) {
+                    if (k < Kt) {
+                        double s = 0.0;
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                        for (int l = 0; l < KTB; ++l) s = fma(G[k][l], ac[l], s);
+                        const double gk = -(b[k] - s);               // gradient, deconvolution.py:286-287
+                        if (k < g.K) { if (k == 0 || gk < m1) { m1 = gk; i1 = k; } }
+                        else { if (k == g.K || gk < m2) { m2 = gk; i2 = k; } }
+                    }
+                }
+#pragma unroll(KTB <= 8 ? KTB : 1)
+                for (int k = 0; k < KTB; ++k)
+                    if (k < Kt) {
+                        const double s = (k < g.K) ? ((k == i1) ? pj : 0.0) : ((k == i2) ? (1.0 - pj) : 0.0);
+                        ac[k] = (double)(T)((1.0 - gamma) * ac[k] + gamma * s);
+                    }
+            }
+        }
+        double sa = 0.0;
+#pragma unroll(KTB <= 8 ? KTB : 1)
+        for (int k = 0; k < KTB; ++k)
+            if (k < Kt) {
+                Acur[(size_t)k * g.N + j] = (T)ac[k];
+                if (!fw) Aprev[(size_t)k * g.N + j] = (T)ap[k];
+                if (k >= g.K) sa = fma(ac[k], ac[k], sa);
+            }
+        sa_thread += sa;       // at most one column per thread unless N > blockDim (then in column order)
+        colred[threadIdx.x] = sa_thread;
+    }
+    if (threadIdx.x >= g.N) colred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_bad) st->done = 3;
+        double sa = 0.0;
+        const int nt = min((int)blockDim.x, g.N);
+        for (int t = 0; t < nt; ++t) sa += colred[t];
+        const double na = sqrt(sa);
+        st->l_w = (na * na) * st->dmax2;                 // deconvolution.py:216 / :327
+        if (!fw) {
+            double am = a_in;
+            for (int it = 0; it < n2; ++it) am = next_momentum(am);
+            st->a2 = am;
+            if (n2 > 0) st->l_h_old = l_h;               // deconvolution.py:101
+        }
+    }
+}
+
+}  // namespace dmf

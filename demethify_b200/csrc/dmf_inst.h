@@ -9,6 +9,10 @@ typedef void (*wls_kern_t)(const WlsArgs);
     kern_t pick_cost_##TAG(int ktb, int nub, int c);       \
     kern_t pick_alpha_##TAG(int ktb, int nub, int c);      \
     kern_t pick_u_##TAG(int ktb, int nub, int c);          \
+    kern_t pick_rowgram_##TAG(int kb, int nub, int initial); \
+    kern_t pick_panel_##TAG(int pb, int, int);             \
+    kern_t pick_uinner_##TAG(int nub, int, int);           \
+    kern_t pick_ainner_##TAG(int ktb, int, int);           \
     wls_kern_t pick_wls_##TAG();
 DMF_DECL(f64_f64) DMF_DECL(f64_u16) DMF_DECL(f32_f32) DMF_DECL(f32_u16)
 #undef DMF_DECL

@@ -2,6 +2,7 @@
 #include "dmf_inst.h"
 #include "dmf_kernels.cuh"
 #include "dmf_wls.cuh"
+#include "dmf_gram.cuh"
 namespace dmf {
 #define DMF_CAT2(a, b) a##b
 #define DMF_CAT(a, b) DMF_CAT2(a, b)
@@ -27,6 +28,36 @@ kern_t DMF_CAT(pick_u_, DMF_TAG)(int kb, int nub, int) {
     DMF_U(6, 2, 2, 4) DMF_U(8, 2, 2, 4) DMF_U(8, 8, 2, 1) DMF_U(16, 2, 2, 4) DMF_U(16, 8, 2, 1) DMF_U(16, 16, 1, 1)
     DMF_U(32, 2, 1, 4) DMF_U(32, 8, 1, 1) DMF_U(32, 32, 1, 1)
 #undef DMF_U
+    return nullptr;
+}
+// Gram engine (dmf_gram.cuh).  rowgram: (known bucket, unknown bucket) -> fixed (columns per thread, rows per thread per tile);
+// see kGramTable in dmf_api.cu
+kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int initial) {
+#define DMF_G(KB_, NUB_, C_, RPT_)                                                                           \
+    if (kb == KB_ && nub == NUB_)                                                                            \
+        return initial ? (kern_t)rowgram_kernel<DMF_T, DMF_WT, KB_, NUB_, C_, RPT_, true> : (kern_t)rowgram_kernel<DMF_T, DMF_WT, KB_, NUB_, C_, RPT_, false>;
+    DMF_G(0, 1, 2, 4) DMF_G(0, 2, 2, 3) DMF_G(0, 4, 2, 2)
+    DMF_G(6, 1, 2, 4) DMF_G(6, 2, 2, 3) DMF_G(6, 4, 2, 2)
+    DMF_G(16, 1, 2, 4) DMF_G(16, 2, 2, 3) DMF_G(16, 4, 2, 2)
+    DMF_G(32, 1, 1, 4) DMF_G(32, 2, 1, 3) DMF_G(32, 4, 1, 2)
+#undef DMF_G
+    return nullptr;
+}
+kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int, int) {
+    if (pb == 8) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 2>;
+    if (pb == 16) return gram_panel_kernel<DMF_T, DMF_WT, 2, 16, 1>;
+    return nullptr;
+}
+kern_t DMF_CAT(pick_uinner_, DMF_TAG)(int nub, int, int) {
+    if (nub == 1) return u_inner_kernel<DMF_T, 1>;
+    if (nub == 2) return u_inner_kernel<DMF_T, 2>;
+    if (nub == 4) return u_inner_kernel<DMF_T, 4>;
+    return nullptr;
+}
+kern_t DMF_CAT(pick_ainner_, DMF_TAG)(int ktb, int, int) {
+    if (ktb == 8) return alpha_inner_kernel<DMF_T, 8>;
+    if (ktb == 16) return alpha_inner_kernel<DMF_T, 16>;
+    if (ktb == 32) return alpha_inner_kernel<DMF_T, 32>;
     return nullptr;
 }
 wls_kern_t DMF_CAT(pick_wls_, DMF_TAG)() { return wls_moments_kernel<DMF_T, DMF_WT>; }

@@ -121,7 +121,7 @@ def _solve(mode, u, alpha, meth_frequency, d_x, R_trunc, n_u, n_iter1, n_iter2, 
     batch = FitBatch(prob, n_u, [np.asarray(u).reshape(-1, n_u)], [np.asarray(alpha)], mode=mode, purity=purity)
     states = batch.fit(n_iter1, n_iter2, tol)
     (u_out, a_out, n_outer, cost), = batch.results(states)
-    _last.update(n_outer=n_outer, cost=cost, launches=batch.launch_count(), geometry=batch.geometry())
+    _last.update(n_outer=n_outer, cost=cost, launches=batch.launch_count(), geometry=batch.geometry(), engine=batch.engine)
     batch.close()
     return u_out, a_out
 

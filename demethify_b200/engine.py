@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, get_precision
+from . import _lib, get_engine, get_precision
 
 _handles = {}
 
@@ -161,7 +161,7 @@ class FitBatch:
     """n_fits independent fits of one (M, N, K, n_u) shape, advanced together by single launches."""
 
     def __init__(self, problems, n_u, U0, A0, mode=_lib.DMF_MODE_PARTIAL, purity=None, rows=None, trace_cap=0,
-                 max_ctas_per_fit=0):
+                 max_ctas_per_fit=0, engine=None):
         probs = problems if isinstance(problems, (list, tuple)) else [problems]
         self.n_fits = len(U0)
         if len(probs) == 1:
@@ -222,6 +222,15 @@ class FitBatch:
         ws_ptr = (self.ws.data_ptr() + 255) // 256 * 256
         self.b = C.c_void_p()
         _lib.check(lib.dmf_batch_create(self.h, C.byref(self.shape), descs, C.c_void_p(ws_ptr), nbytes.value, _stream_ptr(), C.byref(self.b)))
+        engine = engine or get_engine()
+        if engine != "auto":
+            _lib.check(lib.dmf_batch_set_engine(self.b, _lib.DMF_ENGINE_GRAM if engine == "gram" else _lib.DMF_ENGINE_STREAM))
+
+    @property
+    def engine(self):
+        e = C.c_int32()
+        _lib.check(_lib.lib().dmf_batch_get_engine(self.b, C.byref(e)))
+        return "gram" if e.value == _lib.DMF_ENGINE_GRAM else "stream"
 
     def u_view(self, i, slot):
         return self.U[i, slot, :self.M * self.ldu].view(self.M, self.ldu)[:, :self.n_u]
@@ -241,6 +250,25 @@ class FitBatch:
 
     def pass_cost(self, tol):
         _lib.check(_lib.lib().dmf_pass_cost(self.b, float(tol), _stream_ptr()))
+
+    # -- Gram-form engine steps
+    def gram_init(self):
+        _lib.check(_lib.lib().dmf_gram_init(self.b, _stream_ptr()))
+
+    def gram_rowgram(self, initial=False, tol=0.0):
+        _lib.check(_lib.lib().dmf_gram_rowgram(self.b, int(bool(initial)), float(tol), _stream_ptr()))
+
+    def gram_u_inner(self, n_iter2):
+        _lib.check(_lib.lib().dmf_gram_u_inner(self.b, int(n_iter2), _stream_ptr()))
+
+    def gram_panels(self, known_block=False):
+        _lib.check(_lib.lib().dmf_gram_panels(self.b, int(bool(known_block)), _stream_ptr()))
+
+    def gram_alpha_inner(self, n_iter2):
+        _lib.check(_lib.lib().dmf_gram_alpha_inner(self.b, int(n_iter2), _stream_ptr()))
+
+    def gram_outer(self, n_iter2, tol):
+        _lib.check(_lib.lib().dmf_gram_outer(self.b, int(n_iter2), float(tol), _stream_ptr()))
 
     def enqueue_outer(self, n_outer, n_iter2, tol):
         _lib.check(_lib.lib().dmf_enqueue_outer(self.b, int(n_outer), int(n_iter2), float(tol), _stream_ptr()))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DMF_ABI_VERSION 1
+#define DMF_ABI_VERSION 2
 
 enum { DMF_OK = 0, DMF_E_ARG = 1, DMF_E_CUDA = 2, DMF_E_SHAPE = 3, DMF_E_STATE = 4 };
 
@@ -43,6 +43,12 @@ enum {
     DMF_MODE_PURITY = 1,       /* mdwbssmf_deconv_p    deconvolution.py:305-337 */
     DMF_MODE_UNSUPERVISED = 2  /* unsupervised_deconv  deconvolution.py:107-184 (K = 0; U-gradient at u, :163) */
 };
+
+/* how the inner iterations are executed (results agree to ~1e-15 on alpha; both are pinned by the same golden vectors)
+ *   STREAM: one launch per reference inner iteration, each a streaming pass over X, d_x (dmf_pass_u / _alpha / _fw / _cost)
+ *   GRAM  : per outer iteration two streaming passes build the sufficient statistics of the U step (per CpG row) and of the
+ *           alpha step (per sample); the n_iter2 inner iterations then run on those (dmf_gram_*).  Default when n_u <= 4. */
+enum { DMF_ENGINE_STREAM = 0, DMF_ENGINE_GRAM = 1 };
 
 typedef struct dmf_shape {
     int64_t M;      /* CpG rows                         */
@@ -121,6 +127,24 @@ int dmf_pass_alpha(dmf_batch_t b, void* stream);
 int dmf_pass_fw(dmf_batch_t b, int32_t k_inner, void* stream);
 /* cost_f_w + termination test |cf - cf_0| < tol (deconvolution.py:218-221) */
 int dmf_pass_cost(dmf_batch_t b, double tol, void* stream);
+
+/* Gram-form engine: the same outer iteration (deconvolution.py:206-221 / :320-335) on sufficient statistics ------- */
+int dmf_batch_set_engine(dmf_batch_t b, int32_t engine);
+int dmf_batch_get_engine(dmf_batch_t b, int32_t* engine);
+/* streaming pass 1: cost_f_w of the current iterate (set-up when initial != 0, else termination test against tol,
+ * deconvolution.py:192-204 / :218-221) + per-row statistics b_m = (d o (x - R_trunc a_k)) a_u^T, H_m = a_u diag(d_m) a_u^T */
+int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream);
+/* n_iter2 update_u iterations (deconvolution.py:82-89) per row on (b_m, H_m) */
+int dmf_gram_u_inner(dmf_batch_t b, int32_t n_iter2, void* stream);
+/* streaming pass 2: blocks of G_j = R^T diag(d_.j) R and R^T (d_.j o x_.j) that involve u (known_block = 0, every outer
+ * iteration) or only R_trunc (known_block = 1, once at set-up) */
+int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream);
+/* n_iter2 update_alpha iterations incl. simplex projection (deconvolution.py:94-101, :21-37), or Frank-Wolfe iterations
+ * (deconvolution.py:285-299) for purity batches, per sample on (G_j, bx_j) */
+int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream);
+/* set-up (rowgram initial + known panels) and one whole outer iteration (u_inner, panels, alpha_inner, rowgram) */
+int dmf_gram_init(dmf_batch_t b, void* stream);
+int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
 
 /* whole loops --------------------------------------------------------------------------------- */
 /* enqueue n_outer outer iterations (n_iter2 U steps, n_iter2 alpha/FW steps, cost) without host sync;

@@ -11,14 +11,25 @@ TOL64 = 1e-6
 TOL32 = 1e-4
 
 
-@pytest.fixture(scope="module")
-def dec():
+@pytest.fixture(scope="module", params=["stream", "auto"])
+def dec(request):
+    """The reference-shaped API with both device engines: 'stream' = one pass per inner iteration,
+    'auto' = Gram-form engine wherever the library supports the shape (n_u <= 4)."""
     import torch
     assert torch.cuda.is_available()
     import __graft_entry__ as g
     g.build()
+    import demethify_b200
     from demethify_b200 import deconvolution
-    return deconvolution
+    demethify_b200.set_engine(request.param)
+    deconvolution.engine_mode = request.param
+    yield deconvolution
+    demethify_b200.set_engine("auto")
+
+
+def check_engine(dec, n_u):
+    want = "gram" if (dec.engine_mode == "auto" and n_u <= 4) else "stream"
+    assert dec.last_fit_info()["engine"] == want
 
 
 @pytest.fixture(scope="module")
@@ -47,6 +58,7 @@ def test_partial_reference_fixture(dec, shipped, live, n_u):
     assert np.array_equal(u0, live[f"pr{n_u}_u0"]) and np.array_equal(a0, live[f"pr{n_u}_a0"])
     u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, n_u, n_iter1=10000, n_iter2=20, tol=1e-2)
     info = dec.last_fit_info()
+    check_engine(dec, n_u)
     assert info["n_outer"] == len(live[f"pr{n_u}_costs"]) - 1, "outer-iteration count differs from the reference"
     assert abs(info["cost"] - live[f"pr{n_u}_costs"][-1]) <= 1e-9 * live[f"pr{n_u}_costs"][-1]
     assert np.abs(a - live[f"pr{n_u}_a"]).max() <= TOL64 and np.abs(u - live[f"pr{n_u}_u"]).max() <= TOL64
@@ -59,6 +71,7 @@ def test_purity_fixture(dec, shipped, live):
     pur = 1 - shipped["purity_pct"] / 100.0
     u0, R0, a0 = dec.init_BSSMF_md_p("uniform_", X, D, Rk, 1, pur, seed=1)
     u, a = dec.mdwbssmf_deconv_p(u0, R0, a0, X, D, Rk, 1, pur, n_iter1=100, n_iter2=500, tol=1e-2)
+    check_engine(dec, 1)
     assert dec.last_fit_info()["n_outer"] == len(live["pur_costs"]) - 1
     assert np.abs(a - shipped["purity_alpha"]).max() <= TOL64 and np.abs(u - shipped["purity_u"]).max() <= TOL64
 
@@ -72,6 +85,7 @@ def test_purity_two_unknowns(dec, live):
 
 def test_unsupervised_fixture(dec, shipped, live):
     u, a = dec.unsupervised_deconv(shipped["X"], 4, shipped["D"], "uniform_", n_iter1=10000, n_iter2=20, tol=1e-2, seed=1)
+    check_engine(dec, 4)
     assert dec.last_fit_info()["n_outer"] == len(live["unsup_costs"]) - 1
     assert np.abs(a - shipped["unsup_alpha"]).max() <= TOL64 and np.abs(u - shipped["unsup_u"]).max() <= TOL64
 
@@ -102,6 +116,7 @@ def test_partial_reference_vs_oracle(dec, orc, M, N, K, n_u, it1, it2):
     uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, n_u, it1, it2, 1e-9, trace=tr)
     u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, n_u, n_iter1=it1, n_iter2=it2, tol=1e-9)
     info = dec.last_fit_info()
+    check_engine(dec, n_u)
     assert info["n_outer"] == tr["n_outer"]
     assert abs(info["cost"] - tr["costs"][-1]) <= 1e-9 * tr["costs"][-1]
     assert np.abs(a - ao).max() <= TOL64 and np.abs(u - uo).max() <= TOL64
@@ -168,6 +183,7 @@ def test_size_independent_properties_full_scale(dec):
     u0 = rs.uniform(size=(X.shape[0], 2)); a0 = rs.dirichlet(np.ones(8), 16).T
     prob = DeviceProblem(X, D, Rk)
     b = FitBatch(prob, 2, [u0], [a0], trace_cap=16)
+    assert b.engine == ("gram" if dec.engine_mode == "auto" else "stream")
     st = b.fit(8, 20, 0.0)
     (u, a, n_outer, cost), = b.results(st)
     tr = b.trace[0, :9].cpu().numpy()
