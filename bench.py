@@ -7,10 +7,13 @@ M = 1,000,000 CpGs x N = 256 samples, K = 6 known + n_u = 2 unknown cell types, 
 (deconvolution.py:206-221) with n_iter2 = 20: 20 update_u + 20 update_alpha inner iterations + cost_f_w each,
 tol = 0 so no step stops early.  metric = update iterations / second (inner iterations of U and alpha).
 
-  value     : inputs resident in HBM when the timed region starts (FitBatch.enqueue_outer)
+  value     : inputs resident in HBM when the timed region starts; the library's default engine (Gram-form: per
+              outer iteration rowgram pass -> u_inner -> Gram panel pass -> alpha_inner, see csrc/dmf_gram.cuh)
   e2e       : the public call demethify_b200.deconvolution.mdwbssmf_deconv with HOST (pinned) numpy buffers;
               H2D of X, d_x, R_trunc, u0, alpha0 and D2H of u, alpha inside the timed region
-  roofline  : dominant kernel (update_u pass), algorithmic bytes / CUDA-event duration
+  roofline  : dominant kernel of the timed region (the slower of the two streaming passes), algorithmic bytes
+               / CUDA-event duration; `stream_passes` = the reference-shaped
+              one-launch-per-inner-iteration kernels (update_u / update_alpha / cost) timed in the same run
   cpu_baseline / --impl reference : the numpy port of the reference loop (oracle/) on the host cores, on a
               bounded row sample of the same workload (cost is linear in M; the sample and the scaling are stated)
 
@@ -32,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 M_FULL, N_S, K_KNOWN, N_UNK = 1_000_000, 256, 6, 2
 N_ITER2 = 20
-OUTER_PER_STEP = 2
+OUTER_PER_STEP = 10
 CPU_SAMPLE_ROWS = 100_000
 METRIC = "update_iters_per_sec"
 UNIT = "inner update iterations/s at 1M CpG x 256 samples (K=6, n_u=2)"
@@ -48,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--profile", action="store_true", help="resident arm only (for runs under ncu): no e2e, no CPU leg")
+    ap.add_argument("--engine", default="auto", choices=["auto", "gram", "stream"], help="device engine of the timed region")
     return ap.parse_args()
 
 
@@ -186,15 +190,19 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     # ---- resident arm
+    demethify_b200.set_engine(args.engine)
     prob = DeviceProblem(X, D, Rk, precision=args.precision)
     del X, D
     batch = FitBatch(prob, N_UNK, [hU], [hA])
-    batch.pass_init()
+    engine = batch.engine
     geom = batch.geometry()
     sT = 8 if args.precision == "fp64" else 4
     sW = 2 if prob.wtype == 1 else sT
+    NG = N_UNK + N_UNK * (N_UNK + 1) // 2
     bytes_u = M * (sT * (N_S + K_KNOWN + 3 * N_UNK) + sW * N_S)          # SURVEY 8 d4, U inner iteration
     bytes_a = M * (sT * (N_S + Kt) + sW * N_S)                             # alpha inner iteration / cost
+    bytes_rowgram = M * (sT * (N_S + Kt) + sW * N_S + 8 * NG)              # read X, d_x, R_trunc, u; write b_m, H_m
+    bytes_panel = M * (sT * (N_S + Kt) + sW * N_S)                         # read X, d_x, R_trunc, u
 
     def barrier():
         torch.cuda.synchronize()
@@ -202,24 +210,41 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(ev=None):
-        for _ in range(OUTER_PER_STEP):
-            if ev is not None:
-                e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-                e0.record()
-            for _i in range(N_ITER2):
-                batch.pass_u()
-            if ev is not None:
-                e1.record()
-            for _i in range(N_ITER2):
-                batch.pass_alpha()
-            if ev is not None:
-                e2.record()
-            batch.pass_cost(0.0)
-            if ev is not None:
-                e3.record()
-                ev.append((e0, e1, e2, e3))
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
 
+    def one_step(evs=None):
+        for _ in range(OUTER_PER_STEP):
+            if engine == "gram":
+                e0 = ev() if evs is not None else None
+                batch.gram_u_inner(N_ITER2)
+                e1 = ev() if evs is not None else None
+                batch.gram_panels(False)
+                e2 = ev() if evs is not None else None
+                batch.gram_alpha_inner(N_ITER2)
+                e3 = ev() if evs is not None else None
+                batch.gram_rowgram(False, 0.0)
+                e4 = ev() if evs is not None else None
+            else:
+                e0 = ev() if evs is not None else None
+                for _i in range(N_ITER2):
+                    batch.pass_u()
+                e1 = ev() if evs is not None else None
+                for _i in range(N_ITER2):
+                    batch.pass_alpha()
+                e2 = ev() if evs is not None else None
+                e3 = e2
+                batch.pass_cost(0.0)
+                e4 = ev() if evs is not None else None
+            if evs is not None:
+                evs.append((e0, e1, e2, e3, e4))
+
+    if engine == "gram":
+        batch.gram_init()
+    else:
+        batch.pass_init()
     for _ in range(args.warmup):
         one_step()
     barrier()
@@ -236,15 +261,41 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     launches = batch.launch_count() - launches0
-    t_u = float(np.mean([a.elapsed_time(b) for a, b, _, _ in evs])) / N_ITER2      # ms per update_u launch
-    t_a = float(np.mean([b.elapsed_time(c) for _, b, c, _ in evs])) / N_ITER2
-    t_c = float(np.mean([c.elapsed_time(d) for _, _, c, d in evs]))
+    seg = [float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k in range(4)]
     st = batch.states()[0]
     assert st.n_outer == (args.warmup + args.steps) * OUTER_PER_STEP and np.isfinite(st.cost)
+    if engine == "gram":
+        kern = {"u_inner_kernel": seg[0], "gram_panel_kernel": seg[1], "alpha_inner_kernel": seg[2], "rowgram_kernel": seg[3]}
+    else:
+        kern = {"u_pass_kernel": seg[0] / N_ITER2, "alpha_pass_kernel": seg[1] / N_ITER2, "cost_kernel": seg[3]}
+
+    # ---- the reference-shaped one-launch-per-inner-iteration passes, same data, timed on their own
+    stream = None
+    if engine == "gram" and not args.profile:
+        sb = FitBatch(prob, N_UNK, [hU], [hA], engine="stream")
+        sb.pass_init()
+        for fn in (sb.pass_u, sb.pass_alpha, lambda: sb.pass_cost(0.0)):
+            for _ in range(3):
+                fn()
+        tms = []
+        for fn in (sb.pass_u, sb.pass_alpha, lambda: sb.pass_cost(0.0)):
+            torch.cuda.synchronize()
+            a0_, n_rep = ev(), 10
+            for _ in range(n_rep):
+                fn()
+            a1_ = ev()
+            torch.cuda.synchronize()
+            tms.append(a0_.elapsed_time(a1_) / n_rep)
+        stream = {"u_pass_kernel": {"ms_per_launch": tms[0], "achieved": bytes_u / tms[0] / 1e6, "algorithmic_bytes_per_launch": int(bytes_u)},
+                  "alpha_pass_kernel": {"ms_per_launch": tms[1], "achieved": bytes_a / tms[1] / 1e6, "algorithmic_bytes_per_launch": int(bytes_a)},
+                  "cost_kernel": {"ms_per_launch": tms[2], "achieved": bytes_a / tms[2] / 1e6, "algorithmic_bytes_per_launch": int(bytes_a)},
+                  "update_iters_per_sec": 2 * N_ITER2 / ((tms[0] + tms[1]) * N_ITER2 + tms[2]) * 1e3}
+        sb.close()
+        del sb
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_u": t_u, "ms_alpha": t_a, "ms_cost": t_c}))
+            print(json.dumps({"profile_run": True, "engine": engine, "ms": kern}))
         return
     # ---- end-to-end arm: public API, host buffers in, host arrays out
     nX, nD, nR, nU, nA = hX.numpy(), hD.numpy(), hR.numpy(), hU.numpy(), hA.numpy()
@@ -277,23 +328,34 @@ def run_b200(args, rank, world, local_rank):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        ach = bytes_u / (t_u * 1e-3) / 1e9
+        if engine == "gram":
+            passes = {"rowgram_kernel": (kern["rowgram_kernel"], bytes_rowgram), "gram_panel_kernel": (kern["gram_panel_kernel"], bytes_panel)}
+        else:
+            passes = {"u_pass_kernel": (kern["u_pass_kernel"], bytes_u), "alpha_pass_kernel": (kern["alpha_pass_kernel"], bytes_a)}
+        dom = max(passes, key=lambda k: passes[k][0])
+        dom_ms, dom_bytes = passes[dom]
+        ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
+                "kernels_ms_per_launch": kern,
+                "passes": {k: {"ms_per_launch": v[0], "achieved": v[1] / (v[0] * 1e-3) / 1e9, "frac": v[1] / (v[0] * 1e-3) / 1e9 / peak,
+                               "algorithmic_bytes_per_launch": int(v[1])} for k, v in passes.items()}}
+        if stream is not None:
+            for k in ("u_pass_kernel", "alpha_pass_kernel", "cost_kernel"):
+                stream[k]["frac"] = stream[k]["achieved"] / peak
+            roof["stream_passes"] = stream
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
-            "config": workload_config(M, {"weights_storage": "u16" if prob_wtype_is_u16(sW, sT) else "float",
+            "config": workload_config(M, {"weights_storage": "u16" if prob_wtype_is_u16(sW, sT) else "float", "engine": engine,
                                           "parallelism": f"fit-sharded x{world}", "ctas_per_fit": geom["ctas_per_fit"],
                                           "tile_rows": geom["tile_rows"], "smem_bytes": geom["smem_bytes"]}),
             "fits_per_sec_at_100_outer": value / (2 * N_ITER2 * 100),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "s_per_call": e2e_s, "call": "demethify_b200.deconvolution.mdwbssmf_deconv(numpy in, numpy out)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "u_pass_kernel (update_u inner iteration)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(bytes_u), "ms_per_launch": t_u,
-                         "alpha_pass": {"ms_per_launch": t_a, "achieved": bytes_a / (t_a * 1e-3) / 1e9, "algorithmic_bytes_per_launch": int(bytes_a)},
-                         "cost_pass": {"ms_per_launch": t_c, "achieved": bytes_a / (t_c * 1e-3) / 1e9}},
+            "roofline": roof,
             "clocks": clocks,
         }
         if not args.no_cpu and world == 1:
