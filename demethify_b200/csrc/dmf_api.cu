@@ -185,11 +185,12 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     if (s.n_u <= 4) {
         p.kb_g = s.K == 0 ? 0 : (p.Kp <= 6 ? 6 : (p.Kp <= 16 ? 16 : 32));
         p.nub_g = s.n_u == 1 ? 1 : (s.n_u == 2 ? 2 : 4);
-        p.c_g = p.kb_g <= 16 ? 2 : 1;
-        p.rpt_g_max = p.nub_g == 1 ? 4 : (p.nub_g == 2 ? 3 : 2);
+        const bool pitch4 = (s.ldx % 4 == 0) && (s.ldd % 4 == 0);     // 4-column kernels: rows of X, d_x padded to multiples of 4
+        p.c_g = (p.kb_g <= 6 && pitch4) ? 4 : (p.kb_g <= 16 ? 2 : 1);
+        p.rpt_g_max = p.c_g == 4 ? (p.nub_g <= 2 ? 4 : 2) : (p.nub_g == 1 ? 4 : (p.nub_g == 2 ? 3 : 2));
         p.ng_g = ng_of_h(p.nub_g);
         p.pb_g = rowlen <= 8 ? 8 : 16;
-        p.c_p = p.pb_g == 8 ? 2 : 1;
+        p.c_p = p.pb_g == 8 ? (pitch4 ? 4 : 2) : 1;
         p.ktb_in = Kt <= 8 ? 8 : (Kt <= 16 ? 16 : 32);
         if (s.N <= kConsumers * p.c_g && s.N <= kConsumers * p.c_p) {
             p.ntc_g = next_pow2((s.N + p.c_g - 1) / p.c_g);
@@ -197,7 +198,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
             p.wpr_g = (p.ntc_g + 31) / 32;
             const int rg_g = kConsumers / p.ntc_g;
             // must mirror the __launch_bounds__ of rowgram_kernel / gram_panel_kernel
-            const int occ_rg = ((p.kb_g + 2 * p.nub_g) * p.c_g + 2 * pow2ceil_h(p.rpt_g_max * p.ng_g) <= 56) ? 2 : 1;
+            const int occ_rg = p.c_g == 4 ? 1 : (((p.kb_g + 2 * p.nub_g) * p.c_g + 2 * pow2ceil_h(p.rpt_g_max * p.ng_g) <= 56) ? 2 : 1);
             const int occ_pn = (2 * (p.pb_g + 1) * p.c_p <= 40) ? 2 : 1;
             p.occ_g = std::min(occ_rg, occ_pn);
             auto a128g = [](size_t v) { return align_up(v, 128); };
@@ -206,7 +207,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
             p.rpt_g = 0;
             for (int attempt = 0; attempt < 2 && !p.rpt_g; ++attempt) {
                 const size_t budget = (p.occ_g == 2 ? std::min<size_t>(smem_cap, 112 * 1024) : std::min<size_t>(smem_cap, 220 * 1024)) - kCtlBytes - 1024;
-                for (int rpt = p.rpt_g_max; rpt >= 1; --rpt) {
+                for (int rpt = p.rpt_g_max; rpt >= 1; rpt = (p.c_g == 4 ? rpt >> 1 : rpt - 1)) {
                     const long long trg = (long long)rpt * rg_g;
                     if (trg % ra) continue;
                     if (stage_g(trg) * kStages <= budget && epi_panel <= budget + kCtlBytes) { p.rpt_g = rpt; break; }
@@ -286,8 +287,8 @@ int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_in
 kern_t k_cost(dmf_batch_s* b, int initial) { return by_types(b->shape, g_cost, b->ktb, initial, b->c_alpha); }
 kern_t k_alpha(dmf_batch_s* b) { return by_types(b->shape, g_alpha, b->ktb, 0, b->c_alpha); }
 kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->kb, b->nub, b->c_u); }
-kern_t k_rowgram(dmf_batch_s* b, int initial) { return by_types(b->shape, g_rowgram, b->kb_g, b->nub_g, initial); }
-kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, 0, 0); }
+kern_t k_rowgram(dmf_batch_s* b, int initial) { return by_types(b->shape, g_rowgram, b->kb_g, b->nub_g, initial | (b->c_g == 4 ? 2 : 0)); }
+kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->c_p, 0); }
 kern_t k_uinner(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 0, 0); }
 kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in, 0, 0); }
 

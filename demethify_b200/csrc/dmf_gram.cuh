@@ -247,6 +247,240 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
 }
 
 // ------------------------------------------------------------------------------------------------
+// rowgram pass, 4 columns per thread (row pitches of X and d_x multiples of 4, zero padded).  Differences to rowgram_kernel:
+//  * a thread owns 4 adjacent columns and RPT rows of the tile -> the broadcast [R_trunc | u] row loads, the address
+//    arithmetic and the per-tile ring bookkeeping are spread over 4 x RPT elements;
+//  * the row -> register-slot assignment is lane dependent (slot rb holds tile row rb ^ rmask(lane)), so the first
+//    log2(RPT) butterfly steps need no selects: every lane keeps its low slots and sends its high slots;
+//  * the cost is assembled from  sum d c^2  (one FMA per element, per-thread accumulator) and the row statistics:
+//    sum_j d (c - u a_u)^2 = sum_j d c^2 - 2 u^T b + u^T H u  (writer lanes add the last two terms per row).
+template <typename T, typename WT, int KB, int NUB, int RPT, bool INITIAL>
+__global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int C = 4;
+    constexpr int NG = ng_of(NUB);
+    constexpr int LOGR = RPT == 4 ? 2 : (RPT == 2 ? 1 : 0);
+    static_assert(RPT == 1 || RPT == 2 || RPT == 4, "RPT must be 1, 2 or 4");
+    const Geom& g = a.g;
+    const FitDev f = a.fits[blockIdx.y];
+    FitState* st = f.st;
+    if (st->done) return;
+    CtaCtx c;
+    cta_setup(g, smem, c);
+    unsigned char* stages = smem + kCtlBytes;
+    const uint32_t stages32 = smem_u32(stages);
+    const int ucur = st->u_cur, acur = st->a_cur;
+    const T* Acur = reinterpret_cast<const T*>(f.A) + (size_t)acur * g.Kt * g.N;
+    const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
+
+    double cost = 0.0, ssq_r = 0.0, ssq_u = 0.0, dmx = 0.0;
+    constexpr int NSRC = 4;
+    if (threadIdx.x == 0) {
+        TileSrc* src = c.ctl->src;
+        src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
+        src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
+        src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
+        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+    }
+    __syncthreads();
+    Ring pr, cr;
+    pr.init(stages32);
+    cr.init(stages32);
+    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    {
+        const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
+        const bool colvalid = C * tc < g.N;
+        const int j0 = colvalid ? C * tc : 0;
+        const int L = min(g.ntc, 32);
+        const int wpr = (g.ntc + 31) / 32;
+        const int wir = tc >> 5;
+        int rmask = 0, nsplit = 0;
+#pragma unroll
+        for (int s = 0; s < LOGR; ++s)
+            if ((1 << s) < L) {
+                ++nsplit;
+                if ((c.lane >> s) & 1) rmask |= 1 << (LOGR - 1 - s);
+            }
+        const int nslots = RPT >> nsplit;
+        const bool writer = ((c.lane & (L - 1)) >> nsplit) == 0;
+        T ak[KB > 0 ? KB : 1][C];
+        T au[NUB][C];
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) ak[k][cc] = (k < g.K && colvalid && j0 + cc < g.N) ? Acur[(size_t)k * g.N + j0 + cc] : (T)0;
+#pragma unroll
+        for (int q = 0; q < NUB; ++q)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) au[q][cc] = (q < g.nu && colvalid && j0 + cc < g.N) ? Acur[(size_t)(g.K + q) * g.N + j0 + cc] : (T)0;
+        const unsigned xpitch = (unsigned)(g.ldx * sizeof(T)), dpitch = (unsigned)(g.ldd * sizeof(WT));
+        const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
+        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), doff = g.offD + (unsigned)(j0 * sizeof(WT));
+        const int nRch = g.Kp >> 1, nUch = g.nup >> 1;
+        double* RG = f.rowgram;
+
+        for (; cr.it < c.n_my; cr.advance(g, stages32)) {
+            produce_next(g, f, c, pr, stages32, NSRC);
+            mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
+            const uint32_t sb = cr.sb;
+            const int nrows = cr.rows(g, c);
+            const long long grow0 = (long long)cr.gtile * g.tile_rows;
+
+            double gp[RPT][NG];
+#pragma unroll
+            for (int rb = 0; rb < RPT; ++rb) {
+                const int rl = rb ^ rmask;
+                const int r = gr + rl * g.rg;
+                const bool live = (rl < g.rpt) && (r < nrows);
+                const int rr = live ? r : 0;                      // dead slots recompute tile row 0; never stored, never counted
+                T rk[KB > 0 ? KB : 1], uc[NUB > 1 ? NUB : 2];
+#pragma unroll
+                for (int i = 0; i < KB / 2; ++i) {
+                    const int ii = i < nRch ? i : 0;
+                    lds2(sb + g.offR + ii * 2 * (unsigned)sizeof(T) + rr * rpitch, rk[2 * i], rk[2 * i + 1]);
+                }
+#pragma unroll
+                for (int i = 0; i < (NUB + 1) / 2; ++i) {
+                    const int ii = i < nUch ? i : 0;
+                    lds2(sb + g.offU + ii * 2 * (unsigned)sizeof(T) + rr * upitch, uc[2 * i], uc[2 * i + 1]);
+                }
+                if (INITIAL && tc == 0 && live) {
+#pragma unroll
+                    for (int k = 0; k < KB; ++k)
+                        if (k < g.K) ssq_r = fma((double)rk[k], (double)rk[k], ssq_r);
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q)
+                        if (q < g.nu) ssq_u = fma((double)uc[q], (double)uc[q], ssq_u);
+                }
+                T x[C], d[C], cres[C], z[C];
+                ldsC<T, C>(sb + xoff + rr * xpitch, x);
+                WLoad<T, WT, C>::ld(sb + doff + rr * dpitch, d);
+                if (INITIAL) {
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) dmx = fmax(dmx, (double)d[cc]);
+                }
+                if (KB > 0) {
+                    T pk[C], pk1[C];
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) { pk[cc] = rk[0] * ak[0][cc]; pk1[cc] = rk[KB > 1 ? 1 : 0] * ak[KB > 1 ? 1 : 0][cc]; }
+#pragma unroll
+                    for (int k = 2; k < KB; k += 2)
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) {
+                            pk[cc] = fma_t<T>(rk[k], ak[k][cc], pk[cc]);
+                            pk1[cc] = fma_t<T>(rk[k + 1], ak[k + 1][cc], pk1[cc]);
+                        }
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) cres[cc] = x[cc] - (pk[cc] + pk1[cc]);     // c = x - R_trunc a_k
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) cres[cc] = x[cc];
+                }
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) z[cc] = d[cc] * cres[cc];
+                {
+                    T ccr = z[0] * cres[0];
+#pragma unroll
+                    for (int cc = 1; cc < C; ++cc) ccr = fma_t<T>(z[cc], cres[cc], ccr);
+                    if (live && colvalid) cost += (double)ccr;
+                }
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    T bq = z[0] * au[q][0];
+#pragma unroll
+                    for (int cc = 1; cc < C; ++cc) bq = fma_t<T>(z[cc], au[q][cc], bq);
+                    gp[rb][q] = (double)bq;
+                    T t[C];
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) t[cc] = d[cc] * au[q][cc];
+#pragma unroll
+                    for (int q2 = q; q2 < NUB; ++q2) {
+                        T h = t[0] * au[q2][0];
+#pragma unroll
+                        for (int cc = 1; cc < C; ++cc) h = fma_t<T>(t[cc], au[q2][cc], h);
+                        gp[rb][NUB + tri_index(q, q2, NUB)] = (double)h;
+                    }
+                }
+            }
+            // select-free butterfly: split steps halve the slots, then plain xor steps on the remaining slot
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int o = 1 << s;
+                if (o < L) {
+                    if (s < LOGR) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int half = RPT >> (s + 1);
+#pragma unroll
+                        for (int i = 0; i < RPT / 2; ++i)
+                            if (i < half) {
+#pragma unroll
+                                for (int v = 0; v < NG; ++v) gp[i][v] += __shfl_xor_sync(0xffffffffu, gp[(i + half) % RPT][v], o);
+                            }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < NG; ++v) gp[0][v] += __shfl_xor_sync(0xffffffffu, gp[0][v], o);
+                    }
+                }
+            }
+            if (writer) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    if (i < nslots) {
+                        const int rl = i ^ rmask;
+                        const int r = gr + rl * g.rg;
+                        if (rl < g.rpt && r < nrows) {
+                            double* dst = RG + ((size_t)(grow0 + r) * wpr + wir) * NG;
+#pragma unroll
+                            for (int v = 0; v < NG; ++v) dst[v] = gp[i][v];
+                            // cost cross terms of this row (per-warp partial statistics are linear, so partial rows add up)
+                            T un[NUB > 1 ? NUB : 2];
+#pragma unroll
+                            for (int k = 0; k < (NUB + 1) / 2; ++k) {
+                                const int kk = k < nUch ? k : 0;
+                                lds2(sb + g.offU + kk * 2 * (unsigned)sizeof(T) + r * upitch, un[2 * k], un[2 * k + 1]);
+                            }
+                            double ct = 0.0;
+#pragma unroll
+                            for (int q = 0; q < NUB; ++q) {
+                                const double uq = (q < g.nu) ? (double)un[q] : 0.0;
+                                double hq = 0.0;
+#pragma unroll
+                                for (int q2 = 0; q2 < NUB; ++q2) {
+                                    const double u2 = (q2 < g.nu) ? (double)un[q2] : 0.0;
+                                    hq = fma(gp[i][NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], u2, hq);
+                                }
+                                ct = fma(uq, hq - 2.0 * gp[i][q], ct);
+                            }
+                            cost += ct;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
+        }
+    }
+    __syncthreads();
+    double* scratch = reinterpret_cast<double*>(stages);
+    double* rec = scratch + 16;
+    if (c.warp < kConsumers / 32) {
+        const double s0 = consumer_block_sum(cost, scratch, c.ctid);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (INITIAL) {
+            s1 = consumer_block_sum(ssq_r, scratch, c.ctid);
+            s2 = consumer_block_sum(ssq_u, scratch, c.ctid);
+            s3 = consumer_block_max(dmx, scratch, c.ctid);
+        }
+        if (c.ctid == 0) {
+            double* p = f.part + (size_t)blockIdx.x * g.part_stride;
+            p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
+        }
+    }
+    if (!hier_reduce(g, f, rec, 3, &c.ctl->flag)) return;
+    if (threadIdx.x == 0) cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol);
+}
+
+// ------------------------------------------------------------------------------------------------
 // n_iter2 iterations of update_u (deconvolution.py:82-89; gradient at u for the unsupervised variant, :163) per row,
 // on the row's (b, H).  One thread per row; both U slots are rewritten (u and u_ persist across outer iterations).
 template <typename T, int NUB>

@@ -32,7 +32,14 @@ kern_t DMF_CAT(pick_u_, DMF_TAG)(int kb, int nub, int) {
 }
 // Gram engine (dmf_gram.cuh).  rowgram: (known bucket, unknown bucket) -> fixed (columns per thread, rows per thread per tile);
 // see kGramTable in dmf_api.cu
-kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int initial) {
+kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int flags) {
+    const int initial = flags & 1, c4 = flags & 2;
+#define DMF_G4(KB_, NUB_, RPT_)                                                                              \
+    if (c4 && kb == KB_ && nub == NUB_)                                                                      \
+        return initial ? (kern_t)rowgram4_kernel<DMF_T, DMF_WT, KB_, NUB_, RPT_, true> : (kern_t)rowgram4_kernel<DMF_T, DMF_WT, KB_, NUB_, RPT_, false>;
+    DMF_G4(0, 1, 4) DMF_G4(0, 2, 4) DMF_G4(0, 4, 2) DMF_G4(6, 1, 4) DMF_G4(6, 2, 4) DMF_G4(6, 4, 2)
+#undef DMF_G4
+    if (c4) return nullptr;
 #define DMF_G(KB_, NUB_, C_, RPT_)                                                                           \
     if (kb == KB_ && nub == NUB_)                                                                            \
         return initial ? (kern_t)rowgram_kernel<DMF_T, DMF_WT, KB_, NUB_, C_, RPT_, true> : (kern_t)rowgram_kernel<DMF_T, DMF_WT, KB_, NUB_, C_, RPT_, false>;
@@ -43,7 +50,8 @@ kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int initial) {
 #undef DMF_G
     return nullptr;
 }
-kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int, int) {
+kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int c, int) {
+    if (pb == 8 && c == 4) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 4>;
     if (pb == 8) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 2>;
     if (pb == 16) return gram_panel_kernel<DMF_T, DMF_WT, 2, 16, 1>;
     return nullptr;
