@@ -52,7 +52,13 @@ struct dmf_batch_s {
     int gram_ok;            // this shape has Gram-engine instantiations
     Geom gg;                // tile geometry of the Gram-engine streaming passes (no u_prev in the stage)
     int kb_g, nub_g, c_g, ntc_g, pb_g, c_p, ntc_p, ktb_in;
+    int n_parts_u, n_groups_u;
     unsigned smem_rg, smem_panel;
+    // momentum table (library-owned, grows on demand): a_t and (a_t - 1) / a_{t+1}
+    std::vector<double> mom_host;   // [a_0 .. a_{n-1} | m_0 .. m_{n-1}] is rebuilt on growth
+    double* mom_dev;
+    size_t mom_cap;                 // entries per array on the device
+    long long t_hi;                 // upper bound of the inner-iteration index any fit of the batch can have reached
 };
 
 namespace {
@@ -85,6 +91,7 @@ struct Plan {
     // Gram engine
     int gram_ok, kb_g, nub_g, c_g, rpt_g_max, rpt_g, ntc_g, occ_g, pb_g, c_p, ntc_p, ktb_in;
     int tile_rows_g, n_tiles_g, n_parts_g, n_groups_g, wpr_g, ng_g;
+    int n_parts_u, n_groups_u;     // u_inner_kernel: one thread per row, many more CTAs than the streaming passes
     unsigned g_offX, g_offD, g_offR, g_offU, g_stage_bytes, smem_rg, smem_panel;
     size_t off_rowgram, off_gram, off_gbx, off_red, per_fit_rowgram, per_fit_gram, per_fit_gbx, per_fit_red;
 };
@@ -180,17 +187,16 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
 
     // ---- Gram-form engine (dmf_gram.cuh): n_u <= 4, own tile geometry (no u_prev in the stage, rows per thread from kGramTable)
     p.gram_ok = 0;
-    p.n_parts_g = p.n_groups_g = 0;
+    p.n_parts_g = p.n_groups_g = p.n_parts_u = p.n_groups_u = 0;
     p.per_fit_rowgram = p.per_fit_gram = p.per_fit_gbx = p.per_fit_red = 0;
     if (s.n_u <= 4) {
         p.kb_g = s.K == 0 ? 0 : (p.Kp <= 6 ? 6 : (p.Kp <= 16 ? 16 : 32));
         p.nub_g = s.n_u == 1 ? 1 : (s.n_u == 2 ? 2 : 4);
-        const bool pitch4 = (s.ldx % 4 == 0) && (s.ldd % 4 == 0);     // 4-column kernels: rows of X, d_x padded to multiples of 4
-        p.c_g = (p.kb_g <= 6 && pitch4) ? 4 : (p.kb_g <= 16 ? 2 : 1);
+        p.c_g = p.kb_g <= 6 ? 4 : (p.kb_g <= 16 ? 2 : 1);
         p.rpt_g_max = p.c_g == 4 ? (p.nub_g <= 2 ? 4 : 2) : (p.nub_g == 1 ? 4 : (p.nub_g == 2 ? 3 : 2));
         p.ng_g = ng_of_h(p.nub_g);
         p.pb_g = rowlen <= 8 ? 8 : 16;
-        p.c_p = p.pb_g == 8 ? (pitch4 ? 4 : 2) : 1;
+        p.c_p = p.pb_g == 8 ? 4 : 1;
         p.ktb_in = Kt <= 8 ? 8 : (Kt <= 16 ? 16 : 32);
         if (s.N <= kConsumers * p.c_g && s.N <= kConsumers * p.c_p) {
             p.ntc_g = next_pow2((s.N + p.c_g - 1) / p.c_g);
@@ -229,6 +235,8 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 if (s.max_ctas_per_fit > 0) per_fit_g = std::min<long long>(per_fit_g, s.max_ctas_per_fit);
                 p.n_parts_g = (int)std::min<long long>(per_fit_g, p.n_tiles_g);
                 p.n_groups_g = (p.n_parts_g + kGroup - 1) / kGroup;
+                p.n_parts_u = (int)std::min<long long>((s.M + kThreads - 1) / kThreads, std::max<long long>(p.n_parts_g, (long long)h->sm_count * 8 / s.n_fits));
+                p.n_groups_u = (p.n_parts_u + kGroup - 1) / kGroup;
                 const size_t pipe_g = kCtlBytes + (size_t)kStages * p.g_stage_bytes;
                 p.smem_rg = (unsigned)std::max(pipe_g, (size_t)kCtlBytes + 512);
                 p.smem_panel = (unsigned)std::max(pipe_g, epi_panel);
@@ -241,7 +249,8 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
             }
         }
     }
-    const int parts_max = std::max(p.n_parts, p.n_parts_g), groups_max = std::max(p.n_groups, p.n_groups_g);
+    const int parts_max = std::max(p.n_parts, p.n_parts_g), groups_max = std::max(std::max(p.n_groups, p.n_groups_g), p.n_groups_u);
+    // u_inner_kernel records are 8 doubles apart: n_parts_u * 8 <= parts_max * part_stride holds because part_stride >= 2 * 9 * N
 
     // workspace layout
     p.off_fits = 0;
@@ -257,6 +266,36 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     p.off_gbx = p.off_gram + p.per_fit_gram * s.n_fits;
     p.off_red = p.off_gbx + p.per_fit_gbx * s.n_fits;
     p.ws_bytes = align_up(p.off_red + p.per_fit_red * s.n_fits, 256);
+    return DMF_OK;
+}
+
+// Make sure the device momentum table covers indices [0, need].  Growth synchronises the stream (rare: the table doubles).
+int ensure_mom(dmf_batch_s* b, long long need, cudaStream_t st) {
+    if ((size_t)need + 1 <= b->mom_cap) return DMF_OK;
+    size_t cap = std::max<size_t>(4096, b->mom_cap * 2);
+    while (cap < (size_t)need + 1) cap *= 2;
+    std::vector<double> h(2 * cap);
+    volatile double a0 = 1.0;
+    for (size_t t = 0; t < cap; ++t) {
+        volatile double sq = 4.0 * a0;
+        sq = sq * a0;
+        sq = 1.0 + sq;
+        volatile double a1 = (1.0 + sqrt((double)sq)) / 2.0;     // deconvolution.py:84, same operation order as the device code
+        h[t] = a0;
+        h[cap + t] = (a0 - 1.0) / a1;
+        a0 = a1;
+    }
+    double* dev = nullptr;
+    CUDA_TRY(cudaMalloc(&dev, 2 * cap * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(dev, h.data(), 2 * cap * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // also retires every launch that still reads the old table
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return fail(DMF_E_CUDA, std::string("momentum table: ") + cudaGetErrorString(e));
+    }
+    if (b->mom_dev) cudaFree(b->mom_dev);
+    b->mom_dev = dev;
+    b->mom_cap = cap;
     return DMF_OK;
 }
 
@@ -277,6 +316,7 @@ int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_in
     a.flags = flags;
     a.tol = tol;
     a.ca0 = a.cb0 = a.with_x = a.pad = 0;
+    a.mom_a = b->mom_dev; a.mom_m = b->mom_dev ? b->mom_dev + b->mom_cap : nullptr;
     dim3 grid(b->g.n_parts, b->shape.n_fits, 1);
     k<<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -294,7 +334,7 @@ kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in,
 
 // Gram-engine launch: geometry gg; ntc selects the thread mapping of the kernel; grid_x CTAs per fit (0: one CTA per fit on grid.x)
 int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_inner, double tol, int ca0, int cb0, int with_x,
-             bool per_fit_grid, cudaStream_t st) {
+             int grid_mode /* 0: pass grid, 1: one CTA per fit, 2: wide row grid of u_inner_kernel */, cudaStream_t st) {
     if (!k) return fail(DMF_E_SHAPE, "no Gram-engine kernel instantiation for this shape");
     PassArgs a;
     a.g = b->gg;
@@ -305,7 +345,14 @@ int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_
     a.flags = flags;
     a.tol = tol;
     a.ca0 = ca0; a.cb0 = cb0; a.with_x = with_x; a.pad = 0;
-    dim3 grid = per_fit_grid ? dim3(b->shape.n_fits, 1, 1) : dim3(b->gg.n_parts, b->shape.n_fits, 1);
+    a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
+    dim3 grid = grid_mode == 1 ? dim3(b->shape.n_fits, 1, 1) : dim3(b->gg.n_parts, b->shape.n_fits, 1);
+    if (grid_mode == 2) {
+        a.g.n_parts = b->n_parts_u;
+        a.g.n_groups = b->n_groups_u;
+        if (b->n_parts_u != b->gg.n_parts) a.g.part_stride = 8;
+        grid = dim3(b->n_parts_u, b->shape.n_fits, 1);
+    }
     k<<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     b->launches++;
@@ -435,6 +482,9 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->shape = s;
     b->launches = 0;
     b->pinned = nullptr;
+    b->mom_dev = nullptr;
+    b->mom_cap = 0;
+    b->t_hi = 0;
     Geom& g = b->g;
     g.M = s.M; g.N = s.N; g.K = s.K; g.nu = s.n_u; g.Kt = s.K + s.n_u;
     g.ldx = s.ldx; g.ldd = s.ldd; g.ldr = s.K ? s.ldr : 0; g.ldu = s.ldu;
@@ -475,6 +525,10 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         q.tile_tx[4] = 0;
         b->kb_g = p.kb_g; b->nub_g = p.nub_g; b->c_g = p.c_g; b->ntc_g = p.ntc_g; b->pb_g = p.pb_g; b->c_p = p.c_p; b->ntc_p = p.ntc_p;
         b->ktb_in = p.ktb_in; b->smem_rg = p.smem_rg; b->smem_panel = p.smem_panel;
+        b->n_parts_u = p.n_parts_u; b->n_groups_u = p.n_groups_u;
+        if ((long long)p.n_parts_u * 8 > (long long)std::max(p.n_parts, p.n_parts_g) * p.part_stride || (long long)p.n_groups_u * 8 > (long long)std::max(p.n_groups, p.n_groups_g) * p.part_stride) {
+            b->n_parts_u = p.n_parts_g; b->n_groups_u = p.n_groups_g;     // partial-sum buffers too small for the wide grid (tiny N): use the pass grid
+        }
         if ((rc = set_smem(k_rowgram(b, 0), b->smem_rg)) || (rc = set_smem(k_rowgram(b, 1), b->smem_rg)) || (rc = set_smem(k_panel(b), b->smem_panel)) ||
             (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0))) {
             delete b;
@@ -502,6 +556,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
 int dmf_batch_destroy(dmf_batch_t b) {
     if (!b) return DMF_OK;
     if (b->pinned) cudaFreeHost(b->pinned);
+    if (b->mom_dev) cudaFree(b->mom_dev);
     delete b;
     return DMF_OK;
 }
@@ -516,6 +571,7 @@ int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows,
 
 int dmf_pass_init(dmf_batch_t b, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
+    b->t_hi = 0;
     return launch(b, k_cost(b, 1), b->ntc_alpha, b->smem_cost, kFlagInitial, 0, 0.0, (cudaStream_t)stream);
 }
 int dmf_pass_cost(dmf_batch_t b, double tol, void* stream) {
@@ -524,6 +580,7 @@ int dmf_pass_cost(dmf_batch_t b, double tol, void* stream) {
 }
 int dmf_pass_u(dmf_batch_t b, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
+    b->t_hi += 1;     // keeps the momentum-table bound valid if Gram-engine steps follow on the same batch
     return launch(b, k_u(b), b->ntc_u, b->smem_u, 0, 0, 0.0, (cudaStream_t)stream);
 }
 int dmf_pass_alpha(dmf_batch_t b, void* stream) {
@@ -553,12 +610,17 @@ int dmf_batch_get_engine(dmf_batch_t b, int32_t* engine) {
 int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
-    return launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, false, (cudaStream_t)stream);
+    if (initial) b->t_hi = 0;
+    return launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 int dmf_gram_u_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
-    return launch_g(b, k_uinner(b), b->ntc_g, 0, 0, n_iter2, 0.0, 0, 0, 0, false, (cudaStream_t)stream);
+    if (n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
+    b->t_hi += n_iter2;
+    int rc = ensure_mom(b, b->t_hi, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_g(b, k_uinner(b), b->ntc_g, 0, 0, n_iter2, 0.0, 0, 0, 0, 2, (cudaStream_t)stream);
 }
 int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
@@ -569,13 +631,17 @@ int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
     int rc;
     for (int ca = ca_lo; ca < ca_hi; ++ca)
         for (int cb = 0; cb < cb_hi; cb += nb)
-            if ((rc = launch_g(b, k_panel(b), b->ntc_p, b->smem_panel, 0, 0, 0.0, ca, cb, cb == 0 ? 1 : 0, false, (cudaStream_t)stream))) return rc;
+            if ((rc = launch_g(b, k_panel(b), b->ntc_p, b->smem_panel, 0, 0, 0.0, ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream))) return rc;
     return DMF_OK;
 }
 int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
-    return launch_g(b, k_ainner(b), b->ntc_p, 0, b->shape.mode == DMF_MODE_PURITY ? kFlagFW : 0, n_iter2, 0.0, 0, 0, 0, true, (cudaStream_t)stream);
+    if (n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
+    // alpha steps never run ahead of the U steps by more than one call; cover t_hi + n_iter2 to be independent of call order
+    int rc = ensure_mom(b, b->t_hi + n_iter2, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_g(b, k_ainner(b), b->ntc_p, 0, b->shape.mode == DMF_MODE_PURITY ? kFlagFW : 0, n_iter2, 0.0, 0, 0, 0, 1, (cudaStream_t)stream);
 }
 int dmf_gram_init(dmf_batch_t b, void* stream) {
     int rc = dmf_gram_rowgram(b, 1, 0.0, stream);

@@ -25,7 +25,8 @@ struct FitState {
     double ssq_rk, ssq_u;          // ||R_trunc||_F^2 (constant) and ||u||_F^2 (current)
     int u_cur, a_cur;              // ping-pong slots holding the current iterate
     int n_outer, done;             // done: 0 running, 1 converged, 3 numerical failure (NaN in projection)
-    int pad[4];
+    int t_u, t_a;                  // inner iterations of update_u / update_alpha executed so far (index into the momentum table)
+    int pad[2];
 };
 
 struct FitDev {
@@ -78,6 +79,10 @@ struct PassArgs {
     int ca0, cb0;     // gram_panel_kernel: first chunk (pair of padded register-row entries) of the za / zb blocks
     int with_x;       // gram_panel_kernel: also emit R^T (d o x) for the za block
     int pad;
+    // momentum table (data independent, deconvolution.py:83-85): mom_a[t] = a_t (a_0 = 1, a_{t+1} = (1 + sqrt(1 + 4 a_t^2)) / 2),
+    // mom_m[t] = (a_t - 1) / a_{t+1}; filled by the host for every inner-iteration index a launch can reach
+    const double* mom_a;
+    const double* mom_m;
 };
 constexpr int kFlagInitial = 1;   // init_cost_kernel: set-up pass (norms, max d, no termination test)
 constexpr int kFlagFW = 2;        // alpha_pass_kernel: Frank-Wolfe step instead of projected gradient

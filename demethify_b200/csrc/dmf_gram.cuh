@@ -57,6 +57,8 @@ __device__ __forceinline__ void cost_state_update(const Geom& g, const FitDev& f
         st->cf = cf;
         st->cf_prev = cf;
         st->n_outer = 0;
+        st->t_u = 0;
+        st->t_a = 0;
         if (f.trace && f.trace_cap > 0) f.trace[0] = cf;
     } else {
         const double prev = st->cf;
@@ -247,7 +249,48 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
 }
 
 // ------------------------------------------------------------------------------------------------
-// rowgram pass, 4 columns per thread (row pitches of X and d_x multiples of 4, zero padded).  Differences to rowgram_kernel:
+// Column ownership of a thread.  C <= 2: C adjacent columns starting at C * tc.  C == 4: two adjacent pairs 2 * ntc columns
+// apart (columns 2 tc, 2 tc + 1, 2 tc + 2 ntc, 2 tc + 2 ntc + 1), so that every vector load of a warp is contiguous in shared
+// memory (no bank conflicts) and even row pitches suffice.  Pairs beyond N are redirected to column 0: they read valid data,
+// their alpha entries are zero and their results are never stored.
+template <int C>
+__device__ __forceinline__ int col_index(int tc, int ntc, int cc) { return C == 4 ? 2 * tc + (cc & 1) + (cc >> 1) * 2 * ntc : C * tc + cc; }
+
+template <typename T, typename WT, int C>
+struct ColLoader {
+    static constexpr int NP = C == 4 ? 2 : 1;
+    unsigned xo[NP], dofs[NP];
+    bool pvalid[NP];
+    __device__ __forceinline__ void init(const Geom& g, int tc) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int jb = col_index<C>(tc, g.ntc, 2 * p);
+            pvalid[p] = jb < g.N;
+            const int j = pvalid[p] ? jb : 0;
+            xo[p] = g.offX + (unsigned)(j * sizeof(T));
+            dofs[p] = g.offD + (unsigned)(j * sizeof(WT));
+        }
+    }
+    // rx / rd: byte offset of the row inside the X / D region of the stage
+    __device__ __forceinline__ void load(uint32_t sb, unsigned rx, unsigned rd, T (&x)[C], T (&d)[C]) const {
+        if (C == 4) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                T xx[2], dd[2];
+                lds2(sb + xo[p] + rx, xx[0], xx[1]);
+                WLoad<T, WT, 2>::ld(sb + dofs[p] + rd, dd);
+                x[(2 * p) % C] = xx[0]; x[(2 * p + 1) % C] = xx[1];
+                d[(2 * p) % C] = dd[0]; d[(2 * p + 1) % C] = dd[1];
+            }
+        } else {
+            ldsC<T, C>(sb + xo[0] + rx, x);
+            WLoad<T, WT, C>::ld(sb + dofs[0] + rd, d);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// rowgram pass, 4 columns per thread (two pairs, see ColLoader).  Differences to rowgram_kernel:
 //  * a thread owns 4 adjacent columns and RPT rows of the tile -> the broadcast [R_trunc | u] row loads, the address
 //    arithmetic and the per-tile ring bookkeeping are spread over 4 x RPT elements;
 //  * the row -> register-slot assignment is lane dependent (slot rb holds tile row rb ^ rmask(lane)), so the first
@@ -289,8 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
-        const bool colvalid = C * tc < g.N;
-        const int j0 = colvalid ? C * tc : 0;
+        ColLoader<T, WT, C> cl;
+        cl.init(g, tc);
         const int L = min(g.ntc, 32);
         const int wpr = (g.ntc + 31) / 32;
         const int wir = tc >> 5;
@@ -308,14 +351,19 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
 #pragma unroll
         for (int k = 0; k < KB; ++k)
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) ak[k][cc] = (k < g.K && colvalid && j0 + cc < g.N) ? Acur[(size_t)k * g.N + j0 + cc] : (T)0;
+            for (int cc = 0; cc < C; ++cc) {
+                const int j = col_index<C>(tc, g.ntc, cc);
+                ak[k][cc] = (k < g.K && j < g.N) ? Acur[(size_t)k * g.N + j] : (T)0;
+            }
 #pragma unroll
         for (int q = 0; q < NUB; ++q)
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) au[q][cc] = (q < g.nu && colvalid && j0 + cc < g.N) ? Acur[(size_t)(g.K + q) * g.N + j0 + cc] : (T)0;
+            for (int cc = 0; cc < C; ++cc) {
+                const int j = col_index<C>(tc, g.ntc, cc);
+                au[q][cc] = (q < g.nu && j < g.N) ? Acur[(size_t)(g.K + q) * g.N + j] : (T)0;
+            }
         const unsigned xpitch = (unsigned)(g.ldx * sizeof(T)), dpitch = (unsigned)(g.ldd * sizeof(WT));
         const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
-        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), doff = g.offD + (unsigned)(j0 * sizeof(WT));
         const int nRch = g.Kp >> 1, nUch = g.nup >> 1;
         double* RG = f.rowgram;
 
@@ -353,8 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                         if (q < g.nu) ssq_u = fma((double)uc[q], (double)uc[q], ssq_u);
                 }
                 T x[C], d[C], cres[C], z[C];
-                ldsC<T, C>(sb + xoff + rr * xpitch, x);
-                WLoad<T, WT, C>::ld(sb + doff + rr * dpitch, d);
+                cl.load(sb, rr * xpitch, rr * dpitch, x, d);
                 if (INITIAL) {
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) dmx = fmax(dmx, (double)d[cc]);
@@ -379,10 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc) z[cc] = d[cc] * cres[cc];
                 {
-                    T ccr = z[0] * cres[0];
-#pragma unroll
-                    for (int cc = 1; cc < C; ++cc) ccr = fma_t<T>(z[cc], cres[cc], ccr);
-                    if (live && colvalid) cost += (double)ccr;
+                    const T ccA = fma_t<T>(z[1], cres[1], z[0] * cres[0]), ccB = fma_t<T>(z[3], cres[3], z[2] * cres[2]);
+                    if (live) cost += (cl.pvalid[0] ? (double)ccA : 0.0) + (cl.pvalid[1] ? (double)ccB : 0.0);
                 }
 #pragma unroll
                 for (int q = 0; q < NUB; ++q) {
@@ -495,8 +540,12 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
     if (st->done) return;
     const int n2 = a.k_inner;
     const int ucur = st->u_cur;
-    const double l_w = st->l_w, a_in = st->a1, lwo_in = st->l_w_old;
-    const T lw = (T)l_w;
+    const double l_w = st->l_w, lwo_in = st->l_w_old;
+    const T inv_lw = (T)1 / (T)l_w;      // step 1 / l_w as a reciprocal multiply: <= 1 ulp of a ~1e-4-sized step vs the division of :88
+    const int t0 = st->t_u;
+    const double* mm = a.mom_m + t0;
+    // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
+    const double cap0 = 0.9999 * sqrt(lwo_in / l_w), cap1 = 0.9999 * sqrt(l_w / l_w);
     T* Uc = reinterpret_cast<T*>(f.U + (size_t)ucur * g.uslot_bytes);
     T* Up = reinterpret_cast<T*>(f.U + (size_t)(ucur ^ 1) * g.uslot_bytes);
     const bool at_current = (g.mode == 2);
@@ -518,12 +567,8 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
             u[q] = q < g.nu ? Uc[(size_t)row * g.ldu + q] : (T)0;
             up[q] = q < g.nu ? Up[(size_t)row * g.ldu + q] : (T)0;
         }
-        double am = a_in, lwo = lwo_in;
         for (int it = 0; it < n2; ++it) {
-            const double a0 = am;
-            am = next_momentum(a0);
-            const T beta = (T)extrap_beta(a0, am, lwo, l_w);
-            lwo = l_w;
+            const T beta = (T)fmin(__ldg(mm + it), it == 0 ? cap0 : cap1);
             T ut[NUB], ug[NUB];
 #pragma unroll
             for (int q = 0; q < NUB; ++q) {
@@ -539,7 +584,7 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
                     s = fma(h, (double)ug[q2], s);
                 }
                 const double gq = v[q] - s;
-                T un = ut[q] + (T)gq / lw;
+                T un = ut[q] + (T)gq * inv_lw;
                 un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
                 up[q] = u[q];
                 u[q] = un;
@@ -557,9 +602,8 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
     if (threadIdx.x == 0) f.part[(size_t)blockIdx.x * g.part_stride] = s0;
     if (!hier_reduce(g, f, rec, 1, &flag)) return;
     if (threadIdx.x == 0) {
-        double am = a_in;
-        for (int it = 0; it < n2; ++it) am = next_momentum(am);
-        st->a1 = am;
+        st->a1 = a.mom_a[t0 + n2];
+        st->t_u = t0 + n2;
         if (n2 > 0) st->l_w_old = l_w;                       // deconvolution.py:89
         st->ssq_u = rec[0];
         const double nr = sqrt(st->ssq_rk + rec[0]);
@@ -587,8 +631,7 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
     const int ucur = st->u_cur;
     const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
     const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
-    const bool colvalid = C * tc < g.N;
-    const int j0 = colvalid ? C * tc : 0;
+    const bool colvalid = col_index<C>(tc, g.ntc, 0) < g.N;      // the first owned column (C == 4: first pair) exists
     double acc[PA][PB][C], accx[PA][C];
 #pragma unroll
     for (int p = 0; p < PA; ++p)
@@ -624,8 +667,9 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
         for (int i = 0; i < NA; ++i) locate(a.ca0 + i, aoff[i], apitch[i]);
 #pragma unroll
         for (int i = 0; i < NB; ++i) locate(a.cb0 + i, boff[i], bpitch[i]);
-        const unsigned xoff = g.offX + (unsigned)(j0 * sizeof(T)), xpitch = (unsigned)(g.ldx * sizeof(T));
-        const unsigned doff = g.offD + (unsigned)(j0 * sizeof(WT)), dpitch = (unsigned)(g.ldd * sizeof(WT));
+        const unsigned xpitch = (unsigned)(g.ldx * sizeof(T)), dpitch = (unsigned)(g.ldd * sizeof(WT));
+        ColLoader<T, WT, C> cl;
+        cl.init(g, tc);
         for (; cr.it < c.n_my; cr.advance(g, stages32)) {
             produce_next(g, f, c, pr, stages32, NSRC);
             mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
@@ -638,8 +682,7 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
                     for (int i = 0; i < NA; ++i) lds2(sb + aoff[i] + r * apitch[i], za[2 * i], za[2 * i + 1]);
 #pragma unroll
                     for (int i = 0; i < NB; ++i) lds2(sb + boff[i] + r * bpitch[i], zb[2 * i], zb[2 * i + 1]);
-                    ldsC<T, C>(sb + xoff + r * xpitch, x);
-                    WLoad<T, WT, C>::ld(sb + doff + r * dpitch, d);
+                    cl.load(sb, r * xpitch, r * dpitch, x, d);
 #pragma unroll
                     for (int p = 0; p < PA; ++p)
 #pragma unroll
@@ -665,16 +708,18 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
         for (int gg = 0; gg < g.rg; ++gg) {
             if (gr == gg && colvalid) {
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc)
-                    if (j0 + cc < g.N) {
+                for (int cc = 0; cc < C; ++cc) {
+                    const int j = col_index<C>(tc, g.ntc, cc);
+                    if (j < g.N) {
 #pragma unroll
                         for (int q = 0; q < PB; ++q) {
-                            double* ptr = &scratch[(size_t)q * g.N + j0 + cc];
+                            double* ptr = &scratch[(size_t)q * g.N + j];
                             *ptr = (gg == 0) ? acc[p][q][cc] : (*ptr + acc[p][q][cc]);
                         }
-                        double* ptr = &scratch[(size_t)PB * g.N + j0 + cc];
+                        double* ptr = &scratch[(size_t)PB * g.N + j];
                         *ptr = (gg == 0) ? accx[p][cc] : (*ptr + accx[p][cc]);
                     }
+                }
             }
             __syncthreads();
         }
@@ -703,6 +748,51 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
 }
 
 // ------------------------------------------------------------------------------------------------
+// projection_simplex_sort_2d (deconvolution.py:21-37) of one column held in registers: bitonic sorting network
+// (compile-time indices only), entries k >= p are padding.  Returns false when v holds a NaN (the reference
+// raises ZeroDivisionError there: rho stays -1).
+template <int KTB>
+__device__ __forceinline__ bool project_simplex_reg(double (&v)[KTB], int p) {
+    double u[KTB];
+    bool nan = false;
+#pragma unroll
+    for (int k = 0; k < KTB; ++k) {
+        u[k] = k < p ? v[k] : -1.0e300;
+        nan |= (k < p) && !(v[k] == v[k]);
+    }
+    if (nan) return false;
+#pragma unroll
+    for (int kk = 2; kk <= KTB; kk <<= 1)
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < KTB; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool desc = (i & kk) == 0;
+                    const double hi = fmax(u[i], u[l]), lo = fmin(u[i], u[l]);
+                    u[i] = desc ? hi : lo;
+                    u[l] = desc ? lo : hi;
+                }
+            }
+    double cs = 0.0, theta = 0.0;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < KTB; ++j) {
+        if (j < p) {
+            cs += u[j];
+            const double pi = cs - 1.0;
+            const double th = pi / (double)(j + 1);
+            if (u[j] - th > 0.0) { found = true; theta = th; }
+        }
+    }
+    if (!found) return false;
+#pragma unroll
+    for (int k = 0; k < KTB; ++k) v[k] = fmax(v[k] - theta, 0.0);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // n_iter2 iterations of update_alpha (deconvolution.py:94-101 with projection :21-37) or of frank_wolfe_nmf (:285-299)
 // per sample column on (G_j, bx_j).  One CTA per fit, one thread per sample.  alpha and alpha_ both persist.
 template <typename T, int KTB>
@@ -716,7 +806,11 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
     const bool fw = (a.flags & kFlagFW) != 0;
     const int n2 = a.k_inner, Kt = g.Kt;
     const int acur = st->a_cur;
-    const double l_h = st->l_h, a_in = st->a2, lho_in = st->l_h_old;
+    const double l_h = st->l_h, lho_in = st->l_h_old;
+    const int t0 = st->t_a;
+    const double* mm = a.mom_m + t0;
+    const double cap0 = 0.9999 * sqrt(lho_in / l_h), cap1 = 0.9999 * sqrt(l_h / l_h);
+    const double inv_lh = 1.0 / l_h;
     T* Acur = reinterpret_cast<T*>(f.A) + (size_t)acur * g.Kt * g.N;
     T* Aprev = reinterpret_cast<T*>(f.A) + (size_t)(acur ^ 1) * g.Kt * g.N;
     if (threadIdx.x == 0) s_bad = 0;
@@ -733,14 +827,10 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
             for (int l = 0; l < KTB; ++l) G[k][l] = (k < Kt && l < Kt) ? f.gram[((size_t)k * Kt + l) * g.N + j] : 0.0;
         }
         if (!fw) {
-            double am = a_in, lho = lho_in;
             bool bad = false;
             for (int it = 0; it < n2 && !bad; ++it) {
-                const double a0 = am;
-                am = next_momentum(a0);
-                const double beta = (double)(T)extrap_beta(a0, am, lho, l_h);
-                lho = l_h;
-                double at[KTB], v[kMaxKt];
+                const double beta = (double)(T)fmin(__ldg(mm + it), it == 0 ? cap0 : cap1);
+                double at[KTB], v[KTB <= 16 ? KTB : kMaxKt];
 #pragma unroll(KTB <= 8 ? KTB : 1)
                 for (int k = 0; k < KTB; ++k) at[k] = (double)(T)(ac[k] + beta * (ac[k] - ap[k]));
 #pragma unroll(KTB <= 8 ? KTB : 1)
@@ -748,9 +838,11 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
                     double s = 0.0;
 #pragma unroll(KTB <= 8 ? KTB : 1)
                     for (int l = 0; l < KTB; ++l) s = fma(G[k][l], at[l], s);
-                    v[k] = (double)(T)(at[k] + (double)(T)((b[k] - s) / l_h));
+                    v[k] = (double)(T)(at[k] + (double)(T)((b[k] - s) * inv_lh));
                 }
-                if (!project_simplex(v, Kt)) { bad = true; break; }
+                if (KTB <= 16) {
+                    if (!project_simplex_reg<(KTB <= 16 ? KTB : 2)>(reinterpret_cast<double(&)[KTB <= 16 ? KTB : 2]>(v), Kt)) { bad = true; break; }
+                } else if (!project_simplex(v, Kt)) { bad = true; break; }
 #pragma unroll(KTB <= 8 ? KTB : 1)
                 for (int k = 0; k < KTB; ++k) { ap[k] = ac[k]; ac[k] = k < Kt ? (double)(T)v[k] : 0.0; }
             }
@@ -801,9 +893,8 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
         const double na = sqrt(sa);
         st->l_w = (na * na) * st->dmax2;                 // deconvolution.py:216 / :327
         if (!fw) {
-            double am = a_in;
-            for (int it = 0; it < n2; ++it) am = next_momentum(am);
-            st->a2 = am;
+            st->a2 = a.mom_a[t0 + n2];
+            st->t_a = t0 + n2;
             if (n2 > 0) st->l_h_old = l_h;               // deconvolution.py:101
         }
     }

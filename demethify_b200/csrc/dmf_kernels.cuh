@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
             st->cf = cf;
             st->cf_prev = cf;
             st->n_outer = 0;
+            st->t_u = 0;
+            st->t_a = 0;
             if (f.trace && f.trace_cap > 0) f.trace[0] = cf;
         } else {
             const double prev = st->cf;
@@ -584,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
     if (!hier_reduce(g, f, rec, 1, &c.ctl->flag)) return;
     if (threadIdx.x == 0) {
         st->a1 = a_next;
+        st->t_u += 1;
         st->l_w_old = l_w;                                   // deconvolution.py:89
         st->u_cur = ucur ^ 1;
         st->ssq_u = rec[0];
@@ -792,6 +795,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
         st->l_w = (na * na) * st->dmax2;                 // deconvolution.py:216 / :327 (read by the U steps only)
         if (!fw) {
             st->a2 = a_next;
+            st->t_a += 1;
             st->l_h_old = l_h;                           // deconvolution.py:101
             st->a_cur = acur ^ 1;
         }

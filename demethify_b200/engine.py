@@ -51,11 +51,6 @@ def _even(n):
     return n + (n & 1)
 
 
-def _pad4(n):
-    """Row pitch of X and d_x: multiples of 4 elements let the library use its 4-columns-per-thread kernels."""
-    return (n + 3) // 4 * 4
-
-
 def _pad_cols(t, width):
     """Zero-pad a 2-D device tensor on the right to `width` columns (ABI: even pitches, zero padding)."""
     if t.shape[1] == width:
@@ -93,7 +88,7 @@ class DeviceProblem:
         self.dtype = _tdtype(self.precision)
         X = to_device(X, self.dtype, self.device)
         self.M, self.N = X.shape
-        self.ldx = _pad4(self.N)
+        self.ldx = _even(self.N)
         self.X = _pad_cols(X, self.ldx)
         self.K = 0
         self.Rk = None

@@ -4,7 +4,7 @@
 # Everything lands in gpurun_out/<tag>_*.
 set -u
 TAG=${1:-rX}; shift || true
-KERNELS=${@:-"rowgram_kernel gram_panel_kernel u_inner_kernel alpha_inner_kernel"}
+KERNELS=${@:-"rowgram4_kernel gram_panel_kernel u_inner_kernel alpha_inner_kernel"}
 OUT=gpurun_out
 mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest=$?"
