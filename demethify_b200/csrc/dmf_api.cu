@@ -9,6 +9,7 @@
 #include "../../include/demethify_b200.h"
 #include "dmf_device.cuh"
 #include "dmf_inst.h"
+#include "dmf_gram.cuh"
 
 using namespace dmf;
 
@@ -54,6 +55,10 @@ struct dmf_batch_s {
     int kb_g, nub_g, c_g, ntc_g, pb_g, c_p, ntc_p, ktb_in;
     int n_parts_u, n_groups_u;
     unsigned smem_rg, smem_panel;
+    int sharded;                    // CpG rows sharded over GPUs: kernels publish partial sums, finalize runs on all-reduced sums
+    std::vector<FitDev> fits_host;
+    double *stats_local, *stats_global;
+    size_t stats_doubles, stats_gbx, stats_scal;
     // momentum table (library-owned, grows on demand): a_t and (a_t - 1) / a_{t+1}
     std::vector<double> mom_host;   // [a_0 .. a_{n-1} | m_0 .. m_{n-1}] is rebuilt on growth
     double* mom_dev;
@@ -93,7 +98,8 @@ struct Plan {
     int tile_rows_g, n_tiles_g, n_parts_g, n_groups_g, wpr_g, ng_g;
     int n_parts_u, n_groups_u;     // u_inner_kernel: one thread per row, many more CTAs than the streaming passes
     unsigned g_offX, g_offD, g_offR, g_offU, g_stage_bytes, smem_rg, smem_panel;
-    size_t off_rowgram, off_gram, off_gbx, off_red, per_fit_rowgram, per_fit_gram, per_fit_gbx, per_fit_red;
+    size_t off_rowgram, off_stats, off_gstats, off_red, per_fit_rowgram, per_fit_stats, per_fit_red;
+    size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
 };
 
 constexpr int pow2ceil_h(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -188,7 +194,8 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     // ---- Gram-form engine (dmf_gram.cuh): n_u <= 4, own tile geometry (no u_prev in the stage, rows per thread from kGramTable)
     p.gram_ok = 0;
     p.n_parts_g = p.n_groups_g = p.n_parts_u = p.n_groups_u = 0;
-    p.per_fit_rowgram = p.per_fit_gram = p.per_fit_gbx = p.per_fit_red = 0;
+    p.per_fit_rowgram = p.per_fit_stats = p.per_fit_red = 0;
+    p.stats_gbx = p.stats_scal = 0;
     if (s.n_u <= 4) {
         p.kb_g = s.K == 0 ? 0 : (p.Kp <= 6 ? 6 : (p.Kp <= 16 ? 16 : 32));
         p.nub_g = s.n_u == 1 ? 1 : (s.n_u == 2 ? 2 : 4);
@@ -242,8 +249,9 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 p.smem_panel = (unsigned)std::max(pipe_g, epi_panel);
                 p.part_stride = std::max(p.part_stride, (int)align_up((size_t)2 * (p.pb_g + 1) * s.N, 2));
                 p.per_fit_rowgram = align_up((size_t)s.M * p.wpr_g * p.ng_g * 8, 256);
-                p.per_fit_gram = align_up((size_t)Kt * Kt * s.N * 8, 256);
-                p.per_fit_gbx = align_up((size_t)Kt * s.N * 8, 256);
+                p.stats_gbx = (size_t)Kt * Kt * s.N;
+                p.stats_scal = p.stats_gbx + (size_t)Kt * s.N;
+                p.per_fit_stats = align_up((p.stats_scal + 8) * 8, 256);
                 p.per_fit_red = align_up((size_t)p.part_stride * 8, 256);
                 p.gram_ok = 1;
             }
@@ -262,9 +270,9 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     p.off_part = align_up(p.off_tickets + p.per_fit_tickets * s.n_fits, 256);
     p.off_gpart = align_up(p.off_part + p.per_fit_part * s.n_fits, 256);
     p.off_rowgram = align_up(p.off_gpart + p.per_fit_gpart * s.n_fits, 256);
-    p.off_gram = p.off_rowgram + p.per_fit_rowgram * s.n_fits;
-    p.off_gbx = p.off_gram + p.per_fit_gram * s.n_fits;
-    p.off_red = p.off_gbx + p.per_fit_gbx * s.n_fits;
+    p.off_stats = p.off_rowgram + p.per_fit_rowgram * s.n_fits;       // this GPU's statistics, fits contiguous
+    p.off_gstats = p.off_stats + p.per_fit_stats * s.n_fits;          // all-reduced copies (row-sharded runs)
+    p.off_red = p.off_gstats + p.per_fit_stats * s.n_fits;
     p.ws_bytes = align_up(p.off_red + p.per_fit_red * s.n_fits, 256);
     return DMF_OK;
 }
@@ -342,7 +350,7 @@ int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_
     a.g.rg = kConsumers / ntc;
     a.fits = b->fits_dev;
     a.k_inner = k_inner;
-    a.flags = flags;
+    a.flags = flags | (b->sharded ? kFlagPartial : 0);
     a.tol = tol;
     a.ca0 = ca0; a.cb0 = cb0; a.with_x = with_x; a.pad = 0;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
@@ -448,6 +456,8 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     const dmf_shape_t& s = *shape;
     std::vector<FitDev> host(s.n_fits);
     char* base = static_cast<char*>(ws);
+    if (p.gram_ok && cudaMemsetAsync(base + p.off_stats, 0, 2 * p.per_fit_stats * s.n_fits, (cudaStream_t)stream) != cudaSuccess)
+        return fail(DMF_E_CUDA, "batch set-up: clearing the statistics buffers failed");
     bool gather = false;
     for (int i = 0; i < s.n_fits; ++i) {
         const dmf_fit_desc_t& d = fits[i];
@@ -472,8 +482,10 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         f.tickets = reinterpret_cast<unsigned*>(base + p.off_tickets + p.per_fit_tickets * i);
         f.st = reinterpret_cast<FitState*>(base + p.off_states) + i;
         f.rowgram = p.gram_ok ? reinterpret_cast<double*>(base + p.off_rowgram + p.per_fit_rowgram * i) : nullptr;
-        f.gram = p.gram_ok ? reinterpret_cast<double*>(base + p.off_gram + p.per_fit_gram * i) : nullptr;
-        f.gbx = p.gram_ok ? reinterpret_cast<double*>(base + p.off_gbx + p.per_fit_gbx * i) : nullptr;
+        f.gram = p.gram_ok ? reinterpret_cast<double*>(base + p.off_stats + p.per_fit_stats * i) : nullptr;
+        f.gbx = p.gram_ok ? f.gram + p.stats_gbx : nullptr;
+        f.scal = p.gram_ok ? f.gram + p.stats_scal : nullptr;
+        f.rgram = f.gram; f.rgbx = f.gbx; f.rscal = f.scal;
         f.red = p.gram_ok ? reinterpret_cast<double*>(base + p.off_red + p.per_fit_red * i) : nullptr;
         f.pad = 0;
     }
@@ -485,6 +497,11 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->mom_dev = nullptr;
     b->mom_cap = 0;
     b->t_hi = 0;
+    b->sharded = 0;
+    b->fits_host = host;
+    b->stats_local = p.gram_ok ? reinterpret_cast<double*>(base + p.off_stats) : nullptr;
+    b->stats_global = p.gram_ok ? reinterpret_cast<double*>(base + p.off_gstats) : nullptr;
+    b->stats_doubles = p.per_fit_stats / 8; b->stats_gbx = p.stats_gbx; b->stats_scal = p.stats_scal;
     Geom& g = b->g;
     g.M = s.M; g.N = s.N; g.K = s.K; g.nu = s.n_u; g.Kt = s.K + s.n_u;
     g.ldx = s.ldx; g.ldd = s.ldd; g.ldr = s.K ? s.ldr : 0; g.ldu = s.ldu;
@@ -643,6 +660,45 @@ int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
     if (rc) return rc;
     return launch_g(b, k_ainner(b), b->ntc_p, 0, b->shape.mode == DMF_MODE_PURITY ? kFlagFW : 0, n_iter2, 0.0, 0, 0, 0, 1, (cudaStream_t)stream);
 }
+int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "row sharding needs the Gram-form engine (n_u <= 4)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per = b->stats_doubles;
+    for (int i = 0; i < b->shape.n_fits; ++i) {
+        FitDev& f = b->fits_host[i];
+        double* src = on ? b->stats_global + per * i : b->stats_local + per * i;
+        f.rgram = src; f.rgbx = src + b->stats_gbx; f.rscal = src + b->stats_scal;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->fits_dev, b->fits_host.data(), sizeof(FitDev) * b->shape.n_fits, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->sharded = on ? 1 : 0;
+    b->engine = DMF_ENGINE_GRAM;
+    return DMF_OK;
+}
+int dmf_batch_stats_buffers(dmf_batch_t b, void** local_dev, void** global_dev, int64_t* doubles_per_fit, int64_t* scal_offset) {
+    if (!b || !local_dev || !global_dev || !doubles_per_fit || !scal_offset) return fail(DMF_E_ARG, "NULL argument");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    *local_dev = b->stats_local; *global_dev = b->stats_global;
+    *doubles_per_fit = (int64_t)b->stats_doubles; *scal_offset = (int64_t)b->stats_scal;
+    return DMF_OK;
+}
+int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->sharded) return fail(DMF_E_STATE, "dmf_gram_finalize_cost is the second half of dmf_gram_rowgram on row-sharded batches");
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = b->gg;
+    a.fits = b->fits_dev;
+    a.k_inner = b->shape.n_fits;
+    a.flags = (initial ? kFlagInitial : 0) | (b->shape.dtype == DMF_F32 ? kFlagF32 : 0);
+    a.tol = tol;
+    finalize_cost_kernel<<<(b->shape.n_fits + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    return DMF_OK;
+}
+
 int dmf_gram_init(dmf_batch_t b, void* stream) {
     int rc = dmf_gram_rowgram(b, 1, 0.0, stream);
     if (rc) return rc;

@@ -43,8 +43,12 @@ struct FitDev {
     unsigned* tickets;   // [n_groups + 1]
     FitState* st;
     double* rowgram;     // Gram engine: [M][warps per row][NG] per-row statistics of the U step
-    double* gram;        // Gram engine: [Kt][Kt][N] per-sample G_j = R^T diag(d_.j) R
+    double* gram;        // Gram engine: [Kt][Kt][N] per-sample G_j = R^T diag(d_.j) R      (written by gram_panel_kernel: this GPU's rows)
     double* gbx;         // Gram engine: [Kt][N]     per-sample R^T (d_.j o x_.j)
+    double* scal;        // Gram engine: [8] row-sharded runs: this GPU's [cost, ||R_trunc||^2, ||u||^2 (set-up), max d, ||u||^2 (U step)]
+    double* rgram;       // what alpha_inner_kernel / finalize_cost_kernel READ: == gram / gbx / scal on one GPU, the all-reduced
+    double* rgbx;        //   copies when the CpG rows are sharded over several GPUs
+    double* rscal;
     double* red;         // Gram engine: [part_stride] totals of the last cross-CTA reduction
     int trace_cap;
     int pad;
@@ -86,6 +90,9 @@ struct PassArgs {
 };
 constexpr int kFlagInitial = 1;   // init_cost_kernel: set-up pass (norms, max d, no termination test)
 constexpr int kFlagFW = 2;        // alpha_pass_kernel: Frank-Wolfe step instead of projected gradient
+constexpr int kFlagPartial = 4;   // Gram engine, CpG rows sharded over GPUs: publish this GPU's sums to FitDev::scal, leave the state to
+                                  // finalize_cost_kernel / alpha_inner_kernel, which run on the all-reduced sums
+constexpr int kFlagF32 = 8;       // finalize_cost_kernel: alpha is stored as float
 
 struct TileSrc {
     const char* base;      // global base of the matrix (fit-specific), nullptr = absent

@@ -29,13 +29,16 @@ __host__ __device__ constexpr int tri_index(int q, int q2, int nub) { return q *
 
 // ------------------------------------------------------------------------------------------------
 // shared by cost_kernel-style epilogues: CTA partial [cost, ssq_rk, ssq_u, dmax] -> fit state
+__device__ __forceinline__ double scan_dmax(const Geom& g, const FitDev& f) {
+    double dm = 0.0;
+    for (int p = 0; p < g.n_parts; ++p) dm = fmax(dm, __ldcg(&f.part[(size_t)p * g.part_stride + 3]));
+    return dm;
+}
 template <bool INITIAL>
 __device__ __forceinline__ void cost_state_update(const Geom& g, const FitDev& f, FitState* st, const double* rec, const void* Acur_v,
-                                                  bool f32, double tol) {
+                                                  bool f32, double tol, double dm) {
     const double cf = rec[0];
     if (INITIAL) {
-        double dm = 0.0;
-        for (int p = 0; p < g.n_parts; ++p) dm = fmax(dm, __ldcg(&f.part[(size_t)p * g.part_stride + 3]));
         st->dmax = dm;
         st->dmax2 = dm * dm;
         st->ssq_rk = rec[1];
@@ -245,7 +248,14 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
         }
     }
     if (!hier_reduce(g, f, rec, 3, &c.ctl->flag)) return;
-    if (threadIdx.x == 0) cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol);
+    if (threadIdx.x == 0) {
+        const double dm = INITIAL ? scan_dmax(g, f) : 0.0;
+        if (a.flags & kFlagPartial) {
+            f.scal[0] = rec[0]; f.scal[1] = rec[1]; f.scal[2] = rec[2]; f.scal[3] = dm;
+        } else {
+            cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol, dm);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -522,7 +532,14 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
         }
     }
     if (!hier_reduce(g, f, rec, 3, &c.ctl->flag)) return;
-    if (threadIdx.x == 0) cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol);
+    if (threadIdx.x == 0) {
+        const double dm = INITIAL ? scan_dmax(g, f) : 0.0;
+        if (a.flags & kFlagPartial) {
+            f.scal[0] = rec[0]; f.scal[1] = rec[1]; f.scal[2] = rec[2]; f.scal[3] = dm;
+        } else {
+            cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol, dm);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -605,9 +622,13 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
         st->a1 = a.mom_a[t0 + n2];
         st->t_u = t0 + n2;
         if (n2 > 0) st->l_w_old = l_w;                       // deconvolution.py:89
-        st->ssq_u = rec[0];
-        const double nr = sqrt(st->ssq_rk + rec[0]);
-        st->l_h = (nr * nr) * st->dmax2;                     // deconvolution.py:212
+        if (a.flags & kFlagPartial) {
+            f.scal[4] = rec[0];                              // this GPU's rows; alpha_inner_kernel forms l_h from the all-reduced sum
+        } else {
+            st->ssq_u = rec[0];
+            const double nr = sqrt(st->ssq_rk + rec[0]);
+            st->l_h = (nr * nr) * st->dmax2;                 // deconvolution.py:212
+        }
     }
 }
 
@@ -806,7 +827,13 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
     const bool fw = (a.flags & kFlagFW) != 0;
     const int n2 = a.k_inner, Kt = g.Kt;
     const int acur = st->a_cur;
-    const double l_h = st->l_h, lho_in = st->l_h_old;
+    double l_h = st->l_h;
+    const bool sharded = (a.flags & kFlagPartial) != 0;
+    if (sharded) {                                           // ||u||^2 summed over all GPUs -> l_h, deconvolution.py:212
+        const double nr = sqrt(st->ssq_rk + f.rscal[4]);
+        l_h = (nr * nr) * st->dmax2;
+    }
+    const double lho_in = st->l_h_old;
     const int t0 = st->t_a;
     const double* mm = a.mom_m + t0;
     const double cap0 = 0.9999 * sqrt(lho_in / l_h), cap1 = 0.9999 * sqrt(l_h / l_h);
@@ -820,11 +847,11 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
         double G[KTB][KTB], b[KTB], ac[KTB], ap[KTB];
 #pragma unroll(KTB <= 8 ? KTB : 1)
         for (int k = 0; k < KTB; ++k) {
-            b[k] = k < Kt ? f.gbx[(size_t)k * g.N + j] : 0.0;
+            b[k] = k < Kt ? f.rgbx[(size_t)k * g.N + j] : 0.0;
             ac[k] = k < Kt ? (double)Acur[(size_t)k * g.N + j] : 0.0;
             ap[k] = k < Kt ? (double)Aprev[(size_t)k * g.N + j] : 0.0;
 #pragma unroll(KTB <= 8 ? KTB : 1)
-            for (int l = 0; l < KTB; ++l) G[k][l] = (k < Kt && l < Kt) ? f.gram[((size_t)k * Kt + l) * g.N + j] : 0.0;
+            for (int l = 0; l < KTB; ++l) G[k][l] = (k < Kt && l < Kt) ? f.rgram[((size_t)k * Kt + l) * g.N + j] : 0.0;
         }
         if (!fw) {
             bool bad = false;
@@ -887,6 +914,10 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_bad) st->done = 3;
+        if (sharded) {
+            st->ssq_u = f.rscal[4];
+            st->l_h = l_h;
+        }
         double sa = 0.0;
         const int nt = min((int)blockDim.x, g.N);
         for (int t = 0; t < nt; ++t) sa += colred[t];
@@ -898,6 +929,21 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
             if (n2 > 0) st->l_h_old = l_h;               // deconvolution.py:101
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CpG rows sharded over GPUs: the set-up / termination logic of the rowgram pass on the all-reduced sums
+// FitDev::rscal = [cost, ||R_trunc||^2, ||u||^2, max d_x] (deconvolution.py:192-204, :218-221).  One thread per fit.
+static __global__ void finalize_cost_kernel(const PassArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.k_inner) return;
+    const FitDev f = a.fits[i];
+    FitState* st = f.st;
+    if (st->done) return;
+    const bool f32 = (a.flags & kFlagF32) != 0;
+    const char* Acur = f.A + (size_t)st->a_cur * a.g.Kt * a.g.N * (f32 ? 4 : 8);
+    if (a.flags & kFlagInitial) cost_state_update<true>(a.g, f, st, f.rscal, Acur, f32, a.tol, f.rscal[3]);
+    else cost_state_update<false>(a.g, f, st, f.rscal, Acur, f32, a.tol, 0.0);
 }
 
 }  // namespace dmf

@@ -1,0 +1,163 @@
+"""CpG-row sharding of ONE fit over the GPUs of a box (BASELINE config 5).
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank r holds a contiguous row range of X, d_x, R_trunc
+and u plus a replica of alpha and of the fit state.  Per outer iteration (deconvolution.py:206-221 / :320-335):
+
+  U step      row-local, no communication          (dmf_gram_u_inner on the rows' statistics)
+  alpha step  ONE sum all-reduce of the per-sample statistics [G_j | bx_j | ||u||^2]  (Kt (Kt + 1) N + 8 doubles per fit),
+              then every rank runs the identical n_iter2 inner iterations on the reduced copy (dmf_gram_alpha_inner)
+  cost        ONE sum all-reduce of 8 doubles per fit, then the identical termination test on every rank
+
+plus one max all-reduce (max d_x) at set-up.  Every rank therefore holds the same alpha and makes the same termination
+decision; u stays distributed.  `RowShardedFit` is the orchestration; the arithmetic sits behind a small backend
+interface whose product implementation (`GpuShardBackend`) drives libdemethify_sm100 through `FitBatch`.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import DeviceProblem, FitBatch, _stream_ptr
+
+__all__ = ["row_range", "GpuShardBackend", "RowShardedFit", "mdwbssmf_deconv_sharded"]
+
+
+def row_range(M, rank, world):
+    """Rows [lo, hi) of rank `rank`: row m belongs to rank floor(m * world / M)."""
+    lo = (M * rank + world - 1) // world
+    hi = (M * (rank + 1) + world - 1) // world
+    return lo, hi
+
+
+class GpuShardBackend:
+    """This rank's rows on its GPU: a one-fit (or few-fit) FitBatch in sharded Gram-engine mode."""
+
+    def __init__(self, X_local, D_local, Rk_local, n_u, U0_local, A0, mode=_lib.DMF_MODE_PARTIAL, purity=None, precision=None):
+        self.prob = X_local if isinstance(X_local, DeviceProblem) else DeviceProblem(X_local, D_local, Rk_local, precision=precision)
+        self.batch = FitBatch(self.prob, n_u, [U0_local], [A0], mode=mode, purity=purity, engine="gram")
+        lib, b = _lib.lib(), self.batch
+        _lib.check(lib.dmf_batch_set_sharded(b.b, 1, _stream_ptr()))
+        loc, glo, per, so = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(lib.dmf_batch_stats_buffers(b.b, C.byref(loc), C.byref(glo), C.byref(per), C.byref(so)))
+        base = b.ws.data_ptr()
+        nbytes = per.value * 8 * b.n_fits
+
+        def view(ptr):
+            off = ptr - base
+            return b.ws[off:off + nbytes].view(torch.float64).view(b.n_fits, per.value)
+        self.local, self.glob = view(loc.value), view(glo.value)
+        self.scal_off = so.value
+        self.has_known = b.K > 0
+        self.device = b.device
+
+    # ---- statistics blocks: (n_fits, doubles_per_fit) tensors [G | bx | scal(8)]
+    def stats_local(self):
+        return self.local
+
+    def stats_global(self):
+        return self.glob
+
+    # ---- this rank's arithmetic
+    def rowgram(self, initial, tol):
+        self.batch.gram_rowgram(initial, tol)
+
+    def u_inner(self, n_iter2):
+        self.batch.gram_u_inner(n_iter2)
+
+    def panels(self, known_block):
+        self.batch.gram_panels(known_block)
+
+    def alpha_inner(self, n_iter2):
+        self.batch.gram_alpha_inner(n_iter2)
+
+    def finalize_cost(self, initial, tol):
+        _lib.check(_lib.lib().dmf_gram_finalize_cost(self.batch.b, int(bool(initial)), float(tol), _stream_ptr()))
+
+    def all_done(self):
+        sts = self.batch.states()
+        bad = [i for i, s in enumerate(sts) if s.done == 3]
+        if bad:
+            raise _lib.DmfError(f"non-finite values reached the simplex projection (fit {bad[0]})")
+        return all(s.done != 0 for s in sts)
+
+    def results(self):
+        """[(u_local, alpha, n_outer, cost)] — u holds only this rank's rows."""
+        return self.batch.results()
+
+    def close(self):
+        self.batch.close()
+
+
+class RowShardedFit:
+    """Outer loop of one row-sharded fit; `backend` does this rank's arithmetic, `group` is the torch.distributed group."""
+
+    def __init__(self, backend, group=None):
+        self.be, self.group = backend, group
+        self.so = backend.scal_off
+        self.collectives = 0
+
+    def _allreduce(self, t, op=dist.ReduceOp.SUM):
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=op, group=self.group)
+        self.collectives += 1
+
+    def _reduce_scal(self, with_max):
+        loc, glo, so = self.be.stats_local(), self.be.stats_global(), self.so
+        sc = loc[:, so:so + 8].contiguous()
+        if with_max:
+            mx = sc[:, 3].clone()
+            self._allreduce(mx, dist.ReduceOp.MAX)
+        self._allreduce(sc)
+        if with_max:
+            sc[:, 3] = mx
+        glo[:, so:so + 8] = sc
+
+    def init(self):
+        """deconvolution.py:192-204: cost, ||R||^2, max d_x over ALL rows; then this rank's known x known statistics."""
+        be = self.be
+        be.rowgram(True, 0.0)
+        self._reduce_scal(with_max=True)
+        be.finalize_cost(True, 0.0)
+        if be.has_known:
+            be.panels(True)
+
+    def outer(self, n_iter2, tol):
+        be = self.be
+        if n_iter2 > 0:
+            be.u_inner(n_iter2)                       # row-local
+            be.panels(False)
+            glo = be.stats_global()
+            glo.copy_(be.stats_local())
+            self._allreduce(glo)                      # G_j, bx_j, ||u||^2 over all rows
+            be.alpha_inner(n_iter2)                   # identical on every rank
+        be.rowgram(False, tol)
+        self._reduce_scal(with_max=False)
+        be.finalize_cost(False, tol)                  # identical termination decision on every rank
+
+    def fit(self, n_iter1, n_iter2, tol):
+        self.init()
+        issued, chunk = 0, 2
+        while issued < n_iter1:
+            todo = min(chunk, n_iter1 - issued)
+            for _ in range(todo):
+                self.outer(n_iter2, tol)
+            issued += todo
+            if self.be.all_done():                    # the state is replicated: every rank leaves the loop together
+                break
+            chunk = min(chunk * 2, 16)
+        return self.be.results()
+
+
+def mdwbssmf_deconv_sharded(u_local, alpha, X_local, d_local, R_local, n_u, n_iter1=100000, n_iter2=50, tol=1e-3, purity=None,
+                            group=None):
+    """mdwbssmf_deconv / mdwbssmf_deconv_p (deconvolution.py:190-223, :305-337) on a row-sharded problem: every rank passes
+    ITS rows of u, X, d_x, R_trunc (see `row_range`) and the full alpha; returns (u_local, alpha, n_outer, cost)."""
+    mode = _lib.DMF_MODE_PURITY if purity is not None else (_lib.DMF_MODE_PARTIAL if R_local is not None else _lib.DMF_MODE_UNSUPERVISED)
+    be = GpuShardBackend(X_local, d_local, R_local, n_u, np.asarray(u_local).reshape(-1, n_u), np.asarray(alpha), mode=mode, purity=purity)
+    try:
+        (u, a, n_outer, cost), = RowShardedFit(be, group).fit(n_iter1, n_iter2, tol)
+    finally:
+        be.close()
+    return u, a, n_outer, cost

@@ -142,6 +142,15 @@ int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream);
 /* n_iter2 update_alpha iterations incl. simplex projection (deconvolution.py:94-101, :21-37), or Frank-Wolfe iterations
  * (deconvolution.py:285-299) for purity batches, per sample on (G_j, bx_j) */
 int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream);
+/* CpG rows sharded over several GPUs (one process per GPU, each batch holds its own row range of X, d_x, R_trunc, u and a
+ * replica of alpha).  With sharding on, dmf_gram_rowgram / dmf_gram_u_inner / dmf_gram_panels publish THIS GPU's sums in the
+ * `local` statistics block of every fit, [G (Kt*Kt*N) | bx (Kt*N) | scal (8): cost, ||R_trunc||^2, ||u||^2 at set-up, max d_x,
+ * ||u||^2 after the U step], and leave the fit state alone.  The caller copies local -> global, all-reduces `global` over the
+ * GPUs (sum; max for scal[3]) and then runs dmf_gram_finalize_cost (after rowgram) / dmf_gram_alpha_inner (after panels), which
+ * read `global`.  Every rank ends up with the identical state and alpha.  Fits are doubles_per_fit apart in both blocks. */
+int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream);
+int dmf_batch_stats_buffers(dmf_batch_t b, void** local_dev, void** global_dev, int64_t* doubles_per_fit, int64_t* scal_offset);
+int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* stream);
 /* set-up (rowgram initial + known panels) and one whole outer iteration (u_inner, panels, alpha_inner, rowgram) */
 int dmf_gram_init(dmf_batch_t b, void* stream);
 int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);

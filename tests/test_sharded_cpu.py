@@ -1,0 +1,128 @@
+"""CPU tests of the multi-GPU host logic (no GPU needed):
+  * the Gram-form restatement (oracle/gram_numpy.py, same arithmetic as csrc/dmf_gram.cuh) against the reference-shaped
+    oracle, so the re-association is pinned on CPU too;
+  * `RowShardedFit` — the product's CpG-row-sharding orchestration — with world_size 2 over gloo: both ranks end with the
+    same alpha, the same outer-iteration count and the rows of u they own, equal to the unsharded run;
+  * fit sharding helpers (seed lists, row ranges)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import bssmf_numpy as orc
+from oracle.gram_numpy import NumpyShardBackend, momentum_table
+from demethify_b200.sharded import RowShardedFit, row_range
+
+
+def synth(seed, M, N, K, n_true, depth=50):
+    rs = np.random.RandomState(seed)
+    a = rs.uniform(0.2, 1.0, size=K + n_true)
+    Rf = rs.beta(a, a, size=(M, K + n_true))
+    unk = rs.uniform(0, 0.9, size=N)
+    Ak = rs.dirichlet(np.ones(max(K, 1)), N).T[:K] * (1 - unk)
+    Au = rs.dirichlet(np.ones(n_true), N).T * unk
+    D = rs.poisson(depth, size=(M, N)) + 1
+    cnt = rs.binomial(D, np.clip(Rf @ np.vstack([Ak, Au]), 0, 1))
+    return cnt / D, D.astype(np.float64), np.ascontiguousarray(Rf[:, :K])
+
+
+def test_row_ranges_partition_the_rows():
+    for M in (1, 7, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            edges = [row_range(M, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == M
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges) <= 1
+
+
+def test_momentum_table_matches_recurrence():
+    a, m = momentum_table(50)
+    a1 = 1.0
+    for t in range(50):
+        a0, (a1, beta) = a1, orc._extrapolation(a1, 1.0, 1.0)
+        assert a[t] == a0 and a[t + 1] == a1 and min(m[t], 0.9999) == beta
+
+
+@pytest.mark.parametrize("n_u,it1,it2,tol", [(1, 60, 20, 1e-2), (2, 6, 10, 1e-9)])
+def test_gram_form_equals_reference_shape(n_u, it1, it2, tol):
+    X, D, Rk = synth(3, 700, 9, 4, max(n_u, 1))
+    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, n_u, seed=1)
+    tr = {}
+    uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D, Rk, n_u, it1, it2, tol, trace=tr)
+    be = NumpyShardBackend(X, D, Rk, n_u, u0, a0)
+    (u, a, n_outer, cost), = RowShardedFit(be).fit(it1, it2, tol)
+    assert n_outer == tr["n_outer"]
+    assert abs(cost - tr["costs"][-1]) <= 1e-10 * cost
+    assert np.abs(a - ao).max() <= 1e-10 and np.abs(u - uo).max() <= 1e-10
+
+
+def test_gram_form_purity_and_unsupervised():
+    X, D, Rk = synth(5, 500, 8, 4, 1)
+    pur = np.random.RandomState(0).uniform(0.2, 0.9, size=8)
+    u0, R0, a0 = orc.draw_init_purity("uniform_", X, D, Rk, 1, pur, seed=2)
+    tr = {}
+    uo, ao = orc.solve_purity(u0.copy(), R0, a0.copy(), X, D, Rk, 1, pur, 5, 30, 1e-9, trace=tr)
+    (u, a, n_outer, _), = RowShardedFit(NumpyShardBackend(X, D, Rk, 1, u0, a0, mode="purity", purity=pur)).fit(5, 30, 1e-9)
+    assert n_outer == tr["n_outer"] and np.abs(a - ao).max() <= 1e-10 and np.abs(u - uo).max() <= 1e-10
+    # unsupervised: the U gradient is taken at u, not at the extrapolated point (deconvolution.py:163)
+    tr = {}
+    uo, ao = orc.solve_unsupervised(X, 2, D, "uniform_", 4, 10, 1e-9, seed=3, trace=tr)
+    rs = orc.legacy_stream(3)
+    u0 = rs.uniform(size=(X.shape[0], 2)); a0 = rs.dirichlet(np.ones(2), X.shape[1]).T
+    (u, a, n_outer, _), = RowShardedFit(NumpyShardBackend(X, D, None, 2, u0, a0, mode="unsupervised")).fit(4, 10, 1e-9)
+    assert n_outer == tr["n_outer"] and np.abs(a - ao).max() <= 1e-10 and np.abs(u - uo).max() <= 1e-10
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, case, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, D, Rk, n_u, u0, a0, mode, pur, it1, it2, tol = case
+        lo, hi = row_range(X.shape[0], rank, world)
+        be = NumpyShardBackend(X[lo:hi], D[lo:hi], None if Rk is None else Rk[lo:hi], n_u, u0[lo:hi], a0, mode=mode, purity=pur)
+        fit = RowShardedFit(be)
+        (u, a, n_outer, cost), = fit.fit(it1, it2, tol)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), u=u, a=a, n_outer=n_outer, cost=cost, lo=lo, hi=hi, coll=fit.collectives)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["partial", "purity"])
+def test_row_sharded_fit_world2_gloo(tmp_path, mode):
+    X, D, Rk = synth(11, 901, 6, 3, 2)
+    n_u = 2
+    pur = np.random.RandomState(1).uniform(0.2, 0.9, size=6) if mode == "purity" else None
+    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, n_u, seed=4)
+    it1, it2, tol = (40, 10, 1e-1) if mode == "partial" else (4, 25, 1e-9)
+    (u1, a1, n1, c1), = RowShardedFit(NumpyShardBackend(X, D, Rk, n_u, u0, a0, mode=mode, purity=pur)).fit(it1, it2, tol)
+    case = (X, D, Rk, n_u, u0, a0, mode, pur, it1, it2, tol)
+    mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(tmp_path / f"rank{k}.npz") for k in range(2)]
+    assert int(r[0]["n_outer"]) == int(r[1]["n_outer"]) == n1                      # identical termination decision on every rank
+    assert np.array_equal(r[0]["a"], r[1]["a"])                                    # alpha is replicated bit for bit
+    assert np.abs(r[0]["a"] - a1).max() <= 1e-10 and abs(float(r[0]["cost"]) - c1) <= 1e-10 * c1
+    u = np.vstack([r[0]["u"], r[1]["u"]])
+    assert (int(r[0]["lo"]), int(r[1]["hi"])) == (0, X.shape[0]) and np.abs(u - u1).max() <= 1e-10
+    # communication volume: set-up = 2 collectives (sum, max), every outer iteration = 2 sum all-reduces
+    assert int(r[0]["coll"]) == 2 + 2 * n1 + (0 if n1 < it1 else 0) or int(r[0]["coll"]) >= 2 + 2 * n1
+
+
+def test_bootstrap_fit_sharding_seed_lists():
+    """Fit sharding (bootstrap.py:26-27): rank r takes resamples r, r + world, ...; the union is the reference's seed list."""
+    seeds = orc.bootstrap_seed_list(1, 10)
+    assert seeds[:5] == [1, 2, 4, 7, 11]
+    world = 4
+    parts = [seeds[r::world] for r in range(world)]
+    assert sorted(s for p in parts for s in p) == sorted(seeds)
