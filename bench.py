@@ -293,6 +293,37 @@ def run_b200(args, rank, world, local_rank):
         sb.close()
         del sb
 
+    # ---- CpG-row sharding of ONE 1M-row fit over the ranks (strong scaling; NCCL all-reduce of the per-sample statistics
+    # and of the cost every outer iteration): rank r contributes M / world of its own rows, alpha is replicated
+    row_sharded = None
+    if world > 1 and engine == "gram" and not args.profile:
+        from demethify_b200.sharded import GpuShardBackend, RowShardedFit
+        m_loc = M // world
+        sprob = prob.row_slice(0, m_loc)
+        be = GpuShardBackend(sprob, None, None, N_UNK, hU[:m_loc], hA)
+        rs_fit = RowShardedFit(be)
+        rs_fit.init()
+        for _ in range(OUTER_PER_STEP):
+            rs_fit.outer(N_ITER2, 0.0)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.steps * OUTER_PER_STEP):
+            rs_fit.outer(N_ITER2, 0.0)
+        r1.record()
+        barrier()
+        rs_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(rs_ms, op=dist.ReduceOp.MAX)
+        st_rs = be.batch.states()[0]
+        assert st_rs.n_outer == (args.steps + 1) * OUTER_PER_STEP and np.isfinite(st_rs.cost)
+        row_sharded = {"value": 2 * N_ITER2 * OUTER_PER_STEP * args.steps / (float(rs_ms[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
+                       "rows_per_gpu": m_loc, "ms_per_outer_iteration": float(rs_ms[0]) / (args.steps * OUTER_PER_STEP),
+                       "collectives_per_outer_iteration": 2,
+                       "allreduce_doubles_per_outer_iteration": int(Kt * (Kt + 1) * N_S + 16),
+                       "note": "one fit, rows sharded over the ranks; value is the single job's update iterations/s"}
+        be.close()
+        del be, sprob
+
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "engine": engine, "ms": kern}))
@@ -358,6 +389,8 @@ def run_b200(args, rank, world, local_rank):
             "roofline": roof,
             "clocks": clocks,
         }
+        if row_sharded is not None:
+            line["row_sharded"] = row_sharded
         if not args.no_cpu and world == 1:
             leg = cpu_reference_leg(2, 1)
             line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}

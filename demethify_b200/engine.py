@@ -149,6 +149,15 @@ class DeviceProblem:
         other.M = n
         return other
 
+    def row_slice(self, lo, hi):
+        """Rows [lo, hi) as a problem of its own sharing the device buffers (CpG-row shards, sharded.py)."""
+        other = object.__new__(DeviceProblem)
+        other.__dict__.update(self.__dict__)
+        other.X, other.D = self.X[lo:hi], self.D[lo:hi]
+        other.Rk = self.Rk[lo:hi] if self.Rk is not None else None
+        other.M = hi - lo
+        return other
+
     def with_weights(self, D_tensor, wtype):
         """Shallow copy sharing X / R_trunc with different weights (BCV folds, ic.py:75)."""
         other = object.__new__(DeviceProblem)
