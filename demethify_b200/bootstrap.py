@@ -52,7 +52,10 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
     n_outer = []
     data_dependent_init = init_option in ("uniform", "SVD")
     # fits per wave: bounded by device memory (two u slots + partials per fit)
-    per_fit = 2 * M * (n_u + (n_u & 1)) * (8 if prob.precision == "fp64" else 4) + 64 * (prob.K + n_u) * N * 8 + 4096
+    ng = {1: 2, 2: 5}.get(n_u, 14)                            # Gram engine: per-row statistics, one record per warp of a row
+    ntc = 1 << max(0, ((N + 3) // 4 - 1).bit_length())
+    per_fit = (2 * M * (n_u + (n_u & 1)) * (8 if prob.precision == "fp64" else 4) + M * ng * ((ntc + 31) // 32) * 8 * (n_u <= 4)
+               + 64 * (prob.K + n_u) * N * 8 + 4096)
     wave = int(max(1, min(n_bootstrap, (device_free_bytes(prob.device) // 2) // max(per_fit, 1), 4096)))
     for w0 in range(0, n_bootstrap, wave):
         chunk = seeds[w0:w0 + wave]

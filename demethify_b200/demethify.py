@@ -1,6 +1,6 @@
 """`demethify` command line — drop-in for the reference's demethify/demethify.py:main (same flags, same output files:
 celltypes_proportions.csv, methylation_profile_estimate.csv, confidence_interval_*.csv, log.log), running the
-deconvolution on the B200 kernel library.  Additive flag: --precision {fp64,fp32}.  Plotting is imported lazily
+deconvolution on the B200 kernel library.  Additive flags: --precision {fp64,fp32}, --engine {auto,gram,stream}.  Plotting is imported lazily
 (matplotlib / seaborn / colorcet are optional)."""
 import argparse
 import os
@@ -11,7 +11,7 @@ from time import time
 import numpy as np
 import pandas as pd
 
-from . import set_precision
+from . import set_engine, set_precision
 from .bootstrap import bt_ci
 from .deconvolution import (cost_f_w, init_BSSMF_md, init_BSSMF_md_p, mdwbssmf_deconv, mdwbssmf_deconv_p, unsupervised_deconv)
 from .ic import evaluate_best_ic
@@ -48,6 +48,8 @@ def build_parser():
     p.add_argument("--noprint", action="store_true", help="Doesnt show the logo.")
     p.add_argument("--bedmethyl", action="store_true", help="Flag to indicate that the input will be bedmethyl files, modkit style")
     p.add_argument("--precision", choices=["fp64", "fp32"], default="fp64", help="(B200 path) arithmetic of the solver kernels")
+    p.add_argument("--engine", choices=["auto", "gram", "stream"], default="auto",
+                   help="(B200 path) device engine: per-iteration streaming passes, or Gram-form statistics (default where supported)")
     return p
 
 
@@ -78,6 +80,7 @@ def read_inputs(args):
 def main(argv=None):
     args = build_parser().parse_args(argv)
     set_precision(args.precision)
+    set_engine(args.engine)
     args.restart = 1 if args.restart is None else args.restart[0]
     if not args.iterations:
         args.iterations = [100, 500] if args.purity else [10000, 20]

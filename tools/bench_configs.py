@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Timings of the BASELINE.json configurations other than the bench.py headline (run on the GPU box).  Prints one JSON line
+per configuration: wall-clock of the public call, outer iterations executed, fits/s.  Synthetic data, recipe of bench.py.
+
+  python tools/bench_configs.py [c2] [c3] [c4] [--resamples B]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def synth(seed, M, N, K, n_true, depth=50):
+    rs = np.random.RandomState(seed)
+    a = rs.uniform(0.2, 1.0, size=K + n_true)
+    Rf = rs.beta(a, a, size=(M, K + n_true))
+    unk = rs.uniform(0, 0.9, size=N)
+    Ak = rs.dirichlet(np.ones(K), N).T * (1 - unk)
+    Au = rs.dirichlet(np.ones(n_true), N).T * unk
+    D = rs.poisson(depth, size=(M, N)) + 1
+    X = rs.binomial(D, np.clip(Rf @ np.vstack([Ak, Au]), 0, 1)) / D
+    return X, D.astype(np.int64), np.ascontiguousarray(Rf[:, :K]), unk
+
+
+def main():
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    from demethify_b200 import deconvolution as dec
+    from demethify_b200.bootstrap import bootstrap_fits
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2", "c3", "c4"]
+    B = int(sys.argv[sys.argv.index("--resamples") + 1]) if "--resamples" in sys.argv else 64
+    out = []
+    if "c2" in which:      # partial reference, 6 + 2 types x 100k CpGs x 16 samples, CLI defaults (10000 x 20, tol 1e-2)
+        X, D, Rk, _ = synth(0, 100_000, 16, 6, 2)
+        u0, R0, a0 = dec.init_BSSMF_md("uniform_", X, D, Rk, 2, seed=1)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, 2, n_iter1=10000, n_iter2=20, tol=1e-2)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+        info = dec.last_fit_info()
+        out.append({"config": "c2 partial-reference 100k x 16, n_u=2, 10000x20, tol 1e-2", "s_per_fit": t, "n_outer": info["n_outer"],
+                    "update_iters_per_s": 40 * info["n_outer"] / t, "engine": info["engine"], "launches": info["launches"]})
+    if "c3" in which:      # purity, n_u = 1, 100 x 500, 200k x 64
+        X, D, Rk, unk = synth(1, 200_000, 64, 6, 1)
+        pur = 1 - unk
+        u0, R0, a0 = dec.init_BSSMF_md_p("uniform_", X, D, Rk, 1, pur, seed=1)
+        for tol in (1e-2, 0.0):
+            for rep in range(2):
+                t0 = time.perf_counter()
+                dec.mdwbssmf_deconv_p(u0, R0, a0, X, D, Rk, 1, pur, n_iter1=100, n_iter2=500, tol=tol)
+                torch.cuda.synchronize()
+                t = time.perf_counter() - t0
+            info = dec.last_fit_info()
+            out.append({"config": f"c3 purity 200k x 64, n_u=1, 100x500, tol {tol}", "s_per_fit": t, "n_outer": info["n_outer"],
+                        "update_iters_per_s": 1000 * info["n_outer"] / t, "engine": info["engine"], "launches": info["launches"]})
+    if "c4" in which:      # bootstrap: B resamples of 500k x 64, n_u = 1, batched
+        X, D, Rk, _ = synth(2, 500_000, 64, 6, 1)
+        for n_iter1, tol in ((20, 0.0), (10000, 1e-2)):
+            t0 = time.perf_counter()
+            alphas, us, n_outer = bootstrap_fits(B, 1, X, D, Rk, "uniform_", n_iter1, 20, tol, None, 1, keep_u=True)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            out.append({"config": f"c4 bootstrap {B} resamples of 500k x 64, n_u=1, n_iter1={n_iter1}, tol {tol}", "s_total": t, "fits_per_s": B / t,
+                        "mean_outer": float(np.mean(n_outer)), "s_per_1000_resamples": 1000 * t / B})
+    for o in out:
+        print(json.dumps(o), flush=True)
+
+
+if __name__ == "__main__":
+    main()

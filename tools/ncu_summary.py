@@ -14,7 +14,12 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 tag, kernels = sys.argv[1], sys.argv[2:]
 cols = {}
 for k in kernels:
-    out = subprocess.run(['ncu', '-i', f'gpurun_out/{tag}_{k}.ncu-rep', '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    import os
+    raw = f'gpurun_out/{tag}_{k}_raw.csv'
+    if os.path.exists(raw):
+        out = open(raw).read()
+    else:
+        out = subprocess.run(['ncu', '-i', f'gpurun_out/{tag}_{k}.ncu-rep', '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     cols[k] = {h: (rows[1][i], rows[2][i]) for i, h in enumerate(rows[0])}
 print("| metric | " + " | ".join(kernels) + " |")
