@@ -13,7 +13,7 @@ DMF_F64, DMF_F32 = 0, 1
 DMF_W_FLOAT, DMF_W_U16 = 0, 1
 DMF_MODE_PARTIAL, DMF_MODE_PURITY, DMF_MODE_UNSUPERVISED = 0, 1, 2
 DMF_ENGINE_STREAM, DMF_ENGINE_GRAM = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Shape(C.Structure):
@@ -25,7 +25,7 @@ class Shape(C.Structure):
 class FitDesc(C.Structure):
     _fields_ = [("X", C.c_void_p), ("D", C.c_void_p), ("Rk", C.c_void_p), ("rows", C.c_void_p), ("U", C.c_void_p),
                 ("A", C.c_void_p), ("purity", C.c_void_p), ("cost_trace", C.c_void_p), ("trace_cap", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("mult", C.c_void_p), ("offs", C.c_void_p)]
 
 
 class FitState(C.Structure):

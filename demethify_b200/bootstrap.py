@@ -1,12 +1,17 @@
 """Mirror of the reference's demethify/bootstrap.py: bootstrap confidence intervals.
 
 The reference fits the resamples one after another (bootstrap.py:26-46); here all resamples of a wave are ONE
-batched launch set (FitBatch with a per-fit row index: the kernels gather rows of the shared X, d_x, R_trunc, while
-every fit owns its position-indexed u).  Seeds, resampling indices, init draws and the percentile arithmetic follow
-the reference exactly: seed_i = seed_{i-1} + i, sklearn.utils.resample == RandomState(seed).randint.
+batched launch set that shares X, d_x, R_trunc in HBM.  Where the library supports it the resamples run in
+MULTIPLICITY FORM: a resample is the source matrix with per-row multiplicities, its u rows (one per resampled position,
+the reference's per-position semantics) are ordered by source row and addressed through a CSR, so the
+streaming passes read the shared matrices contiguously and, with a fit-major grid, mostly out of L2.  Otherwise
+(K > 6, n_u > 4) every fit carries a row index and the kernels gather rows.  Seeds, resampling indices, init draws and
+the percentile arithmetic follow the reference exactly: seed_i = seed_{i-1} + i,
+sklearn.utils.resample == RandomState(seed).randint.
 """
 import numpy as np
 import pandas as pd
+import torch
 
 from . import _lib
 from .deconvolution import init_BSSMF_md, init_BSSMF_md_p
@@ -57,9 +62,12 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
     per_fit = (2 * M * (n_u + (n_u & 1)) * (8 if prob.precision == "fp64" else 4) + M * ng * ((ntc + 31) // 32) * 8 * (n_u <= 4)
                + 64 * (prob.K + n_u) * N * 8 + 4096)
     wave = int(max(1, min(n_bootstrap, (device_free_bytes(prob.device) // 2) // max(per_fit, 1), 4096)))
+    mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
+    use_mult = prob.K <= 6 and n_u <= 4 and prob.K + (prob.K & 1) + n_u + (n_u & 1) <= 8
+    dev = prob.device
     for w0 in range(0, n_bootstrap, wave):
         chunk = seeds[w0:w0 + wave]
-        rows, U0, A0, inv = [], [], [], []
+        rows, U0, A0, inv, mults, offs = [], [], [], [], [], []
         for s in chunk:
             idx = resample_indices(s, M)
             if data_dependent_init:
@@ -70,20 +78,32 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
                 u0, _, a0 = init_BSSMF_md_p(init_option, Xb, Db, Rb, n_u, purity, seed=s)
             else:
                 u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
-            # visit the resampled rows in source order (HBM locality); u is position-indexed, so permute it along
-            order = np.argsort(idx, kind="stable")
-            rows.append(idx[order])
-            U0.append(u0[order])
+            # order the resampled positions by source row (stable sort on the device); u is position-indexed, so permute it along
+            idx_d = torch.from_numpy(idx).to(dev)
+            order_d = torch.sort(idx_d, stable=True).indices
+            u0_d = torch.from_numpy(np.ascontiguousarray(u0)).to(dev)[order_d]
+            if use_mult:
+                cnt = torch.bincount(idx_d, minlength=M)
+                mults.append(cnt.to(torch.int32))
+                offs.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]).to(torch.int32))
+            else:
+                rows.append(idx_d[order_d].to(torch.int32))
+            U0.append(u0_d)
             A0.append(a0)
-            inv.append(order)
-        mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
-        batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows)
+            inv.append(order_d)
+        if use_mult:
+            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, mult=mults, offs=offs)
+        else:
+            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows)
         states = batch.fit(n_iter1, n_iter2, tol)
-        for k, (u, a, n_o, _cost) in enumerate(batch.results(states)):
-            alphas[w0 + k] = a
-            if keep_u:
-                us[w0 + k][inv[k]] = u           # back to the resampled-position order of the reference (Q6)
-            n_outer.append(n_o)
+        for k, st in enumerate(states):
+            u_d, a_d = batch.current(k, states)
+            alphas[w0 + k] = a_d.to(torch.float64).cpu().numpy()
+            if keep_u:                           # back to the resampled-position order of the reference (Q6)
+                back = torch.empty((M, n_u), dtype=torch.float64, device=dev)
+                back[inv[k]] = u_d.to(torch.float64)
+                us[w0 + k] = back.cpu().numpy()
+            n_outer.append(st.n_outer)
         batch.close()
     return alphas, us, n_outer
 

@@ -55,6 +55,7 @@ struct dmf_batch_s {
     int kb_g, nub_g, c_g, ntc_g, pb_g, c_p, ntc_p, ktb_in;
     int n_parts_u, n_groups_u;
     unsigned smem_rg, smem_panel;
+    int multmode;                   // fits are bootstrap resamples in multiplicity form
     int sharded;                    // CpG rows sharded over GPUs: kernels publish partial sums, finalize runs on all-reduced sums
     std::vector<FitDev> fits_host;
     double *stats_local, *stats_global;
@@ -97,7 +98,9 @@ struct Plan {
     int gram_ok, kb_g, nub_g, c_g, rpt_g_max, rpt_g, ntc_g, occ_g, pb_g, c_p, ntc_p, ktb_in;
     int tile_rows_g, n_tiles_g, n_parts_g, n_groups_g, wpr_g, ng_g;
     int n_parts_u, n_groups_u;     // u_inner_kernel: one thread per row, many more CTAs than the streaming passes
-    unsigned g_offX, g_offD, g_offR, g_offU, g_stage_bytes, smem_rg, smem_panel;
+    unsigned g_offX, g_offD, g_offR, g_offU, g_offUp, g_stage_bytes, smem_rg, smem_panel;
+    int mult_ok;                   // multiplicity form (bootstrap resamples) available for this shape
+    size_t off_usum, per_fit_usum;
     size_t off_rowgram, off_stats, off_gstats, off_red, per_fit_rowgram, per_fit_stats, per_fit_red;
     size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
 };
@@ -194,6 +197,8 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     // ---- Gram-form engine (dmf_gram.cuh): n_u <= 4, own tile geometry (no u_prev in the stage, rows per thread from kGramTable)
     p.gram_ok = 0;
     p.n_parts_g = p.n_groups_g = p.n_parts_u = p.n_groups_u = 0;
+    p.mult_ok = 0;
+    p.per_fit_usum = 0;
     p.per_fit_rowgram = p.per_fit_stats = p.per_fit_red = 0;
     p.stats_gbx = p.stats_scal = 0;
     if (s.n_u <= 4) {
@@ -215,7 +220,9 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
             const int occ_pn = (2 * (p.pb_g + 1) * p.c_p <= 40) ? 2 : 1;
             p.occ_g = std::min(occ_rg, occ_pn);
             auto a128g = [](size_t v) { return align_up(v, 128); };
-            auto stage_g = [&](long long tr) { return a128g(tr * px) + a128g(tr * pd) + a128g(tr * pr) + a128g(tr * pu); };
+            // the U region also holds the per-source-row sums of the multiplicity form (NG doubles per row), followed by the multiplicities
+            const size_t pu_stage = std::max(pu, (size_t)p.ng_g * 8);
+            auto stage_g = [&](long long tr) { return a128g(tr * px) + a128g(tr * pd) + a128g(tr * pr) + a128g(tr * pu_stage) + a128g(tr * 4); };
             const size_t epi_panel = kCtlBytes + (size_t)(p.pb_g + 1) * s.N * 8 + 256;
             p.rpt_g = 0;
             for (int attempt = 0; attempt < 2 && !p.rpt_g; ++attempt) {
@@ -237,7 +244,10 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 p.g_offD = (unsigned)a128g(p.g_offX + trg * px);
                 p.g_offR = (unsigned)a128g(p.g_offD + trg * pd);
                 p.g_offU = (unsigned)a128g(p.g_offR + trg * pr);
-                p.g_stage_bytes = (unsigned)a128g(p.g_offU + trg * pu);
+                p.g_offUp = (unsigned)a128g(p.g_offU + trg * pu_stage);
+                p.g_stage_bytes = (unsigned)a128g(p.g_offUp + trg * 4);
+                p.mult_ok = (p.c_g == 4 && p.pb_g == 8 && trg % 4 == 0 && s.mode != DMF_MODE_UNSUPERVISED) ? 1 : 0;
+                p.per_fit_usum = p.mult_ok ? align_up((size_t)s.M * p.ng_g * 8, 256) : 0;
                 long long per_fit_g = std::max<long long>(1, (long long)h->sm_count * p.occ_g / s.n_fits);
                 if (s.max_ctas_per_fit > 0) per_fit_g = std::min<long long>(per_fit_g, s.max_ctas_per_fit);
                 p.n_parts_g = (int)std::min<long long>(per_fit_g, p.n_tiles_g);
@@ -273,7 +283,8 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     p.off_stats = p.off_rowgram + p.per_fit_rowgram * s.n_fits;       // this GPU's statistics, fits contiguous
     p.off_gstats = p.off_stats + p.per_fit_stats * s.n_fits;          // all-reduced copies (row-sharded runs)
     p.off_red = p.off_gstats + p.per_fit_stats * s.n_fits;
-    p.ws_bytes = align_up(p.off_red + p.per_fit_red * s.n_fits, 256);
+    p.off_usum = p.off_red + p.per_fit_red * s.n_fits;
+    p.ws_bytes = align_up(p.off_usum + p.per_fit_usum * s.n_fits, 256);
     return DMF_OK;
 }
 
@@ -315,6 +326,7 @@ int set_smem(kern_t k, unsigned bytes) {
 
 int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_inner, double tol, cudaStream_t st) {
     if (!k) return fail(DMF_E_SHAPE, "no kernel instantiation for this shape");
+    if (b->multmode) return fail(DMF_E_STATE, "fits in multiplicity form run on the Gram-form engine only (dmf_gram_*)");
     PassArgs a;
     a.g = b->g;
     a.g.ntc = ntc;
@@ -336,8 +348,9 @@ kern_t k_cost(dmf_batch_s* b, int initial) { return by_types(b->shape, g_cost, b
 kern_t k_alpha(dmf_batch_s* b) { return by_types(b->shape, g_alpha, b->ktb, 0, b->c_alpha); }
 kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->kb, b->nub, b->c_u); }
 kern_t k_rowgram(dmf_batch_s* b, int initial) { return by_types(b->shape, g_rowgram, b->kb_g, b->nub_g, initial | (b->c_g == 4 ? 2 : 0)); }
-kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->c_p, 0); }
-kern_t k_uinner(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 0, 0); }
+kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->c_p, b->multmode); }
+kern_t k_uinner(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, b->multmode ? 1 : 0, 0); }
+kern_t k_costcross(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 2, 0); }
 kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in, 0, 0); }
 
 // Gram-engine launch: geometry gg; ntc selects the thread mapping of the kernel; grid_x CTAs per fit (0: one CTA per fit on grid.x)
@@ -360,6 +373,11 @@ int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_
         a.g.n_groups = b->n_groups_u;
         if (b->n_parts_u != b->gg.n_parts) a.g.part_stride = 8;
         grid = dim3(b->n_parts_u, b->shape.n_fits, 1);
+    }
+    if (grid_mode == 1) a.g.fit_major = 0;
+    else if (a.g.fit_major) {
+        if (grid.x > 65535u) a.g.fit_major = 0;          // grid.y limit
+        else grid = dim3(grid.y, grid.x, 1);
     }
     k<<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -459,8 +477,14 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     if (p.gram_ok && cudaMemsetAsync(base + p.off_stats, 0, 2 * p.per_fit_stats * s.n_fits, (cudaStream_t)stream) != cudaSuccess)
         return fail(DMF_E_CUDA, "batch set-up: clearing the statistics buffers failed");
     bool gather = false;
+    int n_mult = 0;
+    bool shared_inputs = s.n_fits > 1;
     for (int i = 0; i < s.n_fits; ++i) {
         const dmf_fit_desc_t& d = fits[i];
+        if ((d.mult != nullptr) != (d.offs != nullptr)) return fail(DMF_E_ARG, "fit descriptor: mult and offs go together");
+        if (d.mult && d.rows) return fail(DMF_E_ARG, "fit descriptor: a fit is either gathered (rows) or in multiplicity form (mult / offs)");
+        n_mult += d.mult ? 1 : 0;
+        shared_inputs &= (d.X == fits[0].X && d.D == fits[0].D && d.Rk == fits[0].Rk);
         if (!d.X || !d.D || !d.U || !d.A || (s.K && !d.Rk)) return fail(DMF_E_ARG, "fit descriptor has a NULL matrix");
         if (s.mode == DMF_MODE_PURITY && !d.purity) return fail(DMF_E_ARG, "purity mode needs a purity vector");
         const uintptr_t al = reinterpret_cast<uintptr_t>(d.X) | reinterpret_cast<uintptr_t>(d.D) | reinterpret_cast<uintptr_t>(d.Rk) |
@@ -487,11 +511,17 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         f.scal = p.gram_ok ? f.gram + p.stats_scal : nullptr;
         f.rgram = f.gram; f.rgbx = f.gbx; f.rscal = f.scal;
         f.red = p.gram_ok ? reinterpret_cast<double*>(base + p.off_red + p.per_fit_red * i) : nullptr;
+        f.mult = d.mult; f.offs = d.offs;
+        f.usum = p.mult_ok ? reinterpret_cast<double*>(base + p.off_usum + p.per_fit_usum * i) : nullptr;
         f.pad = 0;
     }
+    if (n_mult && n_mult != s.n_fits) return fail(DMF_E_ARG, "either all fits of a batch are in multiplicity form or none");
+    if (n_mult && !p.mult_ok)
+        return fail(DMF_E_SHAPE, "the multiplicity form needs K <= 6, n_u <= 4, K + n_u (even padded) <= 8, partial or purity mode and a tile of a multiple of 4 rows");
     dmf_batch_s* b = new dmf_batch_s;
     b->h = h;
     b->shape = s;
+    b->multmode = n_mult ? 1 : 0;
     b->launches = 0;
     b->pinned = nullptr;
     b->mom_dev = nullptr;
@@ -512,6 +542,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     g.n_parts = p.n_parts; g.n_groups = p.n_groups; g.part_stride = p.part_stride;
     g.offX = p.offX; g.offD = p.offD; g.offR = p.offR; g.offU = p.offU; g.offUp = p.offUp; g.stage_bytes = p.stage_bytes;
     g.row_bulk = p.row_bulk; g.mode = s.mode; g.gather = gather ? 1 : 0;
+    g.fit_major = 0; g.multmode = 0;
     {
         const unsigned sT = s.dtype == DMF_F64 ? 8 : 4, sW = s.wtype == DMF_W_U16 ? 2 : sT;
         g.tile_tx[0] = (unsigned)(p.tile_rows * s.ldx * sT);
@@ -525,7 +556,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->fits_dev = reinterpret_cast<FitDev*>(base + p.off_fits);
     b->states_dev = reinterpret_cast<FitState*>(base + p.off_states);
     b->gram_ok = p.gram_ok;
-    b->engine = p.gram_ok ? DMF_ENGINE_GRAM : DMF_ENGINE_STREAM;
+    b->engine = p.gram_ok ? DMF_ENGINE_GRAM : DMF_ENGINE_STREAM;      // multiplicity form implies gram (checked above)
     if (p.gram_ok) {
         Geom& q = b->gg;
         q = g;
@@ -533,13 +564,15 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         q.tile_rows = p.tile_rows_g; q.n_tiles = p.n_tiles_g;
         q.ntc = p.ntc_g; q.rg = kConsumers / p.ntc_g;
         q.n_parts = p.n_parts_g; q.n_groups = p.n_groups_g;
-        q.offX = p.g_offX; q.offD = p.g_offD; q.offR = p.g_offR; q.offU = p.g_offU; q.offUp = p.g_offU; q.stage_bytes = p.g_stage_bytes;
+        q.offX = p.g_offX; q.offD = p.g_offD; q.offR = p.g_offR; q.offU = p.g_offU; q.offUp = p.g_offUp; q.stage_bytes = p.g_stage_bytes;
+        q.multmode = b->multmode;
+        q.fit_major = shared_inputs ? 1 : 0;
         const unsigned sT = s.dtype == DMF_F64 ? 8 : 4, sW = s.wtype == DMF_W_U16 ? 2 : sT;
         q.tile_tx[0] = (unsigned)(p.tile_rows_g * s.ldx * sT);
         q.tile_tx[1] = (unsigned)(p.tile_rows_g * s.ldd * sW);
         q.tile_tx[2] = s.K ? (unsigned)(p.tile_rows_g * s.ldr * sT) : 0u;
-        q.tile_tx[3] = (unsigned)(p.tile_rows_g * s.ldu * sT);
-        q.tile_tx[4] = 0;
+        q.tile_tx[3] = b->multmode ? (unsigned)(p.tile_rows_g * p.ng_g * 8) : (unsigned)(p.tile_rows_g * s.ldu * sT);
+        q.tile_tx[4] = b->multmode ? (unsigned)(p.tile_rows_g * 4) : 0u;
         b->kb_g = p.kb_g; b->nub_g = p.nub_g; b->c_g = p.c_g; b->ntc_g = p.ntc_g; b->pb_g = p.pb_g; b->c_p = p.c_p; b->ntc_p = p.ntc_p;
         b->ktb_in = p.ktb_in; b->smem_rg = p.smem_rg; b->smem_panel = p.smem_panel;
         b->n_parts_u = p.n_parts_u; b->n_groups_u = p.n_groups_u;
@@ -547,7 +580,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
             b->n_parts_u = p.n_parts_g; b->n_groups_u = p.n_groups_g;     // partial-sum buffers too small for the wide grid (tiny N): use the pass grid
         }
         if ((rc = set_smem(k_rowgram(b, 0), b->smem_rg)) || (rc = set_smem(k_rowgram(b, 1), b->smem_rg)) || (rc = set_smem(k_panel(b), b->smem_panel)) ||
-            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0))) {
+            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0)) || (b->multmode && (rc = set_smem(k_costcross(b), 0)))) {
             delete b;
             return rc;
         }
@@ -615,6 +648,7 @@ int dmf_batch_set_engine(dmf_batch_t b, int32_t engine) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (engine != DMF_ENGINE_STREAM && engine != DMF_ENGINE_GRAM) return fail(DMF_E_ARG, "engine must be DMF_ENGINE_STREAM or DMF_ENGINE_GRAM");
     if (engine == DMF_ENGINE_GRAM && !b->gram_ok) return fail(DMF_E_SHAPE, "the Gram-form engine supports n_u <= 4 (and needs its tile to fit in shared memory)");
+    if (engine == DMF_ENGINE_STREAM && b->multmode) return fail(DMF_E_STATE, "fits in multiplicity form run on the Gram-form engine only");
     b->engine = engine;
     return DMF_OK;
 }
@@ -628,7 +662,10 @@ int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
     if (initial) b->t_hi = 0;
-    return launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, 0, (cudaStream_t)stream);
+    int rc = launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, 0, (cudaStream_t)stream);
+    if (rc || !b->multmode) return rc;
+    // multiplicity form: the per-position cost terms and the set-up / termination logic
+    return launch_g(b, k_costcross(b), b->ntc_g, 0, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, 2, (cudaStream_t)stream);
 }
 int dmf_gram_u_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
@@ -648,7 +685,7 @@ int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
     int rc;
     for (int ca = ca_lo; ca < ca_hi; ++ca)
         for (int cb = 0; cb < cb_hi; cb += nb)
-            if ((rc = launch_g(b, k_panel(b), b->ntc_p, b->smem_panel, 0, 0, 0.0, ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream))) return rc;
+            if ((rc = launch_g(b, k_panel(b), b->ntc_p, b->smem_panel, 0, b->nub_g, 0.0, ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream))) return rc;
     return DMF_OK;
 }
 int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
@@ -663,6 +700,7 @@ int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
 int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "row sharding needs the Gram-form engine (n_u <= 4)");
+    if (b->multmode) return fail(DMF_E_STATE, "row sharding and the multiplicity form are not combined");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t per = b->stats_doubles;
     for (int i = 0; i < b->shape.n_fits; ++i) {

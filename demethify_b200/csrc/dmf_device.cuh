@@ -50,6 +50,11 @@ struct FitDev {
     double* rgbx;        //   copies when the CpG rows are sharded over several GPUs
     double* rscal;
     double* red;         // Gram engine: [part_stride] totals of the last cross-CTA reduction
+    // bootstrap resamples in multiplicity form: the fit's rows are the SOURCE rows of the shared X, d_x, R_trunc; source row m
+    // was drawn mult[m] times and owns the u rows offs[m] .. offs[m + 1] (positions sorted by source row)
+    const int32_t* mult;
+    const int32_t* offs;
+    double* usum;        // [M][NG] per source row: sum of u over its positions, then the upper triangle of sum u u^T
     int trace_cap;
     int pad;
 };
@@ -70,7 +75,12 @@ struct Geom {
     unsigned tile_tx[kMaxSrc];     // bytes of one FULL tile of X, D, Rk, U, Uprev (each a multiple of 16)
     int mode;                      // DMF_MODE_*
     int gather;                    // any fit uses a row index
+    int fit_major;                 // grid = (fits, parts) instead of (parts, fits): CTAs that run together work on the SAME row
+                                   // tiles of different fits, so fits sharing X / d_x / R_trunc are served from L2
+    int multmode;                  // fits are bootstrap resamples in multiplicity form (FitDev::mult / offs / usum)
 };
+__device__ __forceinline__ int part_id(const Geom& g) { return g.fit_major ? (int)blockIdx.y : (int)blockIdx.x; }
+__device__ __forceinline__ int fit_id(const Geom& g) { return g.fit_major ? (int)blockIdx.x : (int)blockIdx.y; }
 
 // ------------------------------------------------------------------------------------------------
 // kernel argument block and shared-memory control block
@@ -234,7 +244,7 @@ __device__ __forceinline__ void produce_full_tile(const Geom& g, const TileSrc* 
 // inside each group and in group order across groups (independent of arrival order).
 __device__ __forceinline__ bool hier_reduce(const Geom& g, const FitDev& f, double* out_sm, int n, int* s_flag) {
     const int tid = threadIdx.x;
-    const int grp = blockIdx.x / kGroup;
+    const int grp = part_id(g) / kGroup;
     const int gfirst = grp * kGroup;
     const int gsize = min(kGroup, g.n_parts - gfirst);
     __threadfence();

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
     constexpr int NG = ng_of(NUB);
     constexpr int NVP = pow2ceil(RPT * NG);
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
             s3 = consumer_block_max(dmx, scratch, c.ctid);
         }
         if (c.ctid == 0) {
-            double* p = f.part + (size_t)blockIdx.x * g.part_stride;
+            double* p = f.part + (size_t)part_id(g) * g.part_stride;
             p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
         }
     }
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
     constexpr int LOGR = RPT == 4 ? 2 : (RPT == 2 ? 1 : 0);
     static_assert(RPT == 1 || RPT == 2 || RPT == 4, "RPT must be 1, 2 or 4");
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
@@ -327,18 +327,20 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
     const char* Ucur = f.U + (size_t)ucur * g.uslot_bytes;
 
     double cost = 0.0, ssq_r = 0.0, ssq_u = 0.0, dmx = 0.0;
-    constexpr int NSRC = 4;
+    constexpr int NSRC = 5;
+    const bool multmode = g.multmode != 0;       // bootstrap resample in multiplicity form: rows are source rows, weighted by mult
     if (threadIdx.x == 0) {
         TileSrc* src = c.ctl->src;
         src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
         src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
         src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
-        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+        src[3] = {multmode ? nullptr : Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+        src[4] = {multmode ? reinterpret_cast<const char*>(f.mult) : nullptr, 4, g.offUp, 0, 0, 0};
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
@@ -402,17 +404,27 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                     const int ii = i < nUch ? i : 0;
                     lds2(sb + g.offU + ii * 2 * (unsigned)sizeof(T) + rr * upitch, uc[2 * i], uc[2 * i + 1]);
                 }
+                double wrow = 1.0;                                 // multiplicity of the row (1 outside multiplicity form)
+                if (multmode) {
+                    int mlt;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)rr));
+                    wrow = (double)mlt;
+                }
                 if (INITIAL && tc == 0 && live) {
+                    double sr = 0.0;
 #pragma unroll
                     for (int k = 0; k < KB; ++k)
-                        if (k < g.K) ssq_r = fma((double)rk[k], (double)rk[k], ssq_r);
+                        if (k < g.K) sr = fma((double)rk[k], (double)rk[k], sr);
+                    ssq_r = fma(wrow, sr, ssq_r);
+                    if (!multmode) {
 #pragma unroll
-                    for (int q = 0; q < NUB; ++q)
-                        if (q < g.nu) ssq_u = fma((double)uc[q], (double)uc[q], ssq_u);
+                        for (int q = 0; q < NUB; ++q)
+                            if (q < g.nu) ssq_u = fma((double)uc[q], (double)uc[q], ssq_u);
+                    }
                 }
                 T x[C], d[C], cres[C], z[C];
                 cl.load(sb, rr * xpitch, rr * dpitch, x, d);
-                if (INITIAL) {
+                if (INITIAL && wrow > 0.0) {
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) dmx = fmax(dmx, (double)d[cc]);
                 }
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                 for (int cc = 0; cc < C; ++cc) z[cc] = d[cc] * cres[cc];
                 {
                     const T ccA = fma_t<T>(z[1], cres[1], z[0] * cres[0]), ccB = fma_t<T>(z[3], cres[3], z[2] * cres[2]);
-                    if (live) cost += (cl.pvalid[0] ? (double)ccA : 0.0) + (cl.pvalid[1] ? (double)ccB : 0.0);
+                    if (live) cost = fma(wrow, (cl.pvalid[0] ? (double)ccA : 0.0) + (cl.pvalid[1] ? (double)ccB : 0.0), cost);
                 }
 #pragma unroll
                 for (int q = 0; q < NUB; ++q) {
@@ -487,6 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                             double* dst = RG + ((size_t)(grow0 + r) * wpr + wir) * NG;
 #pragma unroll
                             for (int v = 0; v < NG; ++v) dst[v] = gp[i][v];
+                            if (multmode) continue;     // cross terms need the per-position u: cost_cross_kernel adds them
                             // cost cross terms of this row (per-warp partial statistics are linear, so partial rows add up)
                             T un[NUB > 1 ? NUB : 2];
 #pragma unroll
@@ -527,14 +540,14 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
             s3 = consumer_block_max(dmx, scratch, c.ctid);
         }
         if (c.ctid == 0) {
-            double* p = f.part + (size_t)blockIdx.x * g.part_stride;
+            double* p = f.part + (size_t)part_id(g) * g.part_stride;
             p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
         }
     }
     if (!hier_reduce(g, f, rec, 3, &c.ctl->flag)) return;
     if (threadIdx.x == 0) {
         const double dm = INITIAL ? scan_dmax(g, f) : 0.0;
-        if (a.flags & kFlagPartial) {
+        if ((a.flags & kFlagPartial) || multmode) {
             f.scal[0] = rec[0]; f.scal[1] = rec[1]; f.scal[2] = rec[2]; f.scal[3] = dm;
         } else {
             cost_state_update<INITIAL>(g, f, st, rec, Acur, sizeof(T) == 4, a.tol, dm);
@@ -552,7 +565,7 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
     __shared__ double rec[2];
     __shared__ int flag;
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     const int n2 = a.k_inner;
@@ -569,7 +582,7 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
     const int wpr = (g.ntc + 31) / 32;
     const double* RG = f.rowgram;
     double ssq = 0.0;
-    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < g.M; row += (long long)gridDim.x * blockDim.x) {
+    for (long long row = (long long)part_id(g) * blockDim.x + threadIdx.x; row < g.M; row += (long long)g.n_parts * blockDim.x) {
         double v[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) v[i] = 0.0;
@@ -616,7 +629,7 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
             }
     }
     const double s0 = consumer_block_sum(ssq, scratch, threadIdx.x);
-    if (threadIdx.x == 0) f.part[(size_t)blockIdx.x * g.part_stride] = s0;
+    if (threadIdx.x == 0) f.part[(size_t)part_id(g) * g.part_stride] = s0;
     if (!hier_reduce(g, f, rec, 1, &flag)) return;
     if (threadIdx.x == 0) {
         st->a1 = a.mom_a[t0 + n2];
@@ -633,16 +646,186 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Multiplicity form (bootstrap resamples, bootstrap.py:28): one thread per SOURCE row m; its positions offs[m] .. offs[m+1]
+// share (b_m, H_m) but own their u.  u_inner_mult_kernel runs the n_iter2 update_u iterations of every position and leaves
+// usum[m] = [sum_p u_p | upper triangle of sum_p u_p u_p^T] for the Gram panel pass, which can then stream the shared,
+// contiguous X / d_x / R_trunc instead of gathering rows.
+template <typename T, int NUB>
+__global__ void __launch_bounds__(kThreads) u_inner_mult_kernel(const PassArgs a) {
+    constexpr int NG = ng_of(NUB);
+    __shared__ double scratch[16];
+    __shared__ double rec[2];
+    __shared__ int flag;
+    const Geom& g = a.g;
+    const FitDev f = a.fits[fit_id(g)];
+    FitState* st = f.st;
+    if (st->done) return;
+    const int n2 = a.k_inner;
+    const int ucur = st->u_cur;
+    const double l_w = st->l_w, lwo_in = st->l_w_old;
+    const T inv_lw = (T)1 / (T)l_w;
+    const int t0 = st->t_u;
+    const double* mm = a.mom_m + t0;
+    const double cap0 = 0.9999 * sqrt(lwo_in / l_w), cap1 = 0.9999 * sqrt(l_w / l_w);
+    T* Uc = reinterpret_cast<T*>(f.U + (size_t)ucur * g.uslot_bytes);
+    T* Up = reinterpret_cast<T*>(f.U + (size_t)(ucur ^ 1) * g.uslot_bytes);
+    const int wpr = (g.ntc + 31) / 32;
+    const double* RG = f.rowgram;
+    double ssq = 0.0;
+    for (long long row = (long long)part_id(g) * blockDim.x + threadIdx.x; row < g.M; row += (long long)g.n_parts * blockDim.x) {
+        const int p0 = f.offs[row], p1 = f.offs[row + 1];
+        double us[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) us[i] = 0.0;
+        if (p1 > p0) {
+            double v[NG];
+#pragma unroll
+            for (int i = 0; i < NG; ++i) v[i] = 0.0;
+            for (int w = 0; w < wpr; ++w) {
+                const double* p = RG + ((size_t)row * wpr + w) * NG;
+#pragma unroll
+                for (int i = 0; i < NG; ++i) v[i] += __ldcg(p + i);
+            }
+            for (int pos = p0; pos < p1; ++pos) {
+                T u[NUB], up[NUB];
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    u[q] = q < g.nu ? Uc[(size_t)pos * g.ldu + q] : (T)0;
+                    up[q] = q < g.nu ? Up[(size_t)pos * g.ldu + q] : (T)0;
+                }
+                for (int it = 0; it < n2; ++it) {
+                    const T beta = (T)fmin(__ldg(mm + it), it == 0 ? cap0 : cap1);
+                    T ut[NUB];
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q) ut[q] = u[q] + beta * (u[q] - up[q]);
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q) {
+                        double sq = 0.0;
+#pragma unroll
+                        for (int q2 = 0; q2 < NUB; ++q2)
+                            sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], (double)ut[q2], sq);
+                        T un = ut[q] + (T)(v[q] - sq) * inv_lw;
+                        un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
+                        up[q] = u[q];
+                        u[q] = un;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NUB; ++q)
+                    if (q < g.nu) {
+                        Uc[(size_t)pos * g.ldu + q] = u[q];
+                        Up[(size_t)pos * g.ldu + q] = up[q];
+                        ssq = fma((double)u[q], (double)u[q], ssq);
+                    }
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    us[q] += (double)u[q];
+#pragma unroll
+                    for (int q2 = q; q2 < NUB; ++q2) us[NUB + tri_index(q, q2, NUB)] = fma((double)u[q], (double)u[q2], us[NUB + tri_index(q, q2, NUB)]);
+                }
+            }
+        }
+        double* dst = f.usum + (size_t)row * NG;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) dst[i] = us[i];
+    }
+    const double s0 = consumer_block_sum(ssq, scratch, threadIdx.x);
+    if (threadIdx.x == 0) f.part[(size_t)part_id(g) * g.part_stride] = s0;
+    if (!hier_reduce(g, f, rec, 1, &flag)) return;
+    if (threadIdx.x == 0) {
+        st->a1 = a.mom_a[t0 + n2];
+        st->t_u = t0 + n2;
+        if (n2 > 0) st->l_w_old = l_w;
+        st->ssq_u = rec[0];
+        const double nr = sqrt(st->ssq_rk + rec[0]);
+        st->l_h = (nr * nr) * st->dmax2;
+    }
+}
+
+// cost of the current iterate in multiplicity form: rowgram4_kernel left  sum_m mult_m sum_j d c^2  (and ||R||^2, max d) in
+// FitDev::scal; this kernel adds the per-position terms  -2 u_p^T b_m + u_p^T H_m u_p  (and ||u||^2 at set-up), writes usum
+// at set-up, and runs the set-up / termination logic (deconvolution.py:192-204, :218-221).
+template <typename T, int NUB>
+__global__ void __launch_bounds__(kThreads) cost_cross_kernel(const PassArgs a) {
+    constexpr int NG = ng_of(NUB);
+    __shared__ double scratch[16];
+    __shared__ double rec[4];
+    __shared__ int flag;
+    const Geom& g = a.g;
+    const FitDev f = a.fits[fit_id(g)];
+    FitState* st = f.st;
+    if (st->done) return;
+    const bool initial = (a.flags & kFlagInitial) != 0;
+    const int ucur = st->u_cur, acur = st->a_cur;
+    const T* Uc = reinterpret_cast<const T*>(f.U + (size_t)ucur * g.uslot_bytes);
+    const int wpr = (g.ntc + 31) / 32;
+    const double* RG = f.rowgram;
+    double cross = 0.0, ssq = 0.0;
+    for (long long row = (long long)part_id(g) * blockDim.x + threadIdx.x; row < g.M; row += (long long)g.n_parts * blockDim.x) {
+        const int p0 = f.offs[row], p1 = f.offs[row + 1];
+        double us[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) us[i] = 0.0;
+        if (p1 > p0) {
+            double v[NG];
+#pragma unroll
+            for (int i = 0; i < NG; ++i) v[i] = 0.0;
+            for (int w = 0; w < wpr; ++w) {
+                const double* p = RG + ((size_t)row * wpr + w) * NG;
+#pragma unroll
+                for (int i = 0; i < NG; ++i) v[i] += __ldcg(p + i);
+            }
+            for (int pos = p0; pos < p1; ++pos) {
+                double u[NUB];
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) u[q] = q < g.nu ? (double)Uc[(size_t)pos * g.ldu + q] : 0.0;
+                double ct = 0.0;
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    double hq = 0.0;
+#pragma unroll
+                    for (int q2 = 0; q2 < NUB; ++q2) hq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], u[q2], hq);
+                    ct = fma(u[q], hq - 2.0 * v[q], ct);
+                    ssq = fma(u[q], u[q], ssq);
+                    us[q] += u[q];
+#pragma unroll
+                    for (int q2 = q; q2 < NUB; ++q2) us[NUB + tri_index(q, q2, NUB)] = fma(u[q], u[q2], us[NUB + tri_index(q, q2, NUB)]);
+                }
+                cross += ct;
+            }
+        }
+        if (initial) {
+            double* dst = f.usum + (size_t)row * NG;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) dst[i] = us[i];
+        }
+    }
+    const double s0 = consumer_block_sum(cross, scratch, threadIdx.x);
+    const double s1 = consumer_block_sum(ssq, scratch, threadIdx.x);
+    if (threadIdx.x == 0) {
+        double* p = f.part + (size_t)part_id(g) * g.part_stride;
+        p[0] = s0; p[1] = s1;
+    }
+    if (!hier_reduce(g, f, rec, 2, &flag)) return;
+    if (threadIdx.x == 0) {
+        double r4[4] = {f.scal[0] + rec[0], f.scal[1], rec[1], f.scal[3]};
+        const char* Acur = f.A + (size_t)acur * g.Kt * g.N * sizeof(T);
+        if (initial) cost_state_update<true>(g, f, st, r4, Acur, sizeof(T) == 4, a.tol, r4[3]);
+        else cost_state_update<false>(g, f, st, r4, Acur, sizeof(T) == 4, a.tol, 0.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-sample Gram panel:  acc[p][q][j] = sum_m d_mj za_p(m) zb_q(m),  accx[p][j] = sum_m d_mj za_p(m) x_mj
 // za = PA consecutive entries of the padded register row [R_trunc (Kp) | u (nup)] starting at chunk a.ca0 (chunks of two),
 // zb = PB entries starting at chunk a.cb0.  The last CTA scatters the totals (and their mirror images) into
 // gram[Kt][Kt][N] and, when a.with_x, gbx[Kt][N].
-template <typename T, typename WT, int PA, int PB, int C>
+template <typename T, typename WT, int PA, int PB, int C, bool MULT>
 __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) gram_panel_kernel(const PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NA = PA / 2, NB = PB / 2;
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
@@ -662,18 +845,27 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
 #pragma unroll
             for (int q = 0; q < PB; ++q) acc[p][q][cc] = 0.0;
         }
-    constexpr int NSRC = 4;
+    constexpr int NSRC = MULT ? 5 : 4;
+    const int nub = a.k_inner;                       // MULT: unknown-type bucket of the usum records (NG = ng_of(nub) doubles per row)
+    const unsigned uspitch = (unsigned)(ng_of(nub) * 8);
     if (threadIdx.x == 0) {
         TileSrc* src = c.ctl->src;
         src[0] = {f.X, g.ldx * (long long)sizeof(T), g.offX, 1, (unsigned char)(g.row_bulk & 1u), 0};
         src[1] = {f.D, g.ldd * (long long)sizeof(WT), g.offD, 1, (unsigned char)((g.row_bulk >> 1) & 1u), 0};
         src[2] = {g.K ? f.Rk : nullptr, g.ldr * (long long)sizeof(T), g.offR, 1, (unsigned char)((g.row_bulk >> 2) & 1u), 0};
-        src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+        if (MULT) {
+            // multiplicity form: the u block reads the per-source-row sums usum, the known block the multiplicities
+            const bool a_is_u = a.ca0 >= (g.Kp >> 1);
+            src[3] = {a_is_u ? reinterpret_cast<const char*>(f.usum) : nullptr, (long long)uspitch, g.offU, 0, 0, 0};
+            src[4] = {a_is_u ? nullptr : reinterpret_cast<const char*>(f.mult), 4, g.offUp, 0, 0, 0};
+        } else {
+            src[3] = {Ucur, g.ldu * (long long)sizeof(T), g.offU, 0, 0, 0};
+        }
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     const int nR = g.Kp >> 1, nU = g.nup >> 1;
     {
@@ -696,7 +888,65 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
             mbar_wait(smem_u32(&c.ctl->full[cr.s]), cr.parity);
             const uint32_t sb = cr.sb;
             const int nrows = cr.rows(g, c);
-            if (colvalid) {
+            if (MULT) {
+                if (colvalid) {
+                    const bool a_is_u = a.ca0 >= nR;
+                    for (int r = gr; r < nrows; r += g.rg) {
+                        T x[C], d[C];
+                        cl.load(sb, r * xpitch, r * dpitch, x, d);
+                        double zax[PA], w[PA][PB];
+                        if (a_is_u) {
+#pragma unroll
+                            for (int p = 0; p < PA; ++p) {
+                                const int q = 2 * (a.ca0 - nR) + p;
+                                zax[p] = 0.0;
+                                if (q < nub) lds1(sb + g.offU + r * uspitch + 8u * (unsigned)q, zax[p]);
+                            }
+                        } else {
+                            int mlt;
+                            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)r));
+                            T za[PA];
+#pragma unroll
+                            for (int i = 0; i < NA; ++i) lds2(sb + aoff[i] + r * apitch[i], za[2 * i], za[2 * i + 1]);
+#pragma unroll
+                            for (int p = 0; p < PA; ++p) zax[p] = (double)mlt * (double)za[p];
+                        }
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) {
+                            const int ch = a.cb0 + i;
+                            if (ch < nR) {
+                                T z0, z1;
+                                lds2(sb + boff[i] + r * bpitch[i], z0, z1);
+#pragma unroll
+                                for (int p = 0; p < PA; ++p) { w[p][2 * i] = zax[p] * (double)z0; w[p][2 * i + 1] = zax[p] * (double)z1; }
+                            } else {
+#pragma unroll
+                                for (int p = 0; p < PA; ++p)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        const int qa = 2 * (a.ca0 - nR) + p, qb = 2 * (ch - nR) + e;
+                                        double sv = 0.0;
+                                        if (a_is_u && ch < nR + nU && qa < nub && qb < nub) {
+                                            const int lo = qa < qb ? qa : qb, hi = qa < qb ? qb : qa;
+                                            lds1(sb + g.offU + r * uspitch + 8u * (unsigned)(nub + tri_index(lo, hi, nub)), sv);
+                                        }
+                                        w[p][2 * i + e] = sv;
+                                    }
+                            }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) {
+                            const double dd = (double)d[cc], dx = dd * (double)x[cc];
+#pragma unroll
+                            for (int p = 0; p < PA; ++p) {
+                                accx[p][cc] = fma(dx, zax[p], accx[p][cc]);
+#pragma unroll
+                                for (int q = 0; q < PB; ++q) acc[p][q][cc] = fma(dd, w[p][q], acc[p][q][cc]);
+                            }
+                        }
+                    }
+                }
+            } else if (colvalid) {
                 for (int r = gr; r < nrows; r += g.rg) {
                     T za[PA], zb[PB], x[C], d[C];
 #pragma unroll
@@ -722,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
     __syncthreads();
     // CTA partial record [p][q (PB + 1, last = x)][N]: row groups are combined in fixed order, one p at a time
     double* scratch = reinterpret_cast<double*>(stages);
-    double* part = f.part + (size_t)blockIdx.x * g.part_stride;
+    double* part = f.part + (size_t)part_id(g) * g.part_stride;
     const int QN = (PB + 1) * g.N;
 #pragma unroll
     for (int p = 0; p < PA; ++p) {

@@ -50,16 +50,23 @@ kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int flags) {
 #undef DMF_G
     return nullptr;
 }
-kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int c, int) {
-    if (pb == 8 && c == 4) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 4>;
-    if (pb == 8) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 2>;
-    if (pb == 16) return gram_panel_kernel<DMF_T, DMF_WT, 2, 16, 1>;
+kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int c, int mult) {
+    if (mult) return (pb == 8 && c == 4) ? (kern_t)gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 4, true> : nullptr;
+    if (pb == 8 && c == 4) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 4, false>;
+    if (pb == 8) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 2, false>;
+    if (pb == 16) return gram_panel_kernel<DMF_T, DMF_WT, 2, 16, 1, false>;
     return nullptr;
 }
-kern_t DMF_CAT(pick_uinner_, DMF_TAG)(int nub, int, int) {
-    if (nub == 1) return u_inner_kernel<DMF_T, 1>;
-    if (nub == 2) return u_inner_kernel<DMF_T, 2>;
-    if (nub == 4) return u_inner_kernel<DMF_T, 4>;
+// which: 0 u_inner_kernel, 1 u_inner_mult_kernel, 2 cost_cross_kernel
+kern_t DMF_CAT(pick_uinner_, DMF_TAG)(int nub, int which, int) {
+#define DMF_UI(NUB_)                                                           \
+    if (nub == NUB_) {                                                         \
+        if (which == 0) return u_inner_kernel<DMF_T, NUB_>;                    \
+        if (which == 1) return u_inner_mult_kernel<DMF_T, NUB_>;               \
+        return cost_cross_kernel<DMF_T, NUB_>;                                 \
+    }
+    DMF_UI(1) DMF_UI(2) DMF_UI(4)
+#undef DMF_UI
     return nullptr;
 }
 kern_t DMF_CAT(pick_ainner_, DMF_TAG)(int ktb, int, int) {

@@ -121,8 +121,8 @@ __device__ __forceinline__ void cta_setup(const Geom& g, unsigned char* smem, Ct
     c.warp = threadIdx.x >> 5;
     c.lane = threadIdx.x & 31;
     c.ctid = threadIdx.x;
-    const int first = blockIdx.x;
-    c.n_my = (g.n_tiles > first) ? (g.n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int first = part_id(g);
+    c.n_my = (g.n_tiles > first) ? (g.n_tiles - first + g.n_parts - 1) / g.n_parts : 0;
     c.last_rows = (int)(g.M - (long long)(g.n_tiles - 1) * g.tile_rows);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -139,10 +139,10 @@ struct Ring {
     int it, s, gtile;
     unsigned parity;
     uint32_t sb;
-    __device__ __forceinline__ void init(uint32_t stages32) { it = 0; s = 0; parity = 0; sb = stages32; gtile = blockIdx.x; }
+    __device__ __forceinline__ void init(const Geom& g, uint32_t stages32) { it = 0; s = 0; parity = 0; sb = stages32; gtile = part_id(g); }
     __device__ __forceinline__ void advance(const Geom& g, uint32_t stages32) {
         ++it;
-        gtile += gridDim.x;
+        gtile += g.n_parts;
         if (++s == kStages) { s = 0; parity ^= 1u; sb = stages32; }
         else sb += g.stage_bytes;
     }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NCH = KTB / 2;
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
             s3 = consumer_block_max(dmx, scratch, c.ctid);
         }
         if (c.ctid == 0) {
-            double* p = f.part + (size_t)blockIdx.x * g.part_stride;
+            double* p = f.part + (size_t)part_id(g) * g.part_stride;
             p[0] = s0; p[1] = s1; p[2] = s2; p[3] = s3;
         }
     }
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NV = RPT * NUB;
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
@@ -429,8 +429,8 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
     double* rec = scratch + 16;
     if (c.warp < kConsumers / 32) {
         const double s0 = consumer_block_sum(ssq_u, scratch, c.ctid);
-        if (c.ctid == 0) f.part[(size_t)blockIdx.x * g.part_stride] = s0;
+        if (c.ctid == 0) f.part[(size_t)part_id(g) * g.part_stride] = s0;
     }
     if (!hier_reduce(g, f, rec, 1, &c.ctl->flag)) return;
     if (threadIdx.x == 0) {
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NCH = KTB / 2;
     const Geom& g = a.g;
-    const FitDev f = a.fits[blockIdx.y];
+    const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     CtaCtx c;
@@ -660,8 +660,8 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         T at[KTB][C];    // evaluation point: alpha_temp (PG) or alpha (FW)
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
             }
             consumer_bar();
         }
-        double* part = f.part + (size_t)blockIdx.x * g.part_stride;
+        double* part = f.part + (size_t)part_id(g) * g.part_stride;
         for (int e = c.ctid; e < KN; e += kConsumers) part[e] = scratch[e];
     }
     if (!hier_reduce(g, f, scratch, KN, &c.ctl->flag)) return;

@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(kThreads, 1) wls_moments_kernel(const WlsArgs 
     }
     __syncthreads();
     Ring pr, cr;
-    pr.init(stages32);
-    cr.init(stages32);
+    pr.init(g, stages32);
+    cr.init(g, stages32);
     for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
     const bool colvalid = tc < g.N;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) wls_moments_kernel(const WlsArgs 
         }
         __syncthreads();
     }
-    double* part = f.part + (size_t)blockIdx.x * g.part_stride;
+    double* part = f.part + (size_t)part_id(g) * g.part_stride;
     for (int e = threadIdx.x; e < BN; e += blockDim.x) part[e] = scratch[e];
     if (!hier_reduce(g, f, scratch, BN, &c.ctl->flag)) return;
     const int Kz = a.Kfull + 2;

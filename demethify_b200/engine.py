@@ -170,7 +170,7 @@ class FitBatch:
     """n_fits independent fits of one (M, N, K, n_u) shape, advanced together by single launches."""
 
     def __init__(self, problems, n_u, U0, A0, mode=_lib.DMF_MODE_PARTIAL, purity=None, rows=None, trace_cap=0,
-                 max_ctas_per_fit=0, engine=None):
+                 max_ctas_per_fit=0, engine=None, mult=None, offs=None):
         probs = problems if isinstance(problems, (list, tuple)) else [problems]
         self.n_fits = len(U0)
         if len(probs) == 1:
@@ -203,7 +203,11 @@ class FitBatch:
                 raise ValueError("purity needs one value per sample")
         self.rows = None
         if rows is not None:
-            self.rows = [to_device(np.asarray(r, dtype=np.int32), torch.int32, dev) for r in rows]
+            self.rows = [to_device(r if isinstance(r, torch.Tensor) else np.asarray(r, dtype=np.int32), torch.int32, dev) for r in rows]
+        # bootstrap resamples in multiplicity form: per fit int32 device tensors mult (M) and offs (M + 1)
+        self.mult, self.offs = mult, offs
+        if (mult is None) != (offs is None) or (mult is not None and rows is not None):
+            raise ValueError("pass either rows (gather form) or mult + offs (multiplicity form)")
         self.trace_cap = int(trace_cap)
         self.trace = torch.zeros((self.n_fits, max(self.trace_cap, 1)), dtype=torch.float64, device=dev) if trace_cap else None
 
@@ -224,6 +228,8 @@ class FitBatch:
             d.X, d.D = p.X.data_ptr(), p.D.data_ptr()
             d.Rk = p.Rk.data_ptr() if p.Rk is not None else None
             d.rows = self.rows[i].data_ptr() if self.rows is not None else None
+            if self.mult is not None:
+                d.mult, d.offs = self.mult[i].data_ptr(), self.offs[i].data_ptr()
             d.U, d.A = self.U[i].data_ptr(), self.A[i].data_ptr()
             d.purity = self.purity.data_ptr() if self.purity is not None else None
             d.cost_trace = self.trace[i].data_ptr() if self.trace is not None else None

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DMF_ABI_VERSION 2
+#define DMF_ABI_VERSION 3
 
 enum { DMF_OK = 0, DMF_E_ARG = 1, DMF_E_CUDA = 2, DMF_E_SHAPE = 3, DMF_E_STATE = 4 };
 
@@ -82,6 +82,13 @@ typedef struct dmf_fit_desc {
     double* cost_trace;    /* optional [trace_cap] cost after every outer iteration, or NULL    */
     int32_t trace_cap;
     int32_t reserved;
+    /* Bootstrap resample in MULTIPLICITY FORM (alternative to `rows`; all fits of a batch or none).  X, D, Rk are the SOURCE
+     * matrices (shape.M source rows, typically shared by all fits); source row m was drawn mult[m] times and owns the u rows
+     * offs[m] .. offs[m+1]-1 (offs has M + 1 entries, offs[M] == M: the resample has as many rows as the source,
+     * sklearn.utils.resample, bootstrap.py:28).  u is thus ordered by source row; position p of the resample sorted by
+     * source row.  The streaming passes then read X, D, Rk contiguously instead of gathering rows.  Device pointers, int32. */
+    const int32_t* mult;
+    const int32_t* offs;
 } dmf_fit_desc_t;
 
 /* Per-fit result block, filled by dmf_batch_read_state (host memory). */

@@ -94,6 +94,56 @@ def test_bootstrap_matches_reference(pkg, shipped, live_drivers, tmp_path):
         bt_ci(90, 2, 1, X, D, Rk, "uniform_", 5, 5, 1e-2, header, str(dp), names, None, [5])      # `--seed 5` quirk (Q1)
 
 
+@pytest.mark.parametrize("n_u,N,purity", [(1, 10, False), (2, 70, False), (1, 33, True)])
+def test_multiplicity_form_equals_gathered_fits(pkg, n_u, N, purity):
+    """A bootstrap resample as (shared source matrix + multiplicities + CSR over u) must give what the row-gathering form and
+    the oracle on the materialised resample give (bootstrap.py:28)."""
+    import torch
+    from demethify_b200 import _lib
+    from demethify_b200.engine import DeviceProblem, FitBatch
+    from oracle import bssmf_numpy as orc
+    rs = np.random.RandomState(17 + N)
+    M, K = 3001, 5
+    Rf = rs.beta(0.5, 0.5, size=(M, K + n_u))
+    A = rs.dirichlet(np.ones(K + n_u), N).T
+    D = rs.poisson(40, size=(M, N)) + 1
+    X = rs.binomial(D, np.clip(Rf @ A, 0, 1)) / D
+    Rk = np.ascontiguousarray(Rf[:, :K])
+    pur = rs.uniform(0.3, 0.9, size=N) if purity else None
+    prob = DeviceProblem(X, D, Rk)
+    dev = prob.device
+    fits = []
+    for seed in (3, 4, 9):
+        idx = np.random.RandomState(seed).randint(0, M, size=(M,))
+        order = np.argsort(idx, kind="stable")
+        u0 = np.random.RandomState(seed + 100).uniform(size=(M, n_u))
+        a0 = np.random.RandomState(seed + 200).dirichlet(np.ones(K + n_u), N).T
+        if purity:
+            a0 = np.vstack([a0[:K] / a0[:K].sum(0) * pur, a0[K:] / a0[K:].sum(0) * (1 - pur)])
+        fits.append((idx, order, u0, a0))
+    mode = _lib.DMF_MODE_PURITY if purity else _lib.DMF_MODE_PARTIAL
+    it1, it2, tol = (4, 30, 1e-9) if purity else (6, 10, 1e-9)
+    cnts = [torch.bincount(torch.from_numpy(f[0]).to(dev), minlength=M) for f in fits]
+    bm = FitBatch(prob, n_u, [f[2][f[1]] for f in fits], [f[3] for f in fits], mode=mode, purity=pur,
+                  mult=[c.to(torch.int32) for c in cnts],
+                  offs=[torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(c, 0)]).to(torch.int32) for c in cnts])
+    assert bm.engine == "gram"
+    rm = bm.results(bm.fit(it1, it2, tol))
+    bg = FitBatch(prob, n_u, [f[2][f[1]] for f in fits], [f[3] for f in fits], mode=mode, purity=pur, rows=[f[0][f[1]] for f in fits])
+    rg = bg.results(bg.fit(it1, it2, tol))
+    for (idx, order, u0, a0), (um, am, nm, cm), (ug, ag, ng_, cg) in zip(fits, rm, rg):
+        Xb, Db, Rb = X[idx], D[idx].astype(float), Rk[idx]
+        tr = {}
+        if purity:
+            uo, ao = orc.solve_purity(u0.copy(), np.c_[Rb, u0], a0.copy(), Xb, Db, Rb, n_u, pur, it1, it2, tol, trace=tr)
+        else:
+            uo, ao = orc.solve_partial_reference(u0.copy(), np.c_[Rb, u0], a0.copy(), Xb, Db, Rb, n_u, it1, it2, tol, trace=tr)
+        assert nm == ng_ == tr["n_outer"] and abs(cm - tr["costs"][-1]) <= 1e-9 * cm
+        assert np.abs(am - ao).max() <= TOL and np.abs(ag - ao).max() <= TOL
+        back = np.empty_like(um); back[order] = um
+        assert np.abs(back - uo).max() <= TOL
+
+
 @pytest.mark.parametrize("crit,it1,r", [("AIC", 10000, 5), ("BIC", 10000, 5), ("CCC", 40, 3), ("BCV", 40, 3)])
 def test_ic_sweep_matches_reference(pkg, shipped, live_drivers, crit, it1, r):
     from demethify_b200.ic import evaluate_best_ic
