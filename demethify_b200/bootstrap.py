@@ -39,6 +39,22 @@ def resample_indices(seed, M):
     return np.random.RandomState(seed).randint(0, M, size=(M,))
 
 
+def _shape_only_init(seed, init_option, M, K, N, n_u, with_zero_guard):
+    """uniform_ / beta inits (deconvolution.py:54-61, :246-253) from a PRIVATE legacy stream: RandomState(seed) produces
+    exactly what the reference's set_seed(seed) + global numpy.random calls produce, and is safe to use from worker threads."""
+    rs = np.random.RandomState(seed)
+    if init_option == "uniform_":
+        u = rs.uniform(size=(M, n_u))
+    else:
+        temp = np.ones((M, n_u))
+        u = rs.beta(temp * 0.5, temp * 0.5)
+    alpha = rs.dirichlet(np.ones(K + n_u), N).T
+    if with_zero_guard and alpha[-n_u:][0].all() == 0.0:      # deconvolution.py:74-76 (init_BSSMF_md only)
+        alpha[-n_u:][0] = 1e-10
+        alpha[:-n_u] = (1 - 1e-10) * alpha[:-n_u]
+    return u, alpha
+
+
 def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, purity, seed, prob=None,
                    keep_u=True):
     """All resample fits -> (alphas (B, Kt, N), us (B, M, n_u) or None, n_outer list).
@@ -68,16 +84,27 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
     for w0 in range(0, n_bootstrap, wave):
         chunk = seeds[w0:w0 + wave]
         rows, U0, A0, inv, mults, offs = [], [], [], [], [], []
-        for s in chunk:
+
+        def prepare(s):
             idx = resample_indices(s, M)
-            if data_dependent_init:
+            if data_dependent_init:      # `uniform` / SVD look at the resampled data and use the global stream: sequential
                 Xb, Db, Rb = meth_f[idx], np.asarray(counts)[idx], np.asarray(ref)[idx]
-            else:      # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
-                Xb, Db, Rb = meth_f, counts, ref
-            if purity is not None:
-                u0, _, a0 = init_BSSMF_md_p(init_option, Xb, Db, Rb, n_u, purity, seed=s)
-            else:
-                u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
+                if purity is not None:
+                    u0, _, a0 = init_BSSMF_md_p(init_option, Xb, Db, Rb, n_u, purity, seed=s)
+                else:
+                    u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
+            else:                        # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
+                opt = init_option if init_option in ("uniform_", "beta") and (init_option == "uniform_" or n_u <= N) else "uniform_"
+                u0, a0 = _shape_only_init(s, opt, M, prob.K, N, n_u, with_zero_guard=purity is None)
+            return idx, u0, a0
+        if data_dependent_init or init_option not in ("uniform_", "beta"):
+            prepared = [prepare(s) for s in chunk]
+        else:                            # numpy's legacy generators release the GIL: draw the resamples of the wave in parallel
+            from concurrent.futures import ThreadPoolExecutor
+            import os
+            with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+                prepared = list(ex.map(prepare, chunk))
+        for idx, u0, a0 in prepared:
             # order the resampled positions by source row (stable sort on the device); u is position-indexed, so permute it along
             idx_d = torch.from_numpy(idx).to(dev)
             order_d = torch.sort(idx_d, stable=True).indices

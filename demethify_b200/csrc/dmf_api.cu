@@ -55,6 +55,7 @@ struct dmf_batch_s {
     int kb_g, nub_g, c_g, ntc_g, pb_g, c_p, ntc_p, ktb_in;
     int n_parts_u, n_groups_u;
     unsigned smem_rg, smem_panel;
+    int n_active;                   // fits_dev holds the descriptors of the first n_active still-running fits (compacted at every poll)
     int multmode;                   // fits are bootstrap resamples in multiplicity form
     int sharded;                    // CpG rows sharded over GPUs: kernels publish partial sums, finalize runs on all-reduced sums
     std::vector<FitDev> fits_host;
@@ -179,7 +180,10 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
 
     // CTAs per fit: fill the GPU (SMs x occupancy) across the whole batch, never more than tiles
     long long target = (long long)h->sm_count * p.occ;
-    long long per_fit = std::max<long long>(1, target / s.n_fits);
+    // multi-fit batches: fits terminate at different outer iterations, so every fit gets at least kMinParts CTAs (the grid is
+    // oversubscribed, terminated fits return at once) and the stragglers still spread over the GPU
+    const long long kMinParts = s.n_fits > 1 ? 32 : 1;
+    long long per_fit = std::max<long long>(kMinParts, target / s.n_fits);
     if (s.max_ctas_per_fit > 0) per_fit = std::min<long long>(per_fit, s.max_ctas_per_fit);
     p.n_parts = (int)std::min<long long>(per_fit, p.n_tiles);
     p.n_groups = (p.n_parts + kGroup - 1) / kGroup;
@@ -248,7 +252,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 p.g_stage_bytes = (unsigned)a128g(p.g_offUp + trg * 4);
                 p.mult_ok = (p.c_g == 4 && p.pb_g == 8 && trg % 4 == 0 && s.mode != DMF_MODE_UNSUPERVISED) ? 1 : 0;
                 p.per_fit_usum = p.mult_ok ? align_up((size_t)s.M * p.ng_g * 8, 256) : 0;
-                long long per_fit_g = std::max<long long>(1, (long long)h->sm_count * p.occ_g / s.n_fits);
+                long long per_fit_g = std::max<long long>(kMinParts, (long long)h->sm_count * p.occ_g / s.n_fits);
                 if (s.max_ctas_per_fit > 0) per_fit_g = std::min<long long>(per_fit_g, s.max_ctas_per_fit);
                 p.n_parts_g = (int)std::min<long long>(per_fit_g, p.n_tiles_g);
                 p.n_groups_g = (p.n_parts_g + kGroup - 1) / kGroup;
@@ -318,6 +322,22 @@ int ensure_mom(dmf_batch_s* b, long long need, cudaStream_t st) {
     return DMF_OK;
 }
 
+// Upload the descriptors of the fits listed in `ids` (all fits when ids == nullptr) to the front of fits_dev.
+int upload_fits(dmf_batch_s* b, const std::vector<int>* ids, cudaStream_t st) {
+    const int n = ids ? (int)ids->size() : b->shape.n_fits;
+    if (n == 0) { b->n_active = 0; return DMF_OK; }
+    std::vector<FitDev> tmp;
+    const FitDev* src = b->fits_host.data();
+    if (ids) {
+        tmp.resize(n);
+        for (int i = 0; i < n; ++i) tmp[i] = b->fits_host[(*ids)[i]];
+        src = tmp.data();
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->fits_dev, src, sizeof(FitDev) * n, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    b->n_active = n;
+    return DMF_OK;
+}
+
 int set_smem(kern_t k, unsigned bytes) {
     if (!k) return fail(DMF_E_SHAPE, "no kernel instantiation for this shape");
     CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -337,7 +357,7 @@ int launch(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_in
     a.tol = tol;
     a.ca0 = a.cb0 = a.with_x = a.pad = 0;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev ? b->mom_dev + b->mom_cap : nullptr;
-    dim3 grid(b->g.n_parts, b->shape.n_fits, 1);
+    dim3 grid(b->g.n_parts, b->n_active, 1);
     k<<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     b->launches++;
@@ -349,6 +369,7 @@ kern_t k_alpha(dmf_batch_s* b) { return by_types(b->shape, g_alpha, b->ktb, 0, b
 kern_t k_u(dmf_batch_s* b) { return by_types(b->shape, g_u, b->kb, b->nub, b->c_u); }
 kern_t k_rowgram(dmf_batch_s* b, int initial) { return by_types(b->shape, g_rowgram, b->kb_g, b->nub_g, initial | (b->c_g == 4 ? 2 : 0)); }
 kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->c_p, b->multmode); }
+kern_t k_panel_u1(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->c_p, 2); }     // multiplicity form, n_u == 1
 kern_t k_uinner(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, b->multmode ? 1 : 0, 0); }
 kern_t k_costcross(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 2, 0); }
 kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in, 0, 0); }
@@ -367,12 +388,12 @@ int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_
     a.tol = tol;
     a.ca0 = ca0; a.cb0 = cb0; a.with_x = with_x; a.pad = 0;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
-    dim3 grid = grid_mode == 1 ? dim3(b->shape.n_fits, 1, 1) : dim3(b->gg.n_parts, b->shape.n_fits, 1);
+    dim3 grid = grid_mode == 1 ? dim3(b->n_active, 1, 1) : dim3(b->gg.n_parts, b->n_active, 1);
     if (grid_mode == 2) {
         a.g.n_parts = b->n_parts_u;
         a.g.n_groups = b->n_groups_u;
         if (b->n_parts_u != b->gg.n_parts) a.g.part_stride = 8;
-        grid = dim3(b->n_parts_u, b->shape.n_fits, 1);
+        grid = dim3(b->n_parts_u, b->n_active, 1);
     }
     if (grid_mode == 1) a.g.fit_major = 0;
     else if (a.g.fit_major) {
@@ -528,6 +549,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->mom_cap = 0;
     b->t_hi = 0;
     b->sharded = 0;
+    b->n_active = s.n_fits;
     b->fits_host = host;
     b->stats_local = p.gram_ok ? reinterpret_cast<double*>(base + p.off_stats) : nullptr;
     b->stats_global = p.gram_ok ? reinterpret_cast<double*>(base + p.off_gstats) : nullptr;
@@ -580,7 +602,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
             b->n_parts_u = p.n_parts_g; b->n_groups_u = p.n_groups_g;     // partial-sum buffers too small for the wide grid (tiny N): use the pass grid
         }
         if ((rc = set_smem(k_rowgram(b, 0), b->smem_rg)) || (rc = set_smem(k_rowgram(b, 1), b->smem_rg)) || (rc = set_smem(k_panel(b), b->smem_panel)) ||
-            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0)) || (b->multmode && (rc = set_smem(k_costcross(b), 0)))) {
+            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0)) || (b->multmode && ((rc = set_smem(k_costcross(b), 0)) || (rc = set_smem(k_panel_u1(b), b->smem_panel))))) {
             delete b;
             return rc;
         }
@@ -622,6 +644,7 @@ int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows,
 int dmf_pass_init(dmf_batch_t b, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     b->t_hi = 0;
+    if (b->n_active != b->shape.n_fits) { int rc0 = upload_fits(b, nullptr, (cudaStream_t)stream); if (rc0) return rc0; }
     return launch(b, k_cost(b, 1), b->ntc_alpha, b->smem_cost, kFlagInitial, 0, 0.0, (cudaStream_t)stream);
 }
 int dmf_pass_cost(dmf_batch_t b, double tol, void* stream) {
@@ -661,7 +684,10 @@ int dmf_batch_get_engine(dmf_batch_t b, int32_t* engine) {
 int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
-    if (initial) b->t_hi = 0;
+    if (initial) {
+        b->t_hi = 0;
+        if (b->n_active != b->shape.n_fits) { int rc0 = upload_fits(b, nullptr, (cudaStream_t)stream); if (rc0) return rc0; }
+    }
     int rc = launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, 0, (cudaStream_t)stream);
     if (rc || !b->multmode) return rc;
     // multiplicity form: the per-position cost terms and the set-up / termination logic
@@ -685,7 +711,8 @@ int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
     int rc;
     for (int ca = ca_lo; ca < ca_hi; ++ca)
         for (int cb = 0; cb < cb_hi; cb += nb)
-            if ((rc = launch_g(b, k_panel(b), b->ntc_p, b->smem_panel, 0, b->nub_g, 0.0, ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream))) return rc;
+            if ((rc = launch_g(b, (b->multmode && !known_block && b->shape.n_u == 1) ? k_panel_u1(b) : k_panel(b), b->ntc_p, b->smem_panel, 0, b->nub_g, 0.0,
+                               ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream))) return rc;
     return DMF_OK;
 }
 int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
@@ -708,7 +735,8 @@ int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream) {
         double* src = on ? b->stats_global + per * i : b->stats_local + per * i;
         f.rgram = src; f.rgbx = src + b->stats_gbx; f.rscal = src + b->stats_scal;
     }
-    CUDA_TRY(cudaMemcpyAsync(b->fits_dev, b->fits_host.data(), sizeof(FitDev) * b->shape.n_fits, cudaMemcpyHostToDevice, st));
+    int rc = upload_fits(b, nullptr, st);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
     b->sharded = on ? 1 : 0;
     b->engine = DMF_ENGINE_GRAM;
@@ -728,10 +756,10 @@ int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* str
     memset(&a, 0, sizeof(a));
     a.g = b->gg;
     a.fits = b->fits_dev;
-    a.k_inner = b->shape.n_fits;
+    a.k_inner = b->n_active;
     a.flags = (initial ? kFlagInitial : 0) | (b->shape.dtype == DMF_F32 ? kFlagF32 : 0);
     a.tol = tol;
-    finalize_cost_kernel<<<(b->shape.n_fits + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    finalize_cost_kernel<<<(b->n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     b->launches++;
     return DMF_OK;
@@ -801,12 +829,14 @@ int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol,
         issued += todo;
         CUDA_TRY(cudaMemcpyAsync(b->pinned, b->states_dev, sizeof(FitState) * n, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        bool all_done = true;
+        std::vector<int> active;
         for (int i = 0; i < n; ++i) {
             if (b->pinned[i].done == 3) return fail(DMF_E_STATE, "non-finite values reached the simplex projection (fit " + std::to_string(i) + ")");
-            all_done &= (b->pinned[i].done != 0);
+            if (b->pinned[i].done == 0) active.push_back(i);
         }
-        if (all_done) break;
+        if (active.empty()) break;
+        // launch only the still-running fits from now on (terminated fits would return at once, but their CTAs still cost a launch slot)
+        if ((int)active.size() != b->n_active && (rc = upload_fits(b, &active, st))) return rc;
         chunk = std::min(chunk * 2, 16);
     }
     CUDA_TRY(cudaStreamSynchronize(st));

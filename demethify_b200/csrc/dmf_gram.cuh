@@ -823,7 +823,8 @@ __global__ void __launch_bounds__(kThreads) cost_cross_kernel(const PassArgs a) 
 template <typename T, typename WT, int PA, int PB, int C, bool MULT>
 __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) gram_panel_kernel(const PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NA = PA / 2, NB = PB / 2;
+    constexpr int NA = PA / 2, NB = PB / 2;      // PA == 1 (NA == 0) exists for the MULT u block with a single unknown type only
+    static_assert(PA >= 2 || MULT, "PA = 1 is a multiplicity-form instantiation");
     const Geom& g = a.g;
     const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
@@ -870,7 +871,7 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
     const int nR = g.Kp >> 1, nU = g.nup >> 1;
     {
         // chunk -> (offset, pitch) inside a stage; chunks beyond the row alias chunk 0 (their totals are dropped)
-        unsigned aoff[NA], apitch[NA], boff[NB], bpitch[NB];
+        unsigned aoff[NA > 0 ? NA : 1], apitch[NA > 0 ? NA : 1], boff[NB], bpitch[NB];
         auto locate = [&](int ch, unsigned& off, unsigned& pitch) {
             if (ch >= nR + nU) ch = 0;
             if (ch < nR) { off = g.offR + ch * 2 * (unsigned)sizeof(T); pitch = (unsigned)(g.ldr * sizeof(T)); }
@@ -905,11 +906,11 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
                         } else {
                             int mlt;
                             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)r));
-                            T za[PA];
+                            T za[PA >= 2 ? PA : 2];
 #pragma unroll
                             for (int i = 0; i < NA; ++i) lds2(sb + aoff[i] + r * apitch[i], za[2 * i], za[2 * i + 1]);
 #pragma unroll
-                            for (int p = 0; p < PA; ++p) zax[p] = (double)mlt * (double)za[p];
+                            for (int p = 0; p < PA; ++p) zax[p] = PA >= 2 ? (double)mlt * (double)za[p] : 0.0;
                         }
 #pragma unroll
                         for (int i = 0; i < NB; ++i) {
@@ -948,7 +949,7 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
                 }
             } else if (colvalid) {
                 for (int r = gr; r < nrows; r += g.rg) {
-                    T za[PA], zb[PB], x[C], d[C];
+                    T za[PA >= 2 ? PA : 2], zb[PB], x[C], d[C];
 #pragma unroll
                     for (int i = 0; i < NA; ++i) lds2(sb + aoff[i] + r * apitch[i], za[2 * i], za[2 * i + 1]);
 #pragma unroll

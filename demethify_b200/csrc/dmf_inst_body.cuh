@@ -50,7 +50,9 @@ kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int flags) {
 #undef DMF_G
     return nullptr;
 }
+// mult: 0 plain, 1 multiplicity form, 2 multiplicity form, u block of a single unknown type (PA = 1)
 kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int c, int mult) {
+    if (mult == 2) return (pb == 8 && c == 4) ? (kern_t)gram_panel_kernel<DMF_T, DMF_WT, 1, 8, 4, true> : nullptr;
     if (mult) return (pb == 8 && c == 4) ? (kern_t)gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 4, true> : nullptr;
     if (pb == 8 && c == 4) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 4, false>;
     if (pb == 8) return gram_panel_kernel<DMF_T, DMF_WT, 2, 8, 2, false>;

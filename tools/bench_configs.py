@@ -73,5 +73,51 @@ def main():
         print(json.dumps(o), flush=True)
 
 
-if __name__ == "__main__":
+
+
+def c4_kernel_times(B=128, M=500_000, N=64, n_u=1):
+    """Per-kernel CUDA-event times of the bootstrap batch in multiplicity form (called with `c4prof`)."""
+    import torch
+    from demethify_b200 import _lib
+    from demethify_b200.engine import DeviceProblem, FitBatch
+    X, D, Rk, _ = synth(2, M, N, 6, n_u)
+    prob = DeviceProblem(X, D, Rk)
+    dev = prob.device
+    U0, A0, mults, offs = [], [], [], []
+    for s in range(B):
+        rs = np.random.RandomState(s)
+        idx = torch.from_numpy(rs.randint(0, M, size=(M,))).to(dev)
+        cnt = torch.bincount(idx, minlength=M)
+        mults.append(cnt.to(torch.int32))
+        offs.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]).to(torch.int32))
+        U0.append(torch.from_numpy(rs.uniform(size=(M, n_u))).to(dev))
+        A0.append(rs.dirichlet(np.ones(6 + n_u), N).T)
+    batch = FitBatch(prob, n_u, U0, A0, mult=mults, offs=offs)
+    batch.gram_init()
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+    acc = np.zeros(4)
+    reps = 6
+    for it in range(reps + 2):
+        e0 = ev(); batch.gram_u_inner(20); e1 = ev(); batch.gram_panels(False); e2 = ev(); batch.gram_alpha_inner(20); e3 = ev()
+        batch.gram_rowgram(False, 0.0); e4 = ev()
+        torch.cuda.synchronize()
+        if it >= 2:
+            acc += [e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e3.elapsed_time(e4)]
+    acc /= reps
+    bytes_pass = M * (8 * (N + 6 + n_u) + 2 * N)
+    print(json.dumps({"config": f"c4prof {B} fits x {M} x {N}, n_u={n_u}: ms per launch over ALL fits", "geometry": batch.geometry(),
+                      "u_inner_mult": acc[0], "panels": acc[1], "alpha_inner": acc[2], "rowgram+cost_cross": acc[3],
+                      "ms_per_fit_outer": acc.sum() / B, "panel_GBps_algorithmic": B * bytes_pass / acc[1] / 1e6,
+                      "rowgram_GBps_algorithmic": B * bytes_pass / acc[3] / 1e6}))
+
+
+if __name__ == "__main__" and "c4prof" in sys.argv:
+    c4_kernel_times()
+
+
+if __name__ == "__main__" and "c4prof" not in sys.argv:
     main()
