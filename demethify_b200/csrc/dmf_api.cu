@@ -765,6 +765,12 @@ int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* str
     return DMF_OK;
 }
 
+int dmf_batch_reserve_momentum(dmf_batch_t b, int64_t n_inner_total, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (n_inner_total < 0) return fail(DMF_E_ARG, "negative iteration count");
+    return ensure_mom(b, n_inner_total, (cudaStream_t)stream);
+}
+
 int dmf_gram_init(dmf_batch_t b, void* stream) {
     int rc = dmf_gram_rowgram(b, 1, 0.0, stream);
     if (rc) return rc;

@@ -51,6 +51,11 @@ class GpuShardBackend:
         self.scal_off = so.value
         self.has_known = b.K > 0
         self.device = b.device
+        self.supports_graphs = True
+
+    def reserve(self, n_inner_total):
+        """Make the following steps allocation- and sync-free (CUDA-graph capture)."""
+        _lib.check(_lib.lib().dmf_batch_reserve_momentum(self.batch.b, int(n_inner_total), _stream_ptr()))
 
     # ---- statistics blocks: (n_fits, doubles_per_fit) tensors [G | bx | scal(8)]
     def stats_local(self):
@@ -136,13 +141,36 @@ class RowShardedFit:
         self._reduce_scal(with_max=False)
         be.finalize_cost(False, tol)                  # identical termination decision on every rank
 
-    def fit(self, n_iter1, n_iter2, tol):
+    def capture_outer(self, n_iter2, tol):
+        """One outer iteration (kernels, D2D copies and both NCCL all-reduces) as a CUDA graph: a replay costs one launch
+        instead of ~12 host calls, which is what bounds strong scaling once a rank's share of the rows takes < 0.2 ms."""
+        self.outer(n_iter2, tol)                      # eager once: NCCL and the allocator are warm before the capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.outer(n_iter2, tol)
+        return graph
+
+    def fit(self, n_iter1, n_iter2, tol, use_graph=None):
         self.init()
         issued, chunk = 0, 2
+        graph = None
+        if use_graph is None:      # opt-in: DMF_SHARDED_GRAPH=1 (see DESIGN.md 6 for what was measured)
+            import os
+            use_graph = getattr(self.be, "supports_graphs", False) and n_iter1 > 4 and os.environ.get("DMF_SHARDED_GRAPH", "0") == "1"
+        if use_graph:
+            self.be.reserve((n_iter1 + 2) * max(n_iter2, 1))
+            graph = self.capture_outer(n_iter2, tol)
+            issued = 1
+            if self.be.all_done():
+                return self.be.results()
         while issued < n_iter1:
             todo = min(chunk, n_iter1 - issued)
             for _ in range(todo):
-                self.outer(n_iter2, tol)
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self.outer(n_iter2, tol)
             issued += todo
             if self.be.all_done():                    # the state is replicated: every rank leaves the loop together
                 break

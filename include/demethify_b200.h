@@ -158,6 +158,10 @@ int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream);
 int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream);
 int dmf_batch_stats_buffers(dmf_batch_t b, void** local_dev, void** global_dev, int64_t* doubles_per_fit, int64_t* scal_offset);
 int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* stream);
+/* The extrapolation weights of deconvolution.py:83-85 are data independent; the library keeps them in a device table that
+ * grows on demand (growth allocates and synchronises).  Reserving n_inner_total inner iterations up front makes every later
+ * dmf_gram_* call allocation- and sync-free, so that an outer iteration can be captured into a CUDA graph. */
+int dmf_batch_reserve_momentum(dmf_batch_t b, int64_t n_inner_total, void* stream);
 /* set-up (rowgram initial + known panels) and one whole outer iteration (u_inner, panels, alpha_inner, rowgram) */
 int dmf_gram_init(dmf_batch_t b, void* stream);
 int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
