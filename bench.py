@@ -387,7 +387,14 @@ def run_b200(args, rank, world, local_rank):
         dom = max(passes, key=lambda k: passes[k][0])
         dom_ms, dom_bytes = passes[dom]
         ach = dom_bytes / (dom_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very shape
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            same = tj["shape"] == {"M_cpg": M, "N_samples": N_S, "K_known": K_KNOWN, "n_unknown": N_UNK,
+                                   "dtype": "f64" if args.precision == "fp64" else "f32", "weights_storage": "u16" if sW == 2 else "float"}
+            traffic = tj["kernels"].get({"rowgram_kernel": "rowgram4_kernel"}.get(dom, dom)) if same else None
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
                 "kernels_ms_per_launch": kern,
                 "passes": {k: {"ms_per_launch": v[0], "achieved": v[1] / (v[0] * 1e-3) / 1e9, "frac": v[1] / (v[0] * 1e-3) / 1e9 / peak,

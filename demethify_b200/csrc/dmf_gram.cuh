@@ -378,6 +378,31 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
         const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
         const int nRch = g.Kp >> 1, nUch = g.nup >> 1;
         double* RG = f.rowgram;
+        // per-slot constants (the same for every tile): tile row of the slot and its byte offsets in the X, D, R, U regions.
+        // Slots beyond g.rpt alias slot 0's row; rows beyond the end of the last tile read stale rows of the stage: neither is
+        // ever stored or counted.
+        int rowi[RPT];
+        unsigned ox[RPT], od[RPT], orr[RPT], ou[RPT];
+#pragma unroll
+        for (int rb = 0; rb < RPT; ++rb) {
+            const int rl = rb ^ rmask;
+            const int rowe = gr + (rl < g.rpt ? rl : 0) * g.rg;
+            rowi[rb] = rl < g.rpt ? rowe : 0x3fffffff;
+            ox[rb] = rowe * xpitch; od[rb] = rowe * dpitch; orr[rb] = g.offR + rowe * rpitch; ou[rb] = g.offU + rowe * upitch;
+        }
+        unsigned rco[KB > 1 ? KB / 2 : 1], uco[(NUB + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < KB / 2; ++i) rco[i] = (i < nRch ? i : 0) * 2 * (unsigned)sizeof(T);
+#pragma unroll
+        for (int i = 0; i < (NUB + 1) / 2; ++i) uco[i] = (i < nUch ? i : 0) * 2 * (unsigned)sizeof(T);
+        // au (x) au per owned column: H_m = sum_j d_mj P_j
+        T P[NG - NUB][C];
+#pragma unroll
+        for (int q = 0; q < NUB; ++q)
+#pragma unroll
+            for (int q2 = q; q2 < NUB; ++q2)
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) P[tri_index(q, q2, NUB)][cc] = au[q][cc] * au[q2][cc];
 
         for (; cr.it < c.n_my; cr.advance(g, stages32)) {
             produce_next(g, f, c, pr, stages32, NSRC);
@@ -389,25 +414,18 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
             double gp[RPT][NG];
 #pragma unroll
             for (int rb = 0; rb < RPT; ++rb) {
-                const int rl = rb ^ rmask;
-                const int r = gr + rl * g.rg;
-                const bool live = (rl < g.rpt) && (r < nrows);
-                const int rr = live ? r : 0;                      // dead slots recompute tile row 0; never stored, never counted
+                const bool live = rowi[rb] < nrows;
                 T rk[KB > 0 ? KB : 1], uc[NUB > 1 ? NUB : 2];
 #pragma unroll
-                for (int i = 0; i < KB / 2; ++i) {
-                    const int ii = i < nRch ? i : 0;
-                    lds2(sb + g.offR + ii * 2 * (unsigned)sizeof(T) + rr * rpitch, rk[2 * i], rk[2 * i + 1]);
-                }
+                for (int i = 0; i < KB / 2; ++i) lds2(sb + orr[rb] + rco[i], rk[2 * i], rk[2 * i + 1]);
+                if (!multmode) {
 #pragma unroll
-                for (int i = 0; i < (NUB + 1) / 2; ++i) {
-                    const int ii = i < nUch ? i : 0;
-                    lds2(sb + g.offU + ii * 2 * (unsigned)sizeof(T) + rr * upitch, uc[2 * i], uc[2 * i + 1]);
+                    for (int i = 0; i < (NUB + 1) / 2; ++i) lds2(sb + ou[rb] + uco[i], uc[2 * i], uc[2 * i + 1]);
                 }
                 double wrow = 1.0;                                 // multiplicity of the row (1 outside multiplicity form)
                 if (multmode) {
                     int mlt;
-                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)rr));
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)(live ? rowi[rb] : 0)));
                     wrow = (double)mlt;
                 }
                 if (INITIAL && tc == 0 && live) {
@@ -423,8 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                     }
                 }
                 T x[C], d[C], cres[C], z[C];
-                cl.load(sb, rr * xpitch, rr * dpitch, x, d);
-                if (INITIAL && wrow > 0.0) {
+                cl.load(sb, ox[rb], od[rb], x, d);
+                if (INITIAL && live && wrow > 0.0) {
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) dmx = fmax(dmx, (double)d[cc]);
                 }
@@ -457,16 +475,13 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
 #pragma unroll
                     for (int cc = 1; cc < C; ++cc) bq = fma_t<T>(z[cc], au[q][cc], bq);
                     gp[rb][q] = (double)bq;
-                    T t[C];
+                }
 #pragma unroll
-                    for (int cc = 0; cc < C; ++cc) t[cc] = d[cc] * au[q][cc];
+                for (int e = 0; e < NG - NUB; ++e) {
+                    T h = d[0] * P[e][0];
 #pragma unroll
-                    for (int q2 = q; q2 < NUB; ++q2) {
-                        T h = t[0] * au[q2][0];
-#pragma unroll
-                        for (int cc = 1; cc < C; ++cc) h = fma_t<T>(t[cc], au[q2][cc], h);
-                        gp[rb][NUB + tri_index(q, q2, NUB)] = (double)h;
-                    }
+                    for (int cc = 1; cc < C; ++cc) h = fma_t<T>(d[cc], P[e][cc], h);
+                    gp[rb][NUB + e] = (double)h;
                 }
             }
             // select-free butterfly: split steps halve the slots, then plain xor steps on the remaining slot
@@ -493,9 +508,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
                     if (i < nslots) {
-                        const int rl = i ^ rmask;
-                        const int r = gr + rl * g.rg;
-                        if (rl < g.rpt && r < nrows) {
+                        const int r = rowi[i];
+                        if (r < nrows) {
                             double* dst = RG + ((size_t)(grow0 + r) * wpr + wir) * NG;
 #pragma unroll
                             for (int v = 0; v < NG; ++v) dst[v] = gp[i][v];
