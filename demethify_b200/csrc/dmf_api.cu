@@ -97,7 +97,7 @@ struct Plan {
     size_t ws_bytes, off_fits, off_states, off_tickets, off_part, off_gpart, per_fit_tickets, per_fit_part, per_fit_gpart;
     // Gram engine
     int gram_ok, kb_g, nub_g, c_g, rpt_g_max, rpt_g, ntc_g, occ_g, pb_g, c_p, ntc_p, ktb_in;
-    int tile_rows_g, n_tiles_g, n_parts_g, n_groups_g, wpr_g, ng_g;
+    int tile_rows_g, n_tiles_g, n_parts_g, n_groups_g, wpr_g, ng_g, stages_g;
     int n_parts_u, n_groups_u;     // u_inner_kernel: one thread per row, many more CTAs than the streaming passes
     unsigned g_offX, g_offD, g_offR, g_offU, g_offUp, g_stage_bytes, smem_rg, smem_panel;
     int mult_ok;                   // multiplicity form (bootstrap resamples) available for this shape
@@ -229,12 +229,15 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
             auto stage_g = [&](long long tr) { return a128g(tr * px) + a128g(tr * pd) + a128g(tr * pr) + a128g(tr * pu_stage) + a128g(tr * 4); };
             const size_t epi_panel = kCtlBytes + (size_t)(p.pb_g + 1) * s.N * 8 + 256;
             p.rpt_g = 0;
+            p.stages_g = kStages;
             for (int attempt = 0; attempt < 2 && !p.rpt_g; ++attempt) {
                 const size_t budget = (p.occ_g == 2 ? std::min<size_t>(smem_cap, 112 * 1024) : std::min<size_t>(smem_cap, 220 * 1024)) - kCtlBytes - 1024;
-                for (int rpt = p.rpt_g_max; rpt >= 1; rpt = (p.c_g == 4 ? rpt >> 1 : rpt - 1)) {
+                // full rows-per-thread first (register slots beyond rpt would be dead work), with a shallower ring if need be
+                for (int rpt = p.rpt_g_max; rpt >= 1 && !p.rpt_g; rpt = (p.c_g == 4 ? rpt >> 1 : rpt - 1)) {
                     const long long trg = (long long)rpt * rg_g;
                     if (trg % ra) continue;
-                    if (stage_g(trg) * kStages <= budget && epi_panel <= budget + kCtlBytes) { p.rpt_g = rpt; break; }
+                    for (int stg = kStages; stg >= 3; --stg)
+                        if (stage_g(trg) * stg <= budget && epi_panel <= budget + kCtlBytes) { p.rpt_g = rpt; p.stages_g = stg; break; }
                 }
                 if (!p.rpt_g) {
                     if (p.occ_g == 2) p.occ_g = 1; else break;
@@ -258,7 +261,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 p.n_groups_g = (p.n_parts_g + kGroup - 1) / kGroup;
                 p.n_parts_u = (int)std::min<long long>((s.M + kThreads - 1) / kThreads, std::max<long long>(p.n_parts_g, (long long)h->sm_count * 8 / s.n_fits));
                 p.n_groups_u = (p.n_parts_u + kGroup - 1) / kGroup;
-                const size_t pipe_g = kCtlBytes + (size_t)kStages * p.g_stage_bytes;
+                const size_t pipe_g = kCtlBytes + (size_t)p.stages_g * p.g_stage_bytes;
                 p.smem_rg = (unsigned)std::max(pipe_g, (size_t)kCtlBytes + 512);
                 p.smem_panel = (unsigned)std::max(pipe_g, epi_panel);
                 p.part_stride = std::max(p.part_stride, (int)align_up((size_t)2 * (p.pb_g + 1) * s.N, 2));
@@ -564,7 +567,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     g.n_parts = p.n_parts; g.n_groups = p.n_groups; g.part_stride = p.part_stride;
     g.offX = p.offX; g.offD = p.offD; g.offR = p.offR; g.offU = p.offU; g.offUp = p.offUp; g.stage_bytes = p.stage_bytes;
     g.row_bulk = p.row_bulk; g.mode = s.mode; g.gather = gather ? 1 : 0;
-    g.fit_major = 0; g.multmode = 0;
+    g.fit_major = 0; g.multmode = 0; g.stages = kStages;
     {
         const unsigned sT = s.dtype == DMF_F64 ? 8 : 4, sW = s.wtype == DMF_W_U16 ? 2 : sT;
         g.tile_tx[0] = (unsigned)(p.tile_rows * s.ldx * sT);
@@ -588,6 +591,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         q.n_parts = p.n_parts_g; q.n_groups = p.n_groups_g;
         q.offX = p.g_offX; q.offD = p.g_offD; q.offR = p.g_offR; q.offU = p.g_offU; q.offUp = p.g_offUp; q.stage_bytes = p.g_stage_bytes;
         q.multmode = b->multmode;
+        q.stages = p.stages_g;
         q.fit_major = shared_inputs ? 1 : 0;
         const unsigned sT = s.dtype == DMF_F64 ? 8 : 4, sW = s.wtype == DMF_W_U16 ? 2 : sT;
         q.tile_tx[0] = (unsigned)(p.tile_rows_g * s.ldx * sT);

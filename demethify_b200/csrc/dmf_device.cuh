@@ -78,7 +78,9 @@ struct Geom {
     int fit_major;                 // grid = (fits, parts) instead of (parts, fits): CTAs that run together work on the SAME row
                                    // tiles of different fits, so fits sharing X / d_x / R_trunc are served from L2
     int multmode;                  // fits are bootstrap resamples in multiplicity form (FitDev::mult / offs / usum)
+    int stages;                    // depth of the shared-memory ring actually used (3 .. kStages); 0 = kStages
 };
+__device__ __forceinline__ int n_stages(const Geom& g) { return g.stages ? g.stages : kStages; }
 __device__ __forceinline__ int part_id(const Geom& g) { return g.fit_major ? (int)blockIdx.y : (int)blockIdx.x; }
 __device__ __forceinline__ int fit_id(const Geom& g) { return g.fit_major ? (int)blockIdx.x : (int)blockIdx.y; }
 

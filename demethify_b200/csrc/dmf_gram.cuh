@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C + 2 * pow2ceil(R
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
         const bool colvalid = C * tc < g.N;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
         ColLoader<T, WT, C> cl;
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     const int nR = g.Kp >> 1, nU = g.nup >> 1;
     {
         // chunk -> (offset, pitch) inside a stage; chunks beyond the row alias chunk 0 (their totals are dropped)

@@ -143,16 +143,15 @@ struct Ring {
     __device__ __forceinline__ void advance(const Geom& g, uint32_t stages32) {
         ++it;
         gtile += g.n_parts;
-        if (++s == kStages) { s = 0; parity ^= 1u; sb = stages32; }
+        if (++s == n_stages(g)) { s = 0; parity ^= 1u; sb = stages32; }
         else sb += g.stage_bytes;
     }
     __device__ __forceinline__ int rows(const Geom& g, const CtaCtx& c) const { return gtile == g.n_tiles - 1 ? c.last_rows : g.tile_rows; }
 };
 
 // Producer duty is rotated over the warps (tile t is requested by warp t mod 8, between its own tiles), so no
-// single warp lags behind.  Requests run kAhead = kStages - 2 tiles ahead of consumption: the stage being
+// single warp lags behind.  Requests run (stages - 2) tiles ahead of consumption: the stage being
 // refilled was released a full tile ago, so the requesting warp practically never waits on `empty`.
-constexpr int kAhead = kStages - 2;
 __device__ __forceinline__ void produce_next(const Geom& g, const FitDev& f, const CtaCtx& c, Ring& pr, uint32_t stages32, int nsrc) {
     if (pr.it < c.n_my && c.warp == (pr.it & (kConsumers / 32 - 1))) {
         mbar_wait(smem_u32(&c.ctl->empty[pr.s]), pr.parity ^ 1u);
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) cost_kernel(cons
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
         const bool colvalid = C * tc < g.N;
@@ -431,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, ((KB + 2 * NUB) * C <= 24) ? 2 : 1) 
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
         const bool colvalid = C * tc < g.N;
@@ -662,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, (KTB <= 8) ? 2 : 1) alpha_pass_kerne
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     {
         T at[KTB][C];    // evaluation point: alpha_temp (PG) or alpha (FW)
 #pragma unroll

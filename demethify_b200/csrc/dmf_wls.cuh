@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kThreads, 1) wls_moments_kernel(const WlsArgs 
     Ring pr, cr;
     pr.init(g, stages32);
     cr.init(g, stages32);
-    for (int i = 0; i < kAhead; ++i) produce_next(g, f, c, pr, stages32, NSRC);
+    for (int i = 0; i < n_stages(g) - 2; ++i) produce_next(g, f, c, pr, stages32, NSRC);
     const int tc = c.ctid % g.ntc, gr = c.ctid / g.ntc;
     const bool colvalid = tc < g.N;
     const int j = colvalid ? tc : 0;
