@@ -109,17 +109,16 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
             idx_d = torch.from_numpy(idx).to(dev)
             order_d = torch.sort(idx_d, stable=True).indices
             u0_d = torch.from_numpy(np.ascontiguousarray(u0)).to(dev)[order_d]
+            rows.append(idx_d[order_d].to(torch.int32))
             if use_mult:
                 cnt = torch.bincount(idx_d, minlength=M)
                 mults.append(cnt.to(torch.int32))
                 offs.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]).to(torch.int32))
-            else:
-                rows.append(idx_d[order_d].to(torch.int32))
             U0.append(u0_d)
             A0.append(a0)
             inv.append(order_d)
         if use_mult:
-            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, mult=mults, offs=offs)
+            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows, mult=mults, offs=offs)
         else:
             batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows)
         states = batch.fit(n_iter1, n_iter2, tol)

@@ -375,6 +375,7 @@ kern_t k_panel(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->
 kern_t k_panel_u1(dmf_batch_s* b) { return by_types(b->shape, g_panel, b->pb_g, b->c_p, 2); }     // multiplicity form, n_u == 1
 kern_t k_uinner(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, b->multmode ? 1 : 0, 0); }
 kern_t k_costcross(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 2, 0); }
+kern_t k_usum(dmf_batch_s* b) { return by_types(b->shape, g_uinner, b->nub_g, 3, 0); }
 kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in, 0, 0); }
 
 // Gram-engine launch: geometry gg; ntc selects the thread mapping of the kernel; grid_x CTAs per fit (0: one CTA per fit on grid.x)
@@ -506,7 +507,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     for (int i = 0; i < s.n_fits; ++i) {
         const dmf_fit_desc_t& d = fits[i];
         if ((d.mult != nullptr) != (d.offs != nullptr)) return fail(DMF_E_ARG, "fit descriptor: mult and offs go together");
-        if (d.mult && d.rows) return fail(DMF_E_ARG, "fit descriptor: a fit is either gathered (rows) or in multiplicity form (mult / offs)");
+        if (d.mult && !d.rows) return fail(DMF_E_ARG, "fit descriptor: the multiplicity form needs rows (source row of every position, sorted)");
         n_mult += d.mult ? 1 : 0;
         shared_inputs &= (d.X == fits[0].X && d.D == fits[0].D && d.Rk == fits[0].Rk);
         if (!d.X || !d.D || !d.U || !d.A || (s.K && !d.Rk)) return fail(DMF_E_ARG, "fit descriptor has a NULL matrix");
@@ -518,8 +519,9 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         f.X = static_cast<const char*>(d.X);
         f.D = static_cast<const char*>(d.D);
         f.Rk = static_cast<const char*>(d.Rk);
-        f.rows = d.rows;
-        gather |= (d.rows != nullptr);
+        f.rows = d.mult ? nullptr : d.rows;          // multiplicity form: rows is the position -> source row map, nothing is gathered
+        f.pos_row = d.mult ? d.rows : nullptr;
+        gather |= (d.rows != nullptr && d.mult == nullptr);
         f.U = static_cast<char*>(d.U);
         f.A = static_cast<char*>(d.A);
         f.purity = d.purity;
@@ -704,7 +706,9 @@ int dmf_gram_u_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
     b->t_hi += n_iter2;
     int rc = ensure_mom(b, b->t_hi, (cudaStream_t)stream);
     if (rc) return rc;
-    return launch_g(b, k_uinner(b), b->ntc_g, 0, 0, n_iter2, 0.0, 0, 0, 0, 2, (cudaStream_t)stream);
+    rc = launch_g(b, k_uinner(b), b->ntc_g, 0, 0, n_iter2, 0.0, 0, 0, 0, 2, (cudaStream_t)stream);
+    if (rc || !b->multmode) return rc;
+    return launch_g(b, k_usum(b), b->ntc_g, 0, 0, 0, 0.0, 0, 0, 0, 2, (cudaStream_t)stream);      // per-source-row sums for the panel pass
 }
 int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");

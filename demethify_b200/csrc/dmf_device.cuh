@@ -54,6 +54,7 @@ struct FitDev {
     // was drawn mult[m] times and owns the u rows offs[m] .. offs[m + 1] (positions sorted by source row)
     const int32_t* mult;
     const int32_t* offs;
+    const int32_t* pos_row;   // source row of every position (nondecreasing)
     double* usum;        // [M][NG] per source row: sum of u over its positions, then the upper triangle of sum u u^T
     int trace_cap;
     int pad;

@@ -660,10 +660,24 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Multiplicity form (bootstrap resamples, bootstrap.py:28): one thread per SOURCE row m; its positions offs[m] .. offs[m+1]
-// share (b_m, H_m) but own their u.  u_inner_mult_kernel runs the n_iter2 update_u iterations of every position and leaves
-// usum[m] = [sum_p u_p | upper triangle of sum_p u_p u_p^T] for the Gram panel pass, which can then stream the shared,
-// contiguous X / d_x / R_trunc instead of gathering rows.
+// Multiplicity form (bootstrap resamples, bootstrap.py:28).  Position p of the resample (positions are sorted by source row,
+// rows[p] = its source row) owns one row of u; all positions of a source row m share (b_m, H_m).
+//   u_inner_mult_kernel : one thread per POSITION (no divergence over the multiplicities): n_iter2 update_u iterations
+//   usum_kernel         : one thread per SOURCE row: usum[m] = [sum_p u_p | upper triangle of sum_p u_p u_p^T] for the Gram
+//                         panel pass, which can then stream the shared, contiguous X / d_x / R_trunc instead of gathering rows
+//   cost_cross_kernel   : one thread per position: the per-position terms of the cost, then the set-up / termination logic
+template <typename T, int NUB>
+__device__ __forceinline__ void load_rowstats(const double* RG, long long row, int wpr, double (&v)[ng_of(NUB)]) {
+    constexpr int NG = ng_of(NUB);
+#pragma unroll
+    for (int i = 0; i < NG; ++i) v[i] = 0.0;
+    for (int w = 0; w < wpr; ++w) {
+        const double* p = RG + ((size_t)row * wpr + w) * NG;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) v[i] += __ldcg(p + i);
+    }
+}
+
 template <typename T, int NUB>
 __global__ void __launch_bounds__(kThreads) u_inner_mult_kernel(const PassArgs a) {
     constexpr int NG = ng_of(NUB);
@@ -684,64 +698,40 @@ __global__ void __launch_bounds__(kThreads) u_inner_mult_kernel(const PassArgs a
     T* Uc = reinterpret_cast<T*>(f.U + (size_t)ucur * g.uslot_bytes);
     T* Up = reinterpret_cast<T*>(f.U + (size_t)(ucur ^ 1) * g.uslot_bytes);
     const int wpr = (g.ntc + 31) / 32;
-    const double* RG = f.rowgram;
     double ssq = 0.0;
-    for (long long row = (long long)part_id(g) * blockDim.x + threadIdx.x; row < g.M; row += (long long)g.n_parts * blockDim.x) {
-        const int p0 = f.offs[row], p1 = f.offs[row + 1];
-        double us[NG];
+    for (long long pos = (long long)part_id(g) * blockDim.x + threadIdx.x; pos < g.M; pos += (long long)g.n_parts * blockDim.x) {
+        double v[NG];
+        load_rowstats<T, NUB>(f.rowgram, f.pos_row[pos], wpr, v);
+        T u[NUB], up[NUB];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) us[i] = 0.0;
-        if (p1 > p0) {
-            double v[NG];
+        for (int q = 0; q < NUB; ++q) {
+            u[q] = q < g.nu ? Uc[(size_t)pos * g.ldu + q] : (T)0;
+            up[q] = q < g.nu ? Up[(size_t)pos * g.ldu + q] : (T)0;
+        }
+        for (int it = 0; it < n2; ++it) {
+            const T beta = (T)fmin(__ldg(mm + it), it == 0 ? cap0 : cap1);
+            T ut[NUB];
 #pragma unroll
-            for (int i = 0; i < NG; ++i) v[i] = 0.0;
-            for (int w = 0; w < wpr; ++w) {
-                const double* p = RG + ((size_t)row * wpr + w) * NG;
+            for (int q = 0; q < NUB; ++q) ut[q] = u[q] + beta * (u[q] - up[q]);
 #pragma unroll
-                for (int i = 0; i < NG; ++i) v[i] += __ldcg(p + i);
-            }
-            for (int pos = p0; pos < p1; ++pos) {
-                T u[NUB], up[NUB];
+            for (int q = 0; q < NUB; ++q) {
+                double sq = 0.0;
 #pragma unroll
-                for (int q = 0; q < NUB; ++q) {
-                    u[q] = q < g.nu ? Uc[(size_t)pos * g.ldu + q] : (T)0;
-                    up[q] = q < g.nu ? Up[(size_t)pos * g.ldu + q] : (T)0;
-                }
-                for (int it = 0; it < n2; ++it) {
-                    const T beta = (T)fmin(__ldg(mm + it), it == 0 ? cap0 : cap1);
-                    T ut[NUB];
-#pragma unroll
-                    for (int q = 0; q < NUB; ++q) ut[q] = u[q] + beta * (u[q] - up[q]);
-#pragma unroll
-                    for (int q = 0; q < NUB; ++q) {
-                        double sq = 0.0;
-#pragma unroll
-                        for (int q2 = 0; q2 < NUB; ++q2)
-                            sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], (double)ut[q2], sq);
-                        T un = ut[q] + (T)(v[q] - sq) * inv_lw;
-                        un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
-                        up[q] = u[q];
-                        u[q] = un;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < NUB; ++q)
-                    if (q < g.nu) {
-                        Uc[(size_t)pos * g.ldu + q] = u[q];
-                        Up[(size_t)pos * g.ldu + q] = up[q];
-                        ssq = fma((double)u[q], (double)u[q], ssq);
-                    }
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) {
-                    us[q] += (double)u[q];
-#pragma unroll
-                    for (int q2 = q; q2 < NUB; ++q2) us[NUB + tri_index(q, q2, NUB)] = fma((double)u[q], (double)u[q2], us[NUB + tri_index(q, q2, NUB)]);
-                }
+                for (int q2 = 0; q2 < NUB; ++q2)
+                    sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], (double)ut[q2], sq);
+                T un = ut[q] + (T)(v[q] - sq) * inv_lw;
+                un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
+                up[q] = u[q];
+                u[q] = un;
             }
         }
-        double* dst = f.usum + (size_t)row * NG;
 #pragma unroll
-        for (int i = 0; i < NG; ++i) dst[i] = us[i];
+        for (int q = 0; q < NUB; ++q)
+            if (q < g.nu) {
+                Uc[(size_t)pos * g.ldu + q] = u[q];
+                Up[(size_t)pos * g.ldu + q] = up[q];
+                ssq = fma((double)u[q], (double)u[q], ssq);
+            }
     }
     const double s0 = consumer_block_sum(ssq, scratch, threadIdx.x);
     if (threadIdx.x == 0) f.part[(size_t)part_id(g) * g.part_stride] = s0;
@@ -756,9 +746,38 @@ __global__ void __launch_bounds__(kThreads) u_inner_mult_kernel(const PassArgs a
     }
 }
 
+template <typename T, int NUB>
+__global__ void __launch_bounds__(kThreads) usum_kernel(const PassArgs a) {
+    constexpr int NG = ng_of(NUB);
+    const Geom& g = a.g;
+    const FitDev f = a.fits[fit_id(g)];
+    if (f.st->done) return;
+    const T* Uc = reinterpret_cast<const T*>(f.U + (size_t)f.st->u_cur * g.uslot_bytes);
+    for (long long row = (long long)part_id(g) * blockDim.x + threadIdx.x; row < g.M; row += (long long)g.n_parts * blockDim.x) {
+        const int p0 = f.offs[row], p1 = f.offs[row + 1];
+        double us[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) us[i] = 0.0;
+        for (int pos = p0; pos < p1; ++pos) {
+            double u[NUB];
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) u[q] = q < g.nu ? (double)Uc[(size_t)pos * g.ldu + q] : 0.0;
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                us[q] += u[q];
+#pragma unroll
+                for (int q2 = q; q2 < NUB; ++q2) us[NUB + tri_index(q, q2, NUB)] = fma(u[q], u[q2], us[NUB + tri_index(q, q2, NUB)]);
+            }
+        }
+        double* dst = f.usum + (size_t)row * NG;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) dst[i] = us[i];
+    }
+}
+
 // cost of the current iterate in multiplicity form: rowgram4_kernel left  sum_m mult_m sum_j d c^2  (and ||R||^2, max d) in
-// FitDev::scal; this kernel adds the per-position terms  -2 u_p^T b_m + u_p^T H_m u_p  (and ||u||^2 at set-up), writes usum
-// at set-up, and runs the set-up / termination logic (deconvolution.py:192-204, :218-221).
+// FitDev::scal; this kernel adds the per-position terms  -2 u_p^T b_m + u_p^T H_m u_p  (and ||u||^2 at set-up) and runs the
+// set-up / termination logic (deconvolution.py:192-204, :218-221).
 template <typename T, int NUB>
 __global__ void __launch_bounds__(kThreads) cost_cross_kernel(const PassArgs a) {
     constexpr int NG = ng_of(NUB);
@@ -773,46 +792,23 @@ __global__ void __launch_bounds__(kThreads) cost_cross_kernel(const PassArgs a) 
     const int ucur = st->u_cur, acur = st->a_cur;
     const T* Uc = reinterpret_cast<const T*>(f.U + (size_t)ucur * g.uslot_bytes);
     const int wpr = (g.ntc + 31) / 32;
-    const double* RG = f.rowgram;
     double cross = 0.0, ssq = 0.0;
-    for (long long row = (long long)part_id(g) * blockDim.x + threadIdx.x; row < g.M; row += (long long)g.n_parts * blockDim.x) {
-        const int p0 = f.offs[row], p1 = f.offs[row + 1];
-        double us[NG];
+    for (long long pos = (long long)part_id(g) * blockDim.x + threadIdx.x; pos < g.M; pos += (long long)g.n_parts * blockDim.x) {
+        double v[NG];
+        load_rowstats<T, NUB>(f.rowgram, f.pos_row[pos], wpr, v);
+        double u[NUB];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) us[i] = 0.0;
-        if (p1 > p0) {
-            double v[NG];
+        for (int q = 0; q < NUB; ++q) u[q] = q < g.nu ? (double)Uc[(size_t)pos * g.ldu + q] : 0.0;
+        double ct = 0.0;
 #pragma unroll
-            for (int i = 0; i < NG; ++i) v[i] = 0.0;
-            for (int w = 0; w < wpr; ++w) {
-                const double* p = RG + ((size_t)row * wpr + w) * NG;
+        for (int q = 0; q < NUB; ++q) {
+            double hq = 0.0;
 #pragma unroll
-                for (int i = 0; i < NG; ++i) v[i] += __ldcg(p + i);
-            }
-            for (int pos = p0; pos < p1; ++pos) {
-                double u[NUB];
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) u[q] = q < g.nu ? (double)Uc[(size_t)pos * g.ldu + q] : 0.0;
-                double ct = 0.0;
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) {
-                    double hq = 0.0;
-#pragma unroll
-                    for (int q2 = 0; q2 < NUB; ++q2) hq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], u[q2], hq);
-                    ct = fma(u[q], hq - 2.0 * v[q], ct);
-                    ssq = fma(u[q], u[q], ssq);
-                    us[q] += u[q];
-#pragma unroll
-                    for (int q2 = q; q2 < NUB; ++q2) us[NUB + tri_index(q, q2, NUB)] = fma(u[q], u[q2], us[NUB + tri_index(q, q2, NUB)]);
-                }
-                cross += ct;
-            }
+            for (int q2 = 0; q2 < NUB; ++q2) hq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], u[q2], hq);
+            ct = fma(u[q], hq - 2.0 * v[q], ct);
+            ssq = fma(u[q], u[q], ssq);
         }
-        if (initial) {
-            double* dst = f.usum + (size_t)row * NG;
-#pragma unroll
-            for (int i = 0; i < NG; ++i) dst[i] = us[i];
-        }
+        cross += ct;
     }
     const double s0 = consumer_block_sum(cross, scratch, threadIdx.x);
     const double s1 = consumer_block_sum(ssq, scratch, threadIdx.x);

@@ -59,12 +59,13 @@ kern_t DMF_CAT(pick_panel_, DMF_TAG)(int pb, int c, int mult) {
     if (pb == 16) return gram_panel_kernel<DMF_T, DMF_WT, 2, 16, 1, false>;
     return nullptr;
 }
-// which: 0 u_inner_kernel, 1 u_inner_mult_kernel, 2 cost_cross_kernel
+// which: 0 u_inner_kernel, 1 u_inner_mult_kernel, 2 cost_cross_kernel, 3 usum_kernel
 kern_t DMF_CAT(pick_uinner_, DMF_TAG)(int nub, int which, int) {
 #define DMF_UI(NUB_)                                                           \
     if (nub == NUB_) {                                                         \
         if (which == 0) return u_inner_kernel<DMF_T, NUB_>;                    \
         if (which == 1) return u_inner_mult_kernel<DMF_T, NUB_>;               \
+        if (which == 3) return usum_kernel<DMF_T, NUB_>;                       \
         return cost_cross_kernel<DMF_T, NUB_>;                                 \
     }
     DMF_UI(1) DMF_UI(2) DMF_UI(4)

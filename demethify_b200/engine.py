@@ -184,7 +184,7 @@ class FitBatch:
         self.mode = mode
         dev, dt = p0.device, p0.dtype
         self.device = dev
-        if rows is not None:
+        if rows is not None and mult is None:
             self.M = int(rows[0].shape[0])
         # ping-pong buffers: both slots start at the initial iterate (u_ = u.copy(), deconvolution.py:194-195)
         self.ldu = _even(self.n_u)
@@ -206,8 +206,8 @@ class FitBatch:
             self.rows = [to_device(r if isinstance(r, torch.Tensor) else np.asarray(r, dtype=np.int32), torch.int32, dev) for r in rows]
         # bootstrap resamples in multiplicity form: per fit int32 device tensors mult (M) and offs (M + 1)
         self.mult, self.offs = mult, offs
-        if (mult is None) != (offs is None) or (mult is not None and rows is not None):
-            raise ValueError("pass either rows (gather form) or mult + offs (multiplicity form)")
+        if (mult is None) != (offs is None) or (mult is not None and rows is None):
+            raise ValueError("the multiplicity form needs mult, offs and rows (sorted source row of every position)")
         self.trace_cap = int(trace_cap)
         self.trace = torch.zeros((self.n_fits, max(self.trace_cap, 1)), dtype=torch.float64, device=dev) if trace_cap else None
 

@@ -75,18 +75,20 @@ typedef struct dmf_fit_desc {
     const void* D;         /* M x N   coverage weights d_x                                      */
     const void* Rk;        /* M x K   known reference profiles R_trunc (NULL when K = 0)        */
     const int32_t* rows;   /* optional gather: fit row p reads source row rows[p] of X, D, Rk
-                              (bootstrap.py:28 resample); NULL = identity.  U stays position-indexed */
+                              (bootstrap.py:28 resample); NULL = identity.  U stays position-indexed.
+                              With mult / offs (below): the sorted position -> source row map, nothing is gathered */
     void* U;               /* two slots of M x n_u (pitch ldu), shape.u_slot elements apart; BOTH hold the initial u */
     void* A;               /* [2][Kt][N]; BOTH slots hold the initial alpha (alpha_ = alpha.copy())    */
     const double* purity;  /* [N] internal purity vector (DMF_MODE_PURITY) else NULL            */
     double* cost_trace;    /* optional [trace_cap] cost after every outer iteration, or NULL    */
     int32_t trace_cap;
     int32_t reserved;
-    /* Bootstrap resample in MULTIPLICITY FORM (alternative to `rows`; all fits of a batch or none).  X, D, Rk are the SOURCE
-     * matrices (shape.M source rows, typically shared by all fits); source row m was drawn mult[m] times and owns the u rows
-     * offs[m] .. offs[m+1]-1 (offs has M + 1 entries, offs[M] == M: the resample has as many rows as the source,
-     * sklearn.utils.resample, bootstrap.py:28).  u is thus ordered by source row; position p of the resample sorted by
-     * source row.  The streaming passes then read X, D, Rk contiguously instead of gathering rows.  Device pointers, int32. */
+    /* Bootstrap resample in MULTIPLICITY FORM (all fits of a batch or none).  X, D, Rk are the SOURCE matrices (shape.M source
+     * rows, typically shared by all fits); source row m was drawn mult[m] times and owns the u rows offs[m] .. offs[m+1]-1
+     * (offs has M + 1 entries, offs[M] == M: the resample has as many rows as the source, sklearn.utils.resample,
+     * bootstrap.py:28).  u is thus ordered by source row, and `rows` must hold the nondecreasing source row of every position
+     * (the sorted resample index).  The streaming passes then read X, D, Rk contiguously instead of gathering rows.
+     * Device pointers, int32. */
     const int32_t* mult;
     const int32_t* offs;
 } dmf_fit_desc_t;

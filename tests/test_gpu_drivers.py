@@ -124,7 +124,7 @@ def test_multiplicity_form_equals_gathered_fits(pkg, n_u, N, purity):
     mode = _lib.DMF_MODE_PURITY if purity else _lib.DMF_MODE_PARTIAL
     it1, it2, tol = (4, 30, 1e-9) if purity else (6, 10, 1e-9)
     cnts = [torch.bincount(torch.from_numpy(f[0]).to(dev), minlength=M) for f in fits]
-    bm = FitBatch(prob, n_u, [f[2][f[1]] for f in fits], [f[3] for f in fits], mode=mode, purity=pur,
+    bm = FitBatch(prob, n_u, [f[2][f[1]] for f in fits], [f[3] for f in fits], mode=mode, purity=pur, rows=[f[0][f[1]] for f in fits],
                   mult=[c.to(torch.int32) for c in cnts],
                   offs=[torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(c, 0)]).to(torch.int32) for c in cnts])
     assert bm.engine == "gram"

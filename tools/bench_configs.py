@@ -83,16 +83,17 @@ def c4_kernel_times(B=128, M=500_000, N=64, n_u=1):
     X, D, Rk, _ = synth(2, M, N, 6, n_u)
     prob = DeviceProblem(X, D, Rk)
     dev = prob.device
-    U0, A0, mults, offs = [], [], [], []
+    U0, A0, mults, offs, rows = [], [], [], [], []
     for s in range(B):
         rs = np.random.RandomState(s)
         idx = torch.from_numpy(rs.randint(0, M, size=(M,))).to(dev)
         cnt = torch.bincount(idx, minlength=M)
+        rows.append(torch.sort(idx).values.to(torch.int32))
         mults.append(cnt.to(torch.int32))
         offs.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]).to(torch.int32))
         U0.append(torch.from_numpy(rs.uniform(size=(M, n_u))).to(dev))
         A0.append(rs.dirichlet(np.ones(6 + n_u), N).T)
-    batch = FitBatch(prob, n_u, U0, A0, mult=mults, offs=offs)
+    batch = FitBatch(prob, n_u, U0, A0, rows=rows, mult=mults, offs=offs)
     batch.gram_init()
 
     def ev():
