@@ -28,7 +28,7 @@ def set_engine(mode):
     """How the inner iterations run on the device (include/demethify_b200.h, DMF_ENGINE_*):
     'stream' = one streaming pass over X, d_x per reference inner iteration;
     'gram'   = two streaming passes per OUTER iteration build per-row / per-sample sufficient statistics and the
-               n_iter2 inner iterations run on those (n_u <= 4);
+               n_iter2 inner iterations run on those (n_u <= 4, or n_u <= 8 with K <= 6);
     'auto'   = 'gram' where the library supports the shape, else 'stream' (default)."""
     global _ENGINE
     if mode not in ("auto", "gram", "stream"):

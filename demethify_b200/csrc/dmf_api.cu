@@ -205,11 +205,13 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     p.per_fit_usum = 0;
     p.per_fit_rowgram = p.per_fit_stats = p.per_fit_red = 0;
     p.stats_gbx = p.stats_scal = 0;
-    if (s.n_u <= 4) {
+    if (s.n_u <= 4 || (s.n_u <= 8 && p.Kp <= 6)) {      // 5 .. 8 unknown types: 4-column kernels only (K <= 6)
         p.kb_g = s.K == 0 ? 0 : (p.Kp <= 6 ? 6 : (p.Kp <= 16 ? 16 : 32));
-        p.nub_g = s.n_u == 1 ? 1 : (s.n_u == 2 ? 2 : 4);
+        p.nub_g = s.n_u == 1 ? 1 : (s.n_u == 2 ? 2 : (s.n_u <= 4 ? 4 : 8));
         p.c_g = p.kb_g <= 6 ? 4 : (p.kb_g <= 16 ? 2 : 1);
-        p.rpt_g_max = p.c_g == 4 ? (p.nub_g <= 2 ? 4 : 2) : (p.nub_g == 1 ? 4 : (p.nub_g == 2 ? 3 : 2));
+        // rows per thread and tile: the 4-column kernels walk a tile in batches of their register rows (4 / 4 / 2 / 1 for 1 / 2 / 4 / 8
+        // unknown types), so 4 rows per thread and tile for all of them
+        p.rpt_g_max = p.c_g == 4 ? 4 : (p.nub_g == 1 ? 4 : (p.nub_g == 2 ? 3 : 2));
         p.ng_g = ng_of_h(p.nub_g);
         p.pb_g = rowlen <= 8 ? 8 : 16;
         p.c_p = p.pb_g == 8 ? 4 : 1;
@@ -253,7 +255,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 p.g_offU = (unsigned)a128g(p.g_offR + trg * pr);
                 p.g_offUp = (unsigned)a128g(p.g_offU + trg * pu_stage);
                 p.g_stage_bytes = (unsigned)a128g(p.g_offUp + trg * 4);
-                p.mult_ok = (p.c_g == 4 && p.pb_g == 8 && trg % 4 == 0 && s.mode != DMF_MODE_UNSUPERVISED) ? 1 : 0;
+                p.mult_ok = (p.c_g == 4 && p.pb_g == 8 && p.nub_g <= 4 && trg % 4 == 0 && s.mode != DMF_MODE_UNSUPERVISED) ? 1 : 0;
                 p.per_fit_usum = p.mult_ok ? align_up((size_t)s.M * p.ng_g * 8, 256) : 0;
                 long long per_fit_g = std::max<long long>(kMinParts, (long long)h->sm_count * p.occ_g / s.n_fits);
                 if (s.max_ctas_per_fit > 0) per_fit_g = std::min<long long>(per_fit_g, s.max_ctas_per_fit);
@@ -676,7 +678,8 @@ int dmf_pass_fw(dmf_batch_t b, int32_t k_inner, void* stream) {
 int dmf_batch_set_engine(dmf_batch_t b, int32_t engine) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (engine != DMF_ENGINE_STREAM && engine != DMF_ENGINE_GRAM) return fail(DMF_E_ARG, "engine must be DMF_ENGINE_STREAM or DMF_ENGINE_GRAM");
-    if (engine == DMF_ENGINE_GRAM && !b->gram_ok) return fail(DMF_E_SHAPE, "the Gram-form engine supports n_u <= 4 (and needs its tile to fit in shared memory)");
+    if (engine == DMF_ENGINE_GRAM && !b->gram_ok)
+        return fail(DMF_E_SHAPE, "the Gram-form engine supports n_u <= 4 (n_u <= 8 when K <= 6) and needs its tile to fit in shared memory");
     if (engine == DMF_ENGINE_STREAM && b->multmode) return fail(DMF_E_STATE, "fits in multiplicity form run on the Gram-form engine only");
     b->engine = engine;
     return DMF_OK;
@@ -734,7 +737,7 @@ int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
 }
 int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
-    if (!b->gram_ok) return fail(DMF_E_SHAPE, "row sharding needs the Gram-form engine (n_u <= 4)");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "row sharding needs the Gram-form engine (n_u <= 4, or n_u <= 8 with K <= 6)");
     if (b->multmode) return fail(DMF_E_STATE, "row sharding and the multiplicity form are not combined");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t per = b->stats_doubles;

@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
         const unsigned rpitch = (unsigned)(g.ldr * sizeof(T)), upitch = (unsigned)(g.ldu * sizeof(T));
         const int nRch = g.Kp >> 1, nUch = g.nup >> 1;
         double* RG = f.rowgram;
-        // per-slot constants (the same for every tile): tile row of the slot and its byte offsets in the X, D, R, U regions.
-        // Slots beyond g.rpt alias slot 0's row; rows beyond the end of the last tile read stale rows of the stage: neither is
-        // ever stored or counted.
+        // A tile holds g.rpt rows per row group, processed in batches of RPT (g.rpt is a multiple of RPT, or smaller than RPT: then
+        // the slots beyond it are dead).  Per-slot constants (the same for every tile and batch): tile row of the slot within
+        // batch 0 and its byte offsets in the X, D, R, U regions.  Dead slots alias slot 0's row; rows beyond the end of the last
+        // tile read stale rows of the stage: neither is ever stored or counted.
         int rowi[RPT];
         unsigned ox[RPT], od[RPT], orr[RPT], ou[RPT];
 #pragma unroll
@@ -395,14 +396,20 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
         for (int i = 0; i < KB / 2; ++i) rco[i] = (i < nRch ? i : 0) * 2 * (unsigned)sizeof(T);
 #pragma unroll
         for (int i = 0; i < (NUB + 1) / 2; ++i) uco[i] = (i < nUch ? i : 0) * 2 * (unsigned)sizeof(T);
-        // au (x) au per owned column: H_m = sum_j d_mj P_j
-        T P[NG - NUB][C];
+        // au (x) au per owned column (few unknown types only: registers): H_m = sum_j d_mj P_j
+        constexpr bool USE_P = NUB <= 2;
+        T P[USE_P ? NG - NUB : 1][C];
+        if (USE_P) {
 #pragma unroll
-        for (int q = 0; q < NUB; ++q)
+            for (int q = 0; q < NUB; ++q)
 #pragma unroll
-            for (int q2 = q; q2 < NUB; ++q2)
+                for (int q2 = q; q2 < NUB; ++q2)
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) P[tri_index(q, q2, NUB)][cc] = au[q][cc] * au[q2][cc];
+                    for (int cc = 0; cc < C; ++cc) P[USE_P ? tri_index(q, q2, NUB) : 0][cc] = au[q][cc] * au[q2][cc];
+        }
+        const int nbatch = g.rpt > RPT ? g.rpt / RPT : 1;
+        const unsigned bx = (unsigned)(RPT * g.rg) * xpitch, bd = (unsigned)(RPT * g.rg) * dpitch, br = (unsigned)(RPT * g.rg) * rpitch,
+                       bu = (unsigned)(RPT * g.rg) * upitch;
 
         for (; cr.it < c.n_my; cr.advance(g, stages32)) {
             produce_next(g, f, c, pr, stages32, NSRC);
@@ -411,21 +418,24 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
             const int nrows = cr.rows(g, c);
             const long long grow0 = (long long)cr.gtile * g.tile_rows;
 
+          for (int bb = 0; bb < nbatch; ++bb) {
+            const int brow = bb * RPT * g.rg;                      // first tile row of the batch (row group 0, slot row 0)
+            const uint32_t sbx = sb + bb * bx, sbd = sb + bb * bd, sbr = sb + bb * br, sbu = sb + bb * bu;
             double gp[RPT][NG];
 #pragma unroll
             for (int rb = 0; rb < RPT; ++rb) {
-                const bool live = rowi[rb] < nrows;
+                const bool live = rowi[rb] + brow < nrows;
                 T rk[KB > 0 ? KB : 1], uc[NUB > 1 ? NUB : 2];
 #pragma unroll
-                for (int i = 0; i < KB / 2; ++i) lds2(sb + orr[rb] + rco[i], rk[2 * i], rk[2 * i + 1]);
+                for (int i = 0; i < KB / 2; ++i) lds2(sbr + orr[rb] + rco[i], rk[2 * i], rk[2 * i + 1]);
                 if (!multmode) {
 #pragma unroll
-                    for (int i = 0; i < (NUB + 1) / 2; ++i) lds2(sb + ou[rb] + uco[i], uc[2 * i], uc[2 * i + 1]);
+                    for (int i = 0; i < (NUB + 1) / 2; ++i) lds2(sbu + ou[rb] + uco[i], uc[2 * i], uc[2 * i + 1]);
                 }
                 double wrow = 1.0;                                 // multiplicity of the row (1 outside multiplicity form)
                 if (multmode) {
                     int mlt;
-                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)(live ? rowi[rb] : 0)));
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(mlt) : "r"(sb + g.offUp + 4u * (unsigned)(live ? rowi[rb] + brow : 0)));
                     wrow = (double)mlt;
                 }
                 if (INITIAL && tc == 0 && live) {
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                     }
                 }
                 T x[C], d[C], cres[C], z[C];
-                cl.load(sb, ox[rb], od[rb], x, d);
+                cl.load(sb, bb * bx + ox[rb], bb * bd + od[rb], x, d);
                 if (INITIAL && live && wrow > 0.0) {
 #pragma unroll
                     for (int cc = 0; cc < C; ++cc) dmx = fmax(dmx, (double)d[cc]);
@@ -476,12 +486,28 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                     for (int cc = 1; cc < C; ++cc) bq = fma_t<T>(z[cc], au[q][cc], bq);
                     gp[rb][q] = (double)bq;
                 }
+                if (USE_P) {
 #pragma unroll
-                for (int e = 0; e < NG - NUB; ++e) {
-                    T h = d[0] * P[e][0];
+                    for (int e = 0; e < NG - NUB; ++e) {
+                        T h = d[0] * P[USE_P ? e : 0][0];
 #pragma unroll
-                    for (int cc = 1; cc < C; ++cc) h = fma_t<T>(d[cc], P[e][cc], h);
-                    gp[rb][NUB + e] = (double)h;
+                        for (int cc = 1; cc < C; ++cc) h = fma_t<T>(d[cc], P[USE_P ? e : 0][cc], h);
+                        gp[rb][NUB + e] = (double)h;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q) {
+                        T t[C];
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) t[cc] = d[cc] * au[q][cc];
+#pragma unroll
+                        for (int q2 = q; q2 < NUB; ++q2) {
+                            T h = t[0] * au[q2][0];
+#pragma unroll
+                            for (int cc = 1; cc < C; ++cc) h = fma_t<T>(t[cc], au[q2][cc], h);
+                            gp[rb][NUB + tri_index(q, q2, NUB)] = (double)h;
+                        }
+                    }
                 }
             }
             // select-free butterfly: split steps halve the slots, then plain xor steps on the remaining slot
@@ -508,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
                     if (i < nslots) {
-                        const int r = rowi[i];
+                        const int r = rowi[i] + brow;
                         if (r < nrows) {
                             double* dst = RG + ((size_t)(grow0 + r) * wpr + wir) * NG;
 #pragma unroll
@@ -538,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowgram4_kernel(const PassArgs a)
                     }
                 }
             }
+          }     // batches of the tile
             __syncwarp();
             if (c.lane == 0) mbar_arrive(smem_u32(&c.ctl->empty[cr.s]));
         }

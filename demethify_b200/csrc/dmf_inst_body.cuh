@@ -37,7 +37,7 @@ kern_t DMF_CAT(pick_rowgram_, DMF_TAG)(int kb, int nub, int flags) {
 #define DMF_G4(KB_, NUB_, RPT_)                                                                              \
     if (c4 && kb == KB_ && nub == NUB_)                                                                      \
         return initial ? (kern_t)rowgram4_kernel<DMF_T, DMF_WT, KB_, NUB_, RPT_, true> : (kern_t)rowgram4_kernel<DMF_T, DMF_WT, KB_, NUB_, RPT_, false>;
-    DMF_G4(0, 1, 4) DMF_G4(0, 2, 4) DMF_G4(0, 4, 2) DMF_G4(6, 1, 4) DMF_G4(6, 2, 4) DMF_G4(6, 4, 2)
+    DMF_G4(0, 1, 4) DMF_G4(0, 2, 4) DMF_G4(0, 4, 2) DMF_G4(0, 8, 1) DMF_G4(6, 1, 4) DMF_G4(6, 2, 4) DMF_G4(6, 4, 2) DMF_G4(6, 8, 1)
 #undef DMF_G4
     if (c4) return nullptr;
 #define DMF_G(KB_, NUB_, C_, RPT_)                                                                           \
@@ -68,7 +68,7 @@ kern_t DMF_CAT(pick_uinner_, DMF_TAG)(int nub, int which, int) {
         if (which == 3) return usum_kernel<DMF_T, NUB_>;                       \
         return cost_cross_kernel<DMF_T, NUB_>;                                 \
     }
-    DMF_UI(1) DMF_UI(2) DMF_UI(4)
+    DMF_UI(1) DMF_UI(2) DMF_UI(4) DMF_UI(8)
 #undef DMF_UI
     return nullptr;
 }

@@ -47,7 +47,7 @@ enum {
 /* how the inner iterations are executed (results agree to ~1e-15 on alpha; both are pinned by the same golden vectors)
  *   STREAM: one launch per reference inner iteration, each a streaming pass over X, d_x (dmf_pass_u / _alpha / _fw / _cost)
  *   GRAM  : per outer iteration two streaming passes build the sufficient statistics of the U step (per CpG row) and of the
- *           alpha step (per sample); the n_iter2 inner iterations then run on those (dmf_gram_*).  Default when n_u <= 4. */
+ *           alpha step (per sample); the n_iter2 inner iterations then run on those (dmf_gram_*).  Default when n_u <= 4, or n_u <= 8 with K <= 6. */
 enum { DMF_ENGINE_STREAM = 0, DMF_ENGINE_GRAM = 1 };
 
 typedef struct dmf_shape {

@@ -53,19 +53,19 @@ def test_zero_inner_iterations_and_zero_outer(dec):
 
 
 def test_engine_fallback_for_many_unknowns(dec):
-    """n_u > 4 has no Gram-form instantiation: 'auto' falls back to the streaming engine, 'gram' refuses."""
+    """n_u > 8 has no Gram-form instantiation: 'auto' falls back to the streaming engine, 'gram' refuses."""
     import demethify_b200
     from demethify_b200 import _lib
     from oracle import bssmf_numpy as orc
-    X, D, Rk = synth(5, 600, 12, 3, 6)
-    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, 6, seed=1)
-    uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, 6, 2, 5, 1e-12)
-    u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, 6, n_iter1=2, n_iter2=5, tol=1e-12)
+    X, D, Rk = synth(5, 600, 12, 3, 9)
+    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, 9, seed=1)
+    uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, 9, 2, 5, 1e-12)
+    u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, 9, n_iter1=2, n_iter2=5, tol=1e-12)
     assert dec.last_fit_info()["engine"] == "stream" and np.abs(a - ao).max() <= 1e-6
     demethify_b200.set_engine("gram")
     try:
         with pytest.raises(_lib.DmfError):
-            dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, 6, n_iter1=2, n_iter2=5, tol=1e-12)
+            dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, 9, n_iter1=2, n_iter2=5, tol=1e-12)
     finally:
         demethify_b200.set_engine("auto")
 

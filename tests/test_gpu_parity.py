@@ -27,8 +27,8 @@ def dec(request):
     demethify_b200.set_engine("auto")
 
 
-def check_engine(dec, n_u):
-    want = "gram" if (dec.engine_mode == "auto" and n_u <= 4) else "stream"
+def check_engine(dec, n_u, K=5):
+    want = "gram" if (dec.engine_mode == "auto" and (n_u <= 4 or (n_u <= 8 and K <= 6))) else "stream"
     assert dec.last_fit_info()["engine"] == want
 
 
@@ -106,6 +106,9 @@ def test_ragged_shapes_live(dec, live, tag):
     (3000, 256, 6, 2, 3, 5),       # config 5 sample count (one row spans several warps)
     (2500, 40, 12, 3, 3, 6),       # Kt = 15 -> 16-wide register tile
     (1200, 24, 20, 9, 2, 4),       # Kt = 29 -> 32-wide register tile
+    (2000, 256, 6, 7, 3, 6),       # 7 unknown types: Gram engine with one register row per batch, 16-wide alpha panels
+    (1500, 20, 4, 5, 3, 5),        # 5 unknown types, short rows
+    (1800, 64, 0 + 6, 8, 2, 4),    # 8 unknown types
     (999, 7, 1, 1, 4, 7),          # odd everything: rows not 16-byte aligned
     (33, 2, 2, 1, 3, 3),           # fewer rows than one tile
 ])
@@ -116,7 +119,7 @@ def test_partial_reference_vs_oracle(dec, orc, M, N, K, n_u, it1, it2):
     uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, n_u, it1, it2, 1e-9, trace=tr)
     u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, n_u, n_iter1=it1, n_iter2=it2, tol=1e-9)
     info = dec.last_fit_info()
-    check_engine(dec, n_u)
+    check_engine(dec, n_u, K)
     assert info["n_outer"] == tr["n_outer"]
     assert abs(info["cost"] - tr["costs"][-1]) <= 1e-9 * tr["costs"][-1]
     assert np.abs(a - ao).max() <= TOL64 and np.abs(u - uo).max() <= TOL64
