@@ -55,21 +55,42 @@ def _shape_only_init(seed, init_option, M, K, N, n_u, with_zero_guard):
     return u, alpha
 
 
+def percentile_bounds_device(stack, lower_percentile, upper_percentile):
+    """np.percentile(stack, [lo, hi], axis=0) (bootstrap.py:53-54, :77-78; default linear interpolation) on the device:
+    torch.quantile's linear rule is numpy's (virtual index q (B - 1), lerp between the two neighbours)."""
+    q = torch.tensor([lower_percentile / 100.0, upper_percentile / 100.0], dtype=stack.dtype, device=stack.device)
+    flat = stack.reshape(stack.shape[0], -1)
+    out = torch.empty((2, flat.shape[1]), dtype=stack.dtype, device=stack.device)
+    step = max(1, (1 << 24) // max(stack.shape[0], 1))          # torch.quantile caps the size of its input
+    for c0 in range(0, flat.shape[1], step):
+        out[:, c0:c0 + step] = torch.quantile(flat[:, c0:c0 + step], q, dim=0, interpolation="linear")
+    shape = stack.shape[1:]
+    return out[0].reshape(shape).cpu().numpy(), out[1].reshape(shape).cpu().numpy()
+
+
 def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, purity, seed, prob=None,
-                   keep_u=True):
+                   keep_u=True, on_device=False):
     """All resample fits -> (alphas (B, Kt, N), us (B, M, n_u) or None, n_outer list).
-    `purity` is the internal vector (already divided by 100, bootstrap.py:18) or None."""
+    `purity` is the internal vector (already divided by 100, bootstrap.py:18) or None.  With on_device the two stacks
+    stay torch tensors in HBM (the percentiles of bt_ci are then taken there)."""
     meth_f = np.asarray(meth_f)
     M, N = meth_f.shape
     seeds = bootstrap_seeds(seed, n_bootstrap)
     prob = prob or DeviceProblem(meth_f, counts, ref)
     alphas = np.zeros((n_bootstrap, prob.K + n_u, N))
+    if on_device and n_u > 0:
+        need = n_bootstrap * (M * n_u + (prob.K + n_u) * N) * 8
+        on_device = need < device_free_bytes(prob.device) // 3        # else fall back to host stacks
     if n_u == 0:
         for b, s in enumerate(seeds):          # bootstrap.py:40-43: per-sample NNLS on the resampled rows
             idx = resample_indices(s, M)
             alphas[b] = wls_all_samples(prob.gathered(idx), None, None, y_is_dx=True)
         return alphas, None, [0] * n_bootstrap
-    us = np.zeros((n_bootstrap, M, n_u)) if keep_u else None
+    if on_device:
+        alphas = torch.zeros((n_bootstrap, prob.K + n_u, N), dtype=torch.float64, device=prob.device)
+        us = torch.zeros((n_bootstrap, M, n_u), dtype=torch.float64, device=prob.device) if keep_u else None
+    else:
+        us = np.zeros((n_bootstrap, M, n_u)) if keep_u else None
     n_outer = []
     data_dependent_init = init_option in ("uniform", "SVD")
     # fits per wave: bounded by device memory (two u slots + partials per fit)
@@ -124,6 +145,12 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         states = batch.fit(n_iter1, n_iter2, tol)
         for k, st in enumerate(states):
             u_d, a_d = batch.current(k, states)
+            if on_device:
+                alphas[w0 + k] = a_d.to(torch.float64)
+                if keep_u:                       # back to the resampled-position order of the reference (Q6)
+                    us[w0 + k][inv[k]] = u_d.to(torch.float64)
+                n_outer.append(st.n_outer)
+                continue
             alphas[w0 + k] = a_d.to(torch.float64).cpu().numpy()
             if keep_u:                           # back to the resampled-position order of the reference (Q6)
                 back = torch.empty((M, n_u), dtype=torch.float64, device=dev)
@@ -144,9 +171,12 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
     pur = None
     if purity:
         pur = np.array(purity) / 100.0                      # bootstrap.py:18 (NOT 1 - p/100)
-    alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed)
-    lo = np.percentile(alphas, lower_percentile, axis=0)    # (Kt, N); bootstrap.py:53-54
-    hi = np.percentile(alphas, upper_percentile, axis=0)
+    alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True)
+    if isinstance(alphas, torch.Tensor):
+        lo, hi = percentile_bounds_device(alphas, lower_percentile, upper_percentile)
+    else:
+        lo = np.percentile(alphas, lower_percentile, axis=0)    # (Kt, N); bootstrap.py:53-54
+        hi = np.percentile(alphas, upper_percentile, axis=0)
     results = []
     unknown_header = [] if supervised else ["unknown_cell_" + str(i + 1) for i in range(n_u)]
     cell_types = list(header) + unknown_header
@@ -160,8 +190,11 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
     proportions_df.to_csv(outdir + "/confidence_interval_celltypes_proportions.csv", index=True)
     results.append(proportions_df)
     if not supervised:
-        ulo = np.percentile(us, lower_percentile, axis=0)   # (M, n_u); bootstrap.py:77-78
-        uhi = np.percentile(us, upper_percentile, axis=0)
+        if isinstance(us, torch.Tensor):
+            ulo, uhi = percentile_bounds_device(us, lower_percentile, upper_percentile)
+        else:
+            ulo = np.percentile(us, lower_percentile, axis=0)   # (M, n_u); bootstrap.py:77-78
+            uhi = np.percentile(us, upper_percentile, axis=0)
         ref_cols = {unknown_header[k]: [(float(ulo[j, k]), float(uhi[j, k])) for j in range(us.shape[1])] for k in range(n_u)}
         ref_estimate_df = pd.DataFrame(ref_cols)
         ref_estimate_df.to_csv(outdir + "/confidence_interval_methylation_estimate.csv", index=False)

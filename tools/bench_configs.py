@@ -69,6 +69,16 @@ def main():
             t = time.perf_counter() - t0
             out.append({"config": f"c4 bootstrap {B} resamples of 500k x 64, n_u=1, n_iter1={n_iter1}, tol {tol}", "s_total": t, "fits_per_s": B / t,
                         "mean_outer": float(np.mean(n_outer)), "s_per_1000_resamples": 1000 * t / B})
+    if "pub" in which:     # the reference's own published example: 2500 bootstrap resamples of the 350 x 10 fixture (46.47 fits/s)
+        fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "fixture_shipped.npz"), allow_pickle=False))
+        X, D, Rk = fx["X"], fx["D"], fx["Rk"]
+        for rep in range(2):
+            t0 = time.perf_counter()
+            alphas, us, n_outer = bootstrap_fits(2500, 1, X, D, Rk, "uniform_", 10000, 20, 1e-2, None, 1, keep_u=True)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+        out.append({"config": "pub bootstrap 2500 resamples of the shipped 350 x 10 fixture, n_u=1, 10000x20, tol 1e-2 (README / notebook cell 29)",
+                    "s_total": t, "fits_per_s": 2500 / t, "mean_outer": float(np.mean(n_outer)), "published_fits_per_s_authors_laptop": 46.47})
     for o in out:
         print(json.dumps(o), flush=True)
 
