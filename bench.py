@@ -270,7 +270,7 @@ def run_b200(args, rank, world, local_rank):
     st = batch.states()[0]
     assert st.n_outer == (args.warmup + args.steps) * OUTER_PER_STEP and np.isfinite(st.cost)
     if engine == "gram":
-        kern = {"u_inner_kernel": seg[0], "gram_panel_kernel": seg[1], "alpha_inner_kernel": seg[2], "rowgram_kernel": seg[3]}
+        kern = {"u_inner_kernel": seg[0], "gram_panel_kernel": seg[1], "alpha_inner_kernel": seg[2], "rowgram4_kernel": seg[3]}
     else:
         kern = {"u_pass_kernel": seg[0] / N_ITER2, "alpha_pass_kernel": seg[1] / N_ITER2, "cost_kernel": seg[3]}
 
@@ -381,7 +381,7 @@ def run_b200(args, rank, world, local_rank):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         if engine == "gram":
-            passes = {"rowgram_kernel": (kern["rowgram_kernel"], bytes_rowgram), "gram_panel_kernel": (kern["gram_panel_kernel"], bytes_panel)}
+            passes = {"rowgram4_kernel": (kern["rowgram4_kernel"], bytes_rowgram), "gram_panel_kernel": (kern["gram_panel_kernel"], bytes_panel)}
         else:
             passes = {"u_pass_kernel": (kern["u_pass_kernel"], bytes_u), "alpha_pass_kernel": (kern["alpha_pass_kernel"], bytes_a)}
         dom = max(passes, key=lambda k: passes[k][0])
@@ -393,7 +393,7 @@ def run_b200(args, rank, world, local_rank):
             tj = json.load(open(tpath))
             same = tj["shape"] == {"M_cpg": M, "N_samples": N_S, "K_known": K_KNOWN, "n_unknown": N_UNK,
                                    "dtype": "f64" if args.precision == "fp64" else "f32", "weights_storage": "u16" if sW == 2 else "float"}
-            traffic = tj["kernels"].get({"rowgram_kernel": "rowgram4_kernel"}.get(dom, dom)) if same else None
+            traffic = tj["kernels"].get(dom) if same else None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
                 "kernels_ms_per_launch": kern,
