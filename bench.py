@@ -306,6 +306,7 @@ def run_b200(args, rank, world, local_rank):
         m_loc = M // world
         sprob = prob.row_slice(0, m_loc)
         be = GpuShardBackend(sprob, None, None, N_UNK, hU[:m_loc], hA)
+        use_peer = os.environ.get("DMF_BENCH_PEER", "0") == "1" and be.enable_peer_exchange(None)   # in-kernel NVLink all-reduce instead of NCCL
         rs_fit = RowShardedFit(be)
         rs_fit.init()
         be.reserve((args.steps + 1) * OUTER_PER_STEP * N_ITER2 + 4 * N_ITER2)
@@ -336,6 +337,7 @@ def run_b200(args, rank, world, local_rank):
         row_sharded = {"value": 2 * N_ITER2 * OUTER_PER_STEP * args.steps / (float(rs_ms[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
                        "rows_per_gpu": m_loc, "ms_per_outer_iteration": float(rs_ms[0]) / (args.steps * OUTER_PER_STEP),
                        "collectives_per_outer_iteration": 2, "launch": "one CUDA graph per outer iteration (kernels + NCCL all-reduces)" if use_graph else "eager (host-driven launches)",
+                       "allreduce": "in-kernel over NVLink peer memory (dmf_gram_exchange)" if use_peer else "NCCL",
                        "allreduce_doubles_per_outer_iteration": int(Kt * (Kt + 1) * N_S + 16),
                        "note": "one fit, rows sharded over the ranks; value is the single job's update iterations/s"}
         step_fn = None

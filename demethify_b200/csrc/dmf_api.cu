@@ -56,6 +56,12 @@ struct dmf_batch_s {
     int n_parts_u, n_groups_u;
     unsigned smem_rg, smem_panel;
     int n_active;                   // fits_dev holds the descriptors of the first n_active still-running fits (compacted at every poll)
+    // peer exchange (row-sharded runs): symmetric buffers of all ranks, see peer_allreduce_kernel
+    double** peers_dev;             // device array [world]
+    unsigned* xchg_ticket;          // device
+    int peer_rank, peer_world;
+    long long peer_slot_stride, peer_flag_off;
+    unsigned xchg_epoch;
     int multmode;                   // fits are bootstrap resamples in multiplicity form
     int sharded;                    // CpG rows sharded over GPUs: kernels publish partial sums, finalize runs on all-reduced sums
     std::vector<FitDev> fits_host;
@@ -556,6 +562,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->mom_cap = 0;
     b->t_hi = 0;
     b->sharded = 0;
+    b->peers_dev = nullptr; b->xchg_ticket = nullptr; b->peer_rank = 0; b->peer_world = 0; b->xchg_epoch = 0;
     b->n_active = s.n_fits;
     b->fits_host = host;
     b->stats_local = p.gram_ok ? reinterpret_cast<double*>(base + p.off_stats) : nullptr;
@@ -637,6 +644,8 @@ int dmf_batch_destroy(dmf_batch_t b) {
     if (!b) return DMF_OK;
     if (b->pinned) cudaFreeHost(b->pinned);
     if (b->mom_dev) cudaFree(b->mom_dev);
+    if (b->peers_dev) cudaFree(b->peers_dev);
+    if (b->xchg_ticket) cudaFree(b->xchg_ticket);
     delete b;
     return DMF_OK;
 }
@@ -771,6 +780,54 @@ int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* str
     a.flags = (initial ? kFlagInitial : 0) | (b->shape.dtype == DMF_F32 ? kFlagF32 : 0);
     a.tol = tol;
     finalize_cost_kernel<<<(b->n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    return DMF_OK;
+}
+
+int dmf_batch_peer_bytes(dmf_batch_t b, int32_t world, size_t* bytes) {
+    if (!b || !bytes || world < 1) return fail(DMF_E_ARG, "bad argument");
+    if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    const size_t slot = b->stats_doubles * b->shape.n_fits;
+    *bytes = align_up(2 * (size_t)world * slot * 8, 256) + align_up(2 * (size_t)world * 4, 256);
+    return DMF_OK;
+}
+int dmf_batch_set_peers(dmf_batch_t b, int32_t rank, int32_t world, const void* const* peer_bases, size_t bytes_per_peer, void* stream) {
+    if (!b || !peer_bases || world < 1 || rank < 0 || rank >= world || world > kThreads) return fail(DMF_E_ARG, "bad argument");
+    if (!b->sharded) return fail(DMF_E_STATE, "peer exchange belongs to row-sharded batches (dmf_batch_set_sharded first)");
+    size_t need = 0;
+    int rc = dmf_batch_peer_bytes(b, world, &need);
+    if (rc) return rc;
+    if (bytes_per_peer < need) return fail(DMF_E_ARG, "symmetric buffers too small (dmf_batch_peer_bytes)");
+    for (int r = 0; r < world; ++r)
+        if (!peer_bases[r] || (reinterpret_cast<uintptr_t>(peer_bases[r]) & 15)) return fail(DMF_E_ARG, "peer buffer pointers must be non-NULL and 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!b->peers_dev) CUDA_TRY(cudaMalloc(&b->peers_dev, sizeof(double*) * kThreads));
+    if (!b->xchg_ticket) CUDA_TRY(cudaMalloc(&b->xchg_ticket, 256));
+    CUDA_TRY(cudaMemcpyAsync(b->peers_dev, peer_bases, sizeof(double*) * world, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b->xchg_ticket, 0, 256, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->peer_rank = rank; b->peer_world = world;
+    b->peer_slot_stride = (long long)(b->stats_doubles * b->shape.n_fits);
+    b->peer_flag_off = (long long)align_up(2 * (size_t)world * b->peer_slot_stride * 8, 256);
+    b->xchg_epoch = 0;      // the caller zeroes the symmetric buffers (flags) before the first exchange
+    return DMF_OK;
+}
+int dmf_gram_exchange(dmf_batch_t b, int32_t which, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->peers_dev || b->peer_world < 1) return fail(DMF_E_STATE, "dmf_batch_set_peers first");
+    if (which < 0 || which > 2) return fail(DMF_E_ARG, "which must be 0 (blocks), 1 (scalars) or 2 (scalars at set-up)");
+    XchgArgs a;
+    a.peers = b->peers_dev;
+    a.local = b->stats_local; a.global = b->stats_global;
+    a.ticket = b->xchg_ticket;
+    a.per_fit = (long long)b->stats_doubles; a.slot_stride = b->peer_slot_stride; a.flag_off = b->peer_flag_off;
+    a.scal_off = (long long)b->stats_scal;
+    a.n_fits = b->shape.n_fits; a.rank = b->peer_rank; a.world = b->peer_world; a.which = which;
+    a.epoch = ++b->xchg_epoch;
+    const long long n = which == 0 ? (long long)a.n_fits * a.per_fit : (long long)a.n_fits * 8;
+    const int ctas = (int)std::max<long long>(1, std::min<long long>(32, (n + kThreads * 4 - 1) / (kThreads * 4)));
+    peer_allreduce_kernel<<<ctas, kThreads, 0, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     b->launches++;
     return DMF_OK;

@@ -1234,4 +1234,79 @@ static __global__ void finalize_cost_kernel(const PassArgs a) {
     else cost_state_update<false>(a.g, f, st, f.rscal, Acur, f32, a.tol, 0.0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CpG rows sharded over GPUs: all-reduce of the statistics block over NVLink PEER MEMORY, in one kernel and without NCCL.
+// Every rank owns a symmetric buffer  data[2 parities][world slots][n] + flags[2][world]  that all ranks of the box can address
+// (torch symmetric memory / cuMem peer mappings).  One launch per rank:
+//   1. push   : the rank's local sums go into slot [rank] of EVERY rank's buffer (plain st.global over NVLink, 16-byte vectors)
+//   2. signal : after a system-scope fence the last CTA stores the epoch into flag [rank] of every rank
+//   3. wait   : every CTA spins (ld.acquire.sys) until all `world` flags of ITS OWN buffer show the epoch
+//   4. sum    : slots are added in rank order (the same order on every rank -> bit-identical results everywhere) into the
+//               `global` statistics block that alpha_inner_kernel / finalize_cost_kernel read
+// Two parities alternate with the epoch: a rank can only be one exchange ahead of a peer (it needs the peer's flag of epoch e
+// before it can push e + 1), so a slot is never overwritten while its owner still sums it.
+struct XchgArgs {
+    double* const* peers;     // device array [world]: base of rank r's symmetric buffer as mapped in this process
+    const double* local;      // this rank's statistics blocks (n_fits x per_fit doubles)
+    double* global;           // all-reduced copies, same layout
+    unsigned* ticket;         // grid-completion ticket (zeroed at set-up, re-armed by the last CTA)
+    long long per_fit;        // doubles per fit in local / global
+    long long slot_stride;    // doubles per slot of the symmetric buffer (>= n_fits * per_fit)
+    long long flag_off;       // byte offset of the flags inside a symmetric buffer
+    long long scal_off;       // offset of the 8 scalars inside a fit's block
+    int n_fits, rank, world;
+    int which;                // 0: whole blocks; 1: the 8 scalars of every fit (sum); 2: the same at set-up (slot 3 = max d_x: max)
+    unsigned epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+static __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(const XchgArgs a) {
+    __shared__ int s_last;
+    const int parity = a.epoch & 1u;
+    const long long n = a.which == 0 ? (long long)a.n_fits * a.per_fit : (long long)a.n_fits * 8;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    auto src_index = [&](long long e) { return a.which == 0 ? e : (e >> 3) * a.per_fit + a.scal_off + (e & 7); };
+    // 1. push my sums into slot [rank] of every rank's buffer
+    for (int p = 0; p < a.world; ++p) {
+        double* dst = a.peers[(p + a.rank) % a.world] + ((long long)parity * a.world + a.rank) * a.slot_stride;     // staggered peer order
+        for (long long e = tid; e < n; e += nthr) dst[e] = a.local[src_index(e)];
+    }
+    // 2. signal
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < a.world) {
+            unsigned* flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.peers[threadIdx.x]) + a.flag_off);
+            st_release_sys(flags + parity * a.world + a.rank, a.epoch);
+        }
+        if (threadIdx.x == 0) *a.ticket = 0u;
+    }
+    // 3. wait for every rank's flag in MY buffer
+    if (threadIdx.x < a.world) {
+        const unsigned* flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(a.peers[a.rank]) + a.flag_off);
+        while (ld_acquire_sys(flags + parity * a.world + threadIdx.x) != a.epoch) { __nanosleep(64); }
+    }
+    __syncthreads();
+    // 4. rank-ordered sum (L1 bypassed: the slots were written by peers)
+    const double* mine = a.peers[a.rank] + (long long)parity * a.world * a.slot_stride;
+    for (long long e = tid; e < n; e += nthr) {
+        double s = __ldcg(mine + e);
+        const bool is_max = a.which == 2 && (e & 7) == 3;
+        for (int r = 1; r < a.world; ++r) {
+            const double v = __ldcg(mine + (long long)r * a.slot_stride + e);
+            s = is_max ? fmax(s, v) : s + v;
+        }
+        a.global[src_index(e)] = s;
+    }
+}
+
 }  // namespace dmf

@@ -21,7 +21,9 @@ import torch.distributed as dist
 from . import _lib
 from .engine import DeviceProblem, FitBatch, _stream_ptr
 
-__all__ = ["row_range", "GpuShardBackend", "RowShardedFit", "mdwbssmf_deconv_sharded"]
+__all__ = ["row_range", "GpuShardBackend", "RowShardedFit", "mdwbssmf_deconv_sharded", "last_info"]
+
+last_info = {}      # of the most recent mdwbssmf_deconv_sharded call: {"peer_exchange": bool, "peer_error": str | None, "collectives": int}
 
 
 def row_range(M, rank, world):
@@ -52,6 +54,36 @@ class GpuShardBackend:
         self.has_known = b.K > 0
         self.device = b.device
         self.supports_graphs = True
+        self.peer = None
+
+    def enable_peer_exchange(self, group=None):
+        """All-reduce over NVLink peer memory inside one kernel of the library (dmf_gram_exchange) instead of NCCL: allocates a
+        symmetric buffer that every rank of `group` maps (torch symmetric memory) and hands the peer pointers to the library.
+        Returns False (and leaves the NCCL path in place) when symmetric memory is not available."""
+        if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            lib, b = _lib.lib(), self.batch
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            nbytes = C.c_size_t()
+            _lib.check(lib.dmf_batch_peer_bytes(b.b, world, C.byref(nbytes)))
+            buf = symm_mem.empty((nbytes.value + 7) // 8, dtype=torch.float64, device=self.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            torch.cuda.synchronize()
+            dist.barrier(group)                      # every rank's buffer (flags) is zero before anybody pushes
+            _lib.check(lib.dmf_batch_set_peers(b.b, rank, world, ptrs, nbytes.value, _stream_ptr()))
+            self.peer = (buf, hdl)
+            return True
+        except Exception as e:                       # no symmetric memory on this system: keep NCCL
+            self.peer_error = repr(e)
+            self.peer = None
+            return False
+
+    def exchange(self, which):
+        _lib.check(_lib.lib().dmf_gram_exchange(self.batch.b, int(which), _stream_ptr()))
 
     def reserve(self, n_inner_total):
         """Make the following steps allocation- and sync-free (CUDA-graph capture)."""
@@ -109,6 +141,10 @@ class RowShardedFit:
         self.collectives += 1
 
     def _reduce_scal(self, with_max):
+        if getattr(self.be, "peer", None) is not None:          # one kernel: push to the peers, wait, rank-ordered sum (max for max d_x)
+            self.be.exchange(2 if with_max else 1)
+            self.collectives += 1
+            return
         loc, glo, so = self.be.stats_local(), self.be.stats_global(), self.so
         sc = loc[:, so:so + 8].contiguous()
         if with_max:
@@ -133,9 +169,13 @@ class RowShardedFit:
         if n_iter2 > 0:
             be.u_inner(n_iter2)                       # row-local
             be.panels(False)
-            glo = be.stats_global()
-            glo.copy_(be.stats_local())
-            self._allreduce(glo)                      # G_j, bx_j, ||u||^2 over all rows
+            if getattr(be, "peer", None) is not None:
+                be.exchange(0)                        # G_j, bx_j, ||u||^2 over all rows, over NVLink peer memory
+                self.collectives += 1
+            else:
+                glo = be.stats_global()
+                glo.copy_(be.stats_local())
+                self._allreduce(glo)                  # the same through NCCL
             be.alpha_inner(n_iter2)                   # identical on every rank
         be.rowgram(False, tol)
         self._reduce_scal(with_max=False)
@@ -184,8 +224,14 @@ def mdwbssmf_deconv_sharded(u_local, alpha, X_local, d_local, R_local, n_u, n_it
     ITS rows of u, X, d_x, R_trunc (see `row_range`) and the full alpha; returns (u_local, alpha, n_outer, cost)."""
     mode = _lib.DMF_MODE_PURITY if purity is not None else (_lib.DMF_MODE_PARTIAL if R_local is not None else _lib.DMF_MODE_UNSUPERVISED)
     be = GpuShardBackend(X_local, d_local, R_local, n_u, np.asarray(u_local).reshape(-1, n_u), np.asarray(alpha), mode=mode, purity=purity)
+    import os
+    if os.environ.get("DMF_PEER_XCHG", "0") == "1":
+        be.enable_peer_exchange(group)
+    fit = RowShardedFit(be, group)
     try:
-        (u, a, n_outer, cost), = RowShardedFit(be, group).fit(n_iter1, n_iter2, tol)
+        (u, a, n_outer, cost), = fit.fit(n_iter1, n_iter2, tol)
     finally:
+        last_info.update(peer_exchange=be.peer is not None, peer_error=getattr(be, "peer_error", None), collectives=fit.collectives)
+        torch.cuda.synchronize()
         be.close()
     return u, a, n_outer, cost

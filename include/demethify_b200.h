@@ -160,6 +160,15 @@ int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream);
 int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream);
 int dmf_batch_stats_buffers(dmf_batch_t b, void** local_dev, void** global_dev, int64_t* doubles_per_fit, int64_t* scal_offset);
 int dmf_gram_finalize_cost(dmf_batch_t b, int32_t initial, double tol, void* stream);
+/* Row-sharded runs, all-reduce over NVLink PEER MEMORY instead of NCCL: every rank provides a zero-initialised symmetric buffer of
+ * dmf_batch_peer_bytes() bytes that all ranks of the box have mapped (peer_bases[r] = rank r's buffer as addressable from THIS
+ * process, e.g. torch symmetric memory's buffer_ptrs).  dmf_gram_exchange is then ONE kernel per rank that pushes this rank's sums
+ * into every rank's buffer, signals, waits for all ranks and adds the slots in rank order into the `global` statistics block
+ * (which: 0 whole blocks before dmf_gram_alpha_inner; 1 the cost scalars before dmf_gram_finalize_cost; 2 the same at set-up, where
+ * max d_x is max-reduced).  Every rank must issue the same sequence of exchanges. */
+int dmf_batch_peer_bytes(dmf_batch_t b, int32_t world, size_t* bytes);
+int dmf_batch_set_peers(dmf_batch_t b, int32_t rank, int32_t world, const void* const* peer_bases, size_t bytes_per_peer, void* stream);
+int dmf_gram_exchange(dmf_batch_t b, int32_t which, void* stream);
 /* The extrapolation weights of deconvolution.py:83-85 are data independent; the library keeps them in a device table that
  * grows on demand (growth allocates and synchronises).  Reserving n_inner_total inner iterations up front makes every later
  * dmf_gram_* call allocation- and sync-free, so that an outer iteration can be captured into a CUDA graph. */

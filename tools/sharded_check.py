@@ -20,6 +20,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as g
     g.build()
+    from demethify_b200 import sharded
     from demethify_b200.sharded import mdwbssmf_deconv_sharded, row_range
     from oracle import bssmf_numpy as orc
     rs = np.random.RandomState(5)
@@ -45,8 +46,8 @@ def main():
             da, du = np.abs(al - ao).max(), np.abs(ufull - uo).max()
             good = same_alpha and all(p[3] == tr["n_outer"] for p in parts) and da <= 1e-6 and du <= 1e-6
             ok &= good
-            print(f"sharded_check world={world} it1={it1}: n_outer={n_outer} oracle={tr['n_outer']} max|d alpha|={da:.2e} max|d u|={du:.2e} "
-                  f"alpha replicated={same_alpha} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"sharded_check world={world} peer_xchg={os.environ.get('DMF_PEER_XCHG', '0')} it1={it1}: n_outer={n_outer} oracle={tr['n_outer']} max|d alpha|={da:.2e} max|d u|={du:.2e} "
+                  f"alpha replicated={same_alpha} peer={sharded.last_info} -> {'OK' if good else 'FAIL'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
