@@ -76,11 +76,15 @@ class GpuShardBackend:
             dist.barrier(group)                      # every rank's buffer (flags) is zero before anybody pushes
             _lib.check(lib.dmf_batch_set_peers(b.b, rank, world, ptrs, nbytes.value, _stream_ptr()))
             self.peer = (buf, hdl)
-            return True
         except Exception as e:                       # no symmetric memory on this system: keep NCCL
             self.peer_error = repr(e)
             self.peer = None
-            return False
+        # the ranks must take the same path: one rank on NCCL while the others wait in the exchange kernel would hang the job
+        ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.peer = None
+        return self.peer is not None
 
     def exchange(self, which):
         _lib.check(_lib.lib().dmf_gram_exchange(self.batch.b, int(which), _stream_ptr()))
