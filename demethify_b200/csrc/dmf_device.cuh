@@ -161,13 +161,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// weights: stored as T or as uint16 coverage counts
-template <typename T, typename WT>
-__device__ __forceinline__ T wload(const void* base, long long idx) {
-    return (T) reinterpret_cast<const WT*>(base)[idx];
-}
-
-// ------------------------------------------------------------------------------------------------
 // Tile pipeline.  One stage holds `tile_rows` rows of X, D, Rk, U(cur) and optionally U(prev).
 
 // Executed by the whole producer warp.  Fills stage `sbase` with rows [r0, r0+nrows) of every source
@@ -221,23 +214,6 @@ __device__ __forceinline__ void produce_tile(const TileSrc* src, int nsrc, const
             }
         }
     }
-}
-
-// Full, contiguous tile: every source is ONE bulk copy whose size was fixed on the host; only lane 0 works.
-__device__ __forceinline__ void produce_full_tile(const Geom& g, const TileSrc* src, int nsrc, long long r0, char* sbase,
-                                                  uint32_t full_bar, int lane) {
-    if (lane == 0) {
-        unsigned tx = 0;
-#pragma unroll
-        for (int s = 0; s < kMaxSrc; ++s)
-            if (s < nsrc && src[s].base != nullptr) tx += g.tile_tx[s];
-        mbar_arrive_expect_tx(full_bar, tx);
-        const uint32_t dst = smem_u32(sbase);
-#pragma unroll
-        for (int s = 0; s < kMaxSrc; ++s)
-            if (s < nsrc && src[s].base != nullptr) bulk_g2s(dst + src[s].off, src[s].base + r0 * src[s].pitch, g.tile_tx[s], full_bar);
-    }
-    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------

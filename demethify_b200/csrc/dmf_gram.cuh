@@ -14,6 +14,10 @@
 //   gram_panel_kernel  ONE streaming pass: the blocks of G_j, bx_j that involve u (the known x known block and
 //                      the known part of bx are invariant and computed once at set-up)
 //   alpha_inner_kernel n_iter2 update_alpha (with simplex projection) or Frank-Wolfe iterations per sample on (G_j, bx_j)
+// plus, for bootstrap resamples in multiplicity form (shared source matrices, per-position u through a CSR):
+//   u_inner_mult_kernel / usum_kernel / cost_cross_kernel and the MULT variant of gram_panel_kernel,
+// and, for CpG rows sharded over GPUs: finalize_cost_kernel (set-up / termination on all-reduced sums) and
+//   peer_allreduce_kernel (the all-reduce itself, over NVLink peer memory).
 //
 // An outer iteration is 2 streaming passes + 2 small kernels instead of 2 n_iter2 + 1 streaming passes.  The sums are
 // re-associated with respect to the reference (fp64, fixed order), which moves alpha by ~1e-15; the termination test

@@ -6,11 +6,11 @@
 //   alpha_pass_kernel: one inner iteration of update_alpha            deconvolution.py:94-101 + projection :21-37
 //                      or one Frank-Wolfe iteration                   deconvolution.py:285-299
 //
-// Layout: a producer warp streams row tiles of X, D, R_trunc, u (and u_prev) into a 4-stage shared-memory
-// ring with 1-D bulk copies (TMA engine) signalled through mbarriers; 256 consumer threads are arranged
-// as (row group g, column thread tc): thread tc owns C adjacent sample columns (C = 2: every access is a
-// two-element vector load), keeps its alpha columns in registers and walks the rows of the tile.  All row
-// pitches are even and zero padded (ABI contract), so the inner loops are branch free.
+// Layout: row tiles of X, D, R_trunc, u (and u_prev) are streamed into a shared-memory ring (3 .. 5 stages) with
+// 1-D bulk copies (TMA engine, SASS UBLKCP) signalled through mbarriers; the producer duty rotates over the 8 warps,
+// every warp computes.  The 256 threads are arranged as (row group g, column thread tc): thread tc owns C adjacent
+// sample columns (C = 2: every access is a two-element vector load), keeps its alpha columns in registers and walks
+// the rows of the tile.  All row pitches are even and zero padded (ABI contract), so the inner loops are branch free.
 // Row-wise sums (U gradient) use a transposed warp-shuffle butterfly, column-wise sums (alpha gradient)
 // stay in registers across the whole CTA lifetime; cross-CTA sums go through the deterministic two-level
 // reduction of dmf_device.cuh and the LAST CTA applies the step (clip / simplex projection / Frank-Wolfe
