@@ -12,13 +12,39 @@ sklearn.utils.resample == RandomState(seed).randint.
 import numpy as np
 import pandas as pd
 import torch
+import torch.distributed as dist
 
 from . import _lib
 from .deconvolution import init_BSSMF_md, init_BSSMF_md_p
 from .engine import DeviceProblem, FitBatch, device_free_bytes
 from .init_func import wls_all_samples
 
-__all__ = ["bt_ci", "bootstrap_seeds", "resample_indices", "bootstrap_fits"]
+__all__ = ["bt_ci", "bootstrap_seeds", "resample_indices", "bootstrap_fits", "shard_of", "merge_resample_stacks",
+           "percentile_bounds_device"]
+
+
+def _world(group):
+    return (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def shard_of(items, rank, world):
+    """Fit sharding: resample b runs on rank b mod world — the resamples are independent (bootstrap.py:26)."""
+    return list(items[rank::world])
+
+
+def merge_resample_stacks(local, n_total, group=None):
+    """All-gather the per-rank stacks (B_r, ...) of a fit-sharded bootstrap into the full (n_total, ...) stack on every rank.
+    The order along the fit axis is rank-major; the percentiles of bt_ci do not depend on it."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    counts = [len(range(r, n_total, world)) for r in range(world)]
+    bmax = max(counts)
+    pad = torch.zeros((bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([out[r][:counts[r]] for r in range(world)], dim=0)
 
 
 def bootstrap_seeds(seed, n_bootstrap):
@@ -69,13 +95,15 @@ def percentile_bounds_device(stack, lower_percentile, upper_percentile):
 
 
 def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, purity, seed, prob=None,
-                   keep_u=True, on_device=False):
+                   keep_u=True, on_device=False, seeds=None):
     """All resample fits -> (alphas (B, Kt, N), us (B, M, n_u) or None, n_outer list).
     `purity` is the internal vector (already divided by 100, bootstrap.py:18) or None.  With on_device the two stacks
-    stay torch tensors in HBM (the percentiles of bt_ci are then taken there)."""
+    stay torch tensors in HBM (the percentiles of bt_ci are then taken there).  `seeds` restricts the run to a
+    sub-list of the reference's seed sequence (one rank's share of a fit-sharded bootstrap)."""
     meth_f = np.asarray(meth_f)
     M, N = meth_f.shape
-    seeds = bootstrap_seeds(seed, n_bootstrap)
+    seeds = bootstrap_seeds(seed, n_bootstrap) if seeds is None else list(seeds)
+    n_bootstrap = len(seeds)
     prob = prob or DeviceProblem(meth_f, counts, ref)
     alphas = np.zeros((n_bootstrap, prob.K + n_u, N))
     if on_device and n_u > 0:
@@ -171,7 +199,21 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
     pur = None
     if purity:
         pur = np.array(purity) / 100.0                      # bootstrap.py:18 (NOT 1 - p/100)
-    alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True)
+    rank, world = _world(None)
+    if world > 1:
+        # fit sharding over the GPUs of the job (one process per GPU; every rank calls bt_ci): rank r fits resamples r, r + world, ...,
+        # the stacks are all-gathered over NCCL, every rank takes the percentiles, rank 0 writes the files
+        mine = shard_of(bootstrap_seeds(seed, n_bootstrap), rank, world)
+        alphas, us, _ = bootstrap_fits(len(mine), n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True,
+                                       seeds=mine)
+        if not isinstance(alphas, torch.Tensor):        # supervised path / host stacks: move to the device for the all-gather
+            from .engine import current_device
+            alphas = torch.from_numpy(np.ascontiguousarray(alphas)).to(current_device())
+            us = torch.from_numpy(np.ascontiguousarray(us)).to(current_device()) if us is not None else None
+        alphas = merge_resample_stacks(alphas, n_bootstrap)
+        us = merge_resample_stacks(us, n_bootstrap) if us is not None else None
+    else:
+        alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True)
     if isinstance(alphas, torch.Tensor):
         lo, hi = percentile_bounds_device(alphas, lower_percentile, upper_percentile)
     else:
@@ -187,7 +229,8 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
     proportions_df = pd.DataFrame(cols, index=cell_types)
     proportions_df.columns = samples
     proportions_df.index.name = "Cell Type"
-    proportions_df.to_csv(outdir + "/confidence_interval_celltypes_proportions.csv", index=True)
+    if rank == 0:
+        proportions_df.to_csv(outdir + "/confidence_interval_celltypes_proportions.csv", index=True)
     results.append(proportions_df)
     if not supervised:
         if isinstance(us, torch.Tensor):
@@ -197,6 +240,7 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
             uhi = np.percentile(us, upper_percentile, axis=0)
         ref_cols = {unknown_header[k]: [(float(ulo[j, k]), float(uhi[j, k])) for j in range(us.shape[1])] for k in range(n_u)}
         ref_estimate_df = pd.DataFrame(ref_cols)
-        ref_estimate_df.to_csv(outdir + "/confidence_interval_methylation_estimate.csv", index=False)
+        if rank == 0:
+            ref_estimate_df.to_csv(outdir + "/confidence_interval_methylation_estimate.csv", index=False)
         results.append(ref_estimate_df)
     return results

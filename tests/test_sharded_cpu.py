@@ -142,3 +142,34 @@ def test_percentile_bounds_match_numpy():
             lo, hi = percentile_bounds_device(torch.from_numpy(st), lo_p, hi_p)
             assert np.abs(lo - np.percentile(st, lo_p, axis=0)).max() <= 1e-15
             assert np.abs(hi - np.percentile(st, hi_p, axis=0)).max() <= 1e-15
+
+
+def _merge_worker(rank, world, port, n_total, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from demethify_b200.bootstrap import bootstrap_seeds, merge_resample_stacks, shard_of
+        seeds = bootstrap_seeds(1, n_total)
+        mine = shard_of(seeds, rank, world)
+        # a fake "fit": the stack entry of resample seed s is a deterministic function of s
+        local = torch.tensor([[s * 1.0, s * 0.5 + 1] for s in mine], dtype=torch.float64).reshape(len(mine), 2)
+        full = merge_resample_stacks(local, n_total)
+        np.save(os.path.join(out_dir, f"merge{rank}.npy"), full.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total,world", [(7, 2), (1, 2), (8, 3)])
+def test_fit_sharded_bootstrap_merge_gloo(tmp_path, n_total, world):
+    """Fit sharding of the bootstrap (bootstrap.py:26): rank r fits resamples r, r + world, ...; the all-gathered stack holds every
+    resample exactly once on every rank (uneven shares and empty shares included), so the percentiles equal the unsharded ones."""
+    from demethify_b200.bootstrap import bootstrap_seeds, percentile_bounds_device
+    mp.spawn(_merge_worker, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
+    seeds = bootstrap_seeds(1, n_total)
+    want = np.array([[s * 1.0, s * 0.5 + 1] for s in seeds])
+    got = [np.load(tmp_path / f"merge{r}.npy") for r in range(world)]
+    for g in got:
+        assert g.shape == want.shape and np.array_equal(np.sort(g, axis=0), np.sort(want, axis=0))
+        lo, hi = percentile_bounds_device(torch.from_numpy(g), 5.0, 95.0)
+        assert np.allclose(lo, np.percentile(want, 5.0, axis=0), atol=1e-15) and np.allclose(hi, np.percentile(want, 95.0, axis=0), atol=1e-15)
+    assert all(np.array_equal(got[0], g) for g in got)
