@@ -5,6 +5,7 @@ run_deconvolution / evaluate_best_ic / bicross_validation keep the reference sig
 reference's formulas on the host.
 """
 import numpy as np
+import torch.distributed as dist
 import tqdm
 
 from . import _lib
@@ -12,7 +13,37 @@ from .deconvolution import init_BSSMF_md, mdwbssmf_deconv, unsupervised_deconv, 
 from .engine import DeviceProblem, FitBatch
 
 __all__ = ["compute_bic", "compute_aic", "compute_consensus_matrix", "compute_ccc", "run_deconvolution", "bicross_validation",
-           "evaluate_best_ic"]
+           "evaluate_best_ic", "merge_sweep"]
+
+
+def _world(group=None):
+    return (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def merge_sweep(local_results, local_payload, n_values, group=None):
+    """Fit sharding of the n_u sweep (ic.py:192-216; every n_u re-seeds and is independent): rank r evaluated the positions
+    r, r + world, ... of the sweep.  `local_results` maps position -> criterion, `local_payload` position -> (u, alpha) of this
+    rank's candidates for the overall best.  Returns (criteria in sweep order, best position, (u, alpha) of the best) on every
+    rank; the best is the reference's: the FIRST position whose criterion is strictly below everything before it."""
+    rank, world = _world(group)
+    gathered = [local_results]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local_results, group=group)
+    merged = {}
+    for g in gathered:
+        merged.update(g)
+    values = [merged[p] for p in range(n_values)]
+    best, best_pos = float("inf"), None
+    for p, v in enumerate(values):
+        if v < best:
+            best, best_pos = v, p
+    payload = local_payload.get(best_pos)
+    if world > 1 and best_pos is not None:
+        box = [payload if best_pos % world == rank else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, best_pos % world) if group is not None else best_pos % world, group=group)
+        payload = box[0]
+    return values, best_pos, payload
 
 
 def compute_bic(cost, n_u, n_cpg, n_ct, n_samples):
@@ -115,7 +146,12 @@ def evaluate_best_ic(meth_f, ref, counts, init_option, ic, seed, iter1, iter2, t
         raise TypeError("run_deconvolution() missing 3 required positional arguments: 'iter1', 'iter2', and 'tol'")
     if isinstance(seed, (list, tuple)) and ic == "CCC":
         raise TypeError("can only concatenate list (not \"int\") to list")      # ic.py:196 with `--seed S` (Q1)
-    for n_u in tqdm.tqdm(n_u_values):
+    n_u_values = list(n_u_values)
+    rank, world = _world()
+    local_results, local_payload, local_best = {}, {}, float("inf")
+    positions = list(range(len(n_u_values)))[rank::world]          # under torch.distributed the sweep is sharded over the ranks
+    for pos in tqdm.tqdm(positions, disable=rank != 0):
+        n_u = n_u_values[pos]
         if ic == "CCC":
             if ref is not None:
                 prob = DeviceProblem(meth_f, counts, ref)
@@ -136,7 +172,11 @@ def evaluate_best_ic(meth_f, ref, counts, init_option, ic, seed, iter1, iter2, t
             u, R, alpha = run_deconvolution(meth_f, counts, ref, n_u, init_option, seed, iter1, iter2, tol)
             cost = cost_f_w(meth_f, R, alpha, counts)
             ic_result = compute_bic(cost, n_u, n_cpg, n_ct, n_samples) if ic == "BIC" else compute_aic(cost, n_u, n_cpg, n_ct, n_samples)
-        list_result.append(ic_result)
-        if ic_result < best_ic:
-            best_ic, best_n_u, best_alpha_overall, best_u_overall = ic_result, n_u, alpha, u
+        local_results[pos] = ic_result
+        if ic_result < local_best:                 # the overall best (first position of the minimum) is the LAST strict improvement
+            local_best = ic_result                 # inside its rank's share: keep only that one
+            local_payload = {pos: (u, alpha)}
+    list_result, best_pos, payload = merge_sweep(local_results, local_payload, len(n_u_values))
+    if best_pos is not None:
+        best_n_u, (best_u_overall, best_alpha_overall) = n_u_values[best_pos], payload
     return best_u_overall, best_alpha_overall, best_n_u, list_result

@@ -173,3 +173,31 @@ def test_fit_sharded_bootstrap_merge_gloo(tmp_path, n_total, world):
         lo, hi = percentile_bounds_device(torch.from_numpy(g), 5.0, 95.0)
         assert np.allclose(lo, np.percentile(want, 5.0, axis=0), atol=1e-15) and np.allclose(hi, np.percentile(want, 95.0, axis=0), atol=1e-15)
     assert all(np.array_equal(got[0], g) for g in got)
+
+
+def _sweep_worker(rank, world, port, values, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from demethify_b200.ic import merge_sweep
+        local_results, payload, best = {}, {}, float("inf")
+        for pos in list(range(len(values)))[rank::world]:
+            local_results[pos] = values[pos]
+            if values[pos] < best:
+                best, payload = values[pos], {pos: (np.full(3, pos), np.full((2, 2), values[pos]))}
+        vals, best_pos, pl = merge_sweep(local_results, payload, len(values))
+        np.savez(os.path.join(out_dir, f"sweep{rank}.npz"), vals=np.array(vals), best=best_pos, u=pl[0], a=pl[1])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("values,world", [([5.0, 3.0, 4.0, 3.0, 9.0], 2), ([2.0, 2.0, 1.0, 1.0, 1.0, 7.0, 0.5], 3), ([1.0], 2)])
+def test_ic_sweep_sharding_merge_gloo(tmp_path, values, world):
+    """evaluate_best_ic shards the n_u sweep over the ranks (ic.py:192-216); the merged criteria are in sweep order and the winner is
+    the reference's: the first position whose criterion is strictly below everything before it (ties -> the earlier n_u)."""
+    mp.spawn(_sweep_worker, args=(world, _free_port(), values, str(tmp_path)), nprocs=world, join=True)
+    want = int(np.argmin(values))                      # first occurrence of the minimum
+    for r in range(world):
+        z = np.load(tmp_path / f"sweep{r}.npz")
+        assert list(z["vals"]) == values and int(z["best"]) == want
+        assert np.array_equal(z["u"], np.full(3, want)) and np.array_equal(z["a"], np.full((2, 2), values[want]))

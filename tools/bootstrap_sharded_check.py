@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""2+ GPU check of the fit-sharded bootstrap (run under torchrun on the GPU box): bt_ci with the resamples spread over the ranks
-must reproduce the reference's confidence bounds frozen in tests/golden/live_drivers.npz (B = 4, 90 %), on every rank.
+"""2+ GPU check of the fit-sharded drivers (run under torchrun on the GPU box): bt_ci with the resamples spread over the ranks
+must reproduce the reference's confidence bounds frozen in tests/golden/live_drivers.npz (B = 4, 90 %) on every rank, and
+evaluate_best_ic with the n_u sweep spread over the ranks the reference's AIC values and winner.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/bootstrap_sharded_check.py"""
 import os
 import sys
@@ -37,6 +38,13 @@ def main():
               np.abs(uhi - lv["bt_u_hi"][:, 0]).max())
     wrote = os.path.exists(os.path.join(out, "confidence_interval_celltypes_proportions.csv"))
     ok = err <= 1e-6 and wrote == (rank == 0)
+    # the n_u sweep of --ic AIC (ic.py:169-218), sharded over the ranks, against the reference's frozen criteria and winner
+    from demethify_b200.ic import evaluate_best_ic
+    u, a, best, vals = evaluate_best_ic(X, Rk, D, "uniform_", "AIC", 1, iter1=10000, iter2=20, tol=1e-2, n_restarts=5)
+    ic_ok = (best == int(lv["ic_AIC_best"]) and np.allclose(vals, lv["ic_AIC_vals"], rtol=1e-6, atol=1e-9)
+             and np.abs(a - lv["ic_AIC_a"]).max() <= 1e-6 and np.abs(u - lv["ic_AIC_u"]).max() <= 1e-6)
+    ok = ok and ic_ok
+    err = max(err, float(np.abs(a - lv["ic_AIC_a"]).max()))
     flags = [None] * world
     dist.all_gather_object(flags, (rank, float(err), bool(ok)))
     if rank == 0:
