@@ -156,6 +156,10 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__ as g
+    if world > 1:               # one process compiles (a no-op when the shipped library is current), the others wait
+        if rank == 0:
+            g.build()
+        dist.barrier()
     g.build()
     import demethify_b200
     from demethify_b200 import deconvolution as dec
