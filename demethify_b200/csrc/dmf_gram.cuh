@@ -1110,8 +1110,10 @@ __device__ __forceinline__ bool project_simplex_reg(double (&v)[KTB], int p) {
 // per sample column on (G_j, bx_j).  One CTA per fit, one thread per sample.  alpha and alpha_ both persist.
 template <typename T, int KTB>
 __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a) {
-    __shared__ double colred[kThreads];
-    __shared__ int s_bad;
+    // grid = (fits, ceil(N / blockDim)): a CTA (one warp) owns blockDim consecutive samples, so that the samples of a fit spread
+    // over several SMs (the iterations are FP64-latency bound).  The last CTA of a fit sums the per-sample ||alpha_unk||^2 in
+    // sample order and updates the state; no other CTA writes it.
+    __shared__ int s_last;
     const Geom& g = a.g;
     const FitDev f = a.fits[blockIdx.x];
     FitState* st = f.st;
@@ -1132,10 +1134,11 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
     const double inv_lh = 1.0 / l_h;
     T* Acur = reinterpret_cast<T*>(f.A) + (size_t)acur * g.Kt * g.N;
     T* Aprev = reinterpret_cast<T*>(f.A) + (size_t)(acur ^ 1) * g.Kt * g.N;
-    if (threadIdx.x == 0) s_bad = 0;
-    __syncthreads();
-    double sa_thread = 0.0;
-    for (int j = threadIdx.x; j < g.N; j += blockDim.x) {
+    int any_bad = 0;
+    const int n_cta = gridDim.y;
+    {
+        const int j = blockIdx.y * blockDim.x + threadIdx.x;
+        if (j < g.N) {
         double G[KTB][KTB], b[KTB], ac[KTB], ap[KTB];
 #pragma unroll(KTB <= 8 ? KTB : 1)
         for (int k = 0; k < KTB; ++k) {
@@ -1165,7 +1168,7 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
 #pragma unroll(KTB <= 8 ? KTB : 1)
                 for (int k = 0; k < KTB; ++k) { ap[k] = ac[k]; ac[k] = k < Kt ? (double)(T)v[k] : 0.0; }
             }
-            if (bad) s_bad = 1;
+            if (bad) any_bad = 1;
         } else {
             const double pj = f.purity[j];
             for (int it = 0; it < n2; ++it) {
@@ -1199,20 +1202,29 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
                 if (!fw) Aprev[(size_t)k * g.N + j] = (T)ap[k];
                 if (k >= g.K) sa = fma(ac[k], ac[k], sa);
             }
-        sa_thread += sa;       // at most one column per thread unless N > blockDim (then in column order)
-        colred[threadIdx.x] = sa_thread;
+        f.part[j] = sa;
+        }
     }
-    if (threadIdx.x >= g.N) colred[threadIdx.x] = 0.0;
-    __syncthreads();
+    any_bad = __syncthreads_or(any_bad);
     if (threadIdx.x == 0) {
-        if (s_bad) st->done = 3;
+        f.part[g.N + blockIdx.y] = any_bad ? 1.0 : 0.0;
+        __threadfence();
+        s_last = (atomicAdd(&f.tickets[0], 1u) == (unsigned)(n_cta - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        f.tickets[0] = 0u;                               // re-arm for the next launch
+        bool bad = false;
+        for (int cta = 0; cta < n_cta; ++cta) bad |= __ldcg(&f.part[g.N + cta]) != 0.0;
+        if (bad) st->done = 3;
         if (sharded) {
             st->ssq_u = f.rscal[4];
             st->l_h = l_h;
         }
         double sa = 0.0;
-        const int nt = min((int)blockDim.x, g.N);
-        for (int t = 0; t < nt; ++t) sa += colred[t];
+        for (int t = 0; t < g.N; ++t) sa += __ldcg(&f.part[t]);
         const double na = sqrt(sa);
         st->l_w = (na * na) * st->dmax2;                 // deconvolution.py:216 / :327
         if (!fw) {
