@@ -27,6 +27,11 @@
 
 namespace dmf {
 
+// np.clip(., 0, 1) of deconvolution.py:88 as two min/max instructions (a NaN would become 0 here; non-finite inputs are
+// caught by the simplex projection of the alpha step, which sees the same poisoned statistics)
+__device__ __forceinline__ double clip01(double v) { return fmin(fmax(v, 0.0), 1.0); }
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
 __host__ __device__ constexpr int ng_of(int nub) { return nub + nub * (nub + 1) / 2; }
 __host__ __device__ constexpr int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 __host__ __device__ constexpr int tri_index(int q, int q2, int nub) { return q * nub - q * (q - 1) / 2 + (q2 - q); }   // q <= q2
@@ -660,7 +665,7 @@ __global__ void __launch_bounds__(kThreads) u_inner_kernel(const PassArgs a) {
                 }
                 const double gq = v[q] - s;
                 T un = ut[q] + (T)gq * inv_lw;
-                un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
+                un = clip01(un);
                 up[q] = u[q];
                 u[q] = un;
             }
@@ -751,7 +756,7 @@ __global__ void __launch_bounds__(kThreads) u_inner_mult_kernel(const PassArgs a
                 for (int q2 = 0; q2 < NUB; ++q2)
                     sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], (double)ut[q2], sq);
                 T un = ut[q] + (T)(v[q] - sq) * inv_lw;
-                un = un < (T)0 ? (T)0 : (un > (T)1 ? (T)1 : un);
+                un = clip01(un);
                 up[q] = u[q];
                 u[q] = un;
             }
