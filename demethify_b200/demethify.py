@@ -53,8 +53,26 @@ def build_parser():
     return p
 
 
+def _pinned_matrix(rows, cols, dtype):
+    """(rows, cols) C-ordered numpy matrix backed by page-locked host memory when CUDA is there (the H2D copy of the solver then
+    runs at full PCIe rate); plain numpy otherwise."""
+    import torch
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    try:
+        if torch.cuda.is_available():
+            return torch.empty((rows, cols), dtype=tdt, pin_memory=True).numpy()
+    except RuntimeError:
+        pass
+    return np.empty((rows, cols), dtype=dtype)
+
+
 def read_inputs(args):
-    """demethify.py:103-143 — bedmethyl (tab separated, percent_modified in percent) or csv (fraction) readers."""
+    """demethify.py:103-143 — bedmethyl (tab separated, percent_modified in percent) or csv (fraction) readers.
+
+    Same parser as the reference (pandas' C reader with its default float conversion, so every value is bit-identical), but the
+    sample files are parsed concurrently (the reader releases the GIL), only the two columns the solver uses are converted, and
+    each sample lands directly in its column of one page-locked M x N matrix."""
+    from concurrent.futures import ThreadPoolExecutor
     ref, header = None, []
     sep = "\t" if args.bedmethyl else ","
     if args.ref:
@@ -65,16 +83,45 @@ def read_inputs(args):
             ref_df = ref_df.fillna(0)
         header = list(ref_df.columns)
         ref = ref_df.values
-    freqs, cov = [], []
-    for path in args.methfreq:
-        t = pd.read_csv(path, sep=sep)
-        if not args.bedmethyl and t.shape[1] == 1:
+
+    def load(path):
+        cols = list(pd.read_csv(path, sep=sep, nrows=0).columns)
+        single = (not args.bedmethyl) and len(cols) == 1                 # csv with frequencies only: coverage 1 (demethify.py:136-137)
+        use = ["percent_modified"] + ([] if single else ["valid_coverage"])
+        t = pd.read_csv(path, sep=sep, usecols=use)
+        if single:
             t["valid_coverage"] = 1
         if args.fillna:
             t = t.fillna(0)
-        freqs.append(t["percent_modified"].values / 100 if args.bedmethyl else t["percent_modified"].values)
-        cov.append(t["valid_coverage"].values)
-    return np.column_stack(freqs), np.column_stack(cov), ref, header
+        f = t["percent_modified"].values
+        return (f / 100 if args.bedmethyl else f), t["valid_coverage"].values
+
+    paths = list(args.methfreq)
+    with ThreadPoolExecutor(max_workers=min(len(paths), os.cpu_count() or 1, 32)) as ex:
+        first = load(paths[0])
+        M = first[0].shape[0]
+        int_cov = np.issubdtype(first[1].dtype, np.integer)
+        meth_f = _pinned_matrix(M, len(paths), np.float64)
+        counts = _pinned_matrix(M, len(paths), np.int64 if int_cov else np.float64)
+
+        float_cols = {}                                   # coverage columns that are not integer typed (NaN without --fillna, ...)
+
+        def place(j, pair):
+            f, c = pair
+            if f.shape[0] != M:
+                raise ValueError("all input files must have the same number of rows")      # np.column_stack raises in the reference
+            meth_f[:, j] = f
+            if int_cov and not np.issubdtype(c.dtype, np.integer):
+                float_cols[j] = c
+            else:
+                counts[:, j] = c
+        place(0, first)
+        list(ex.map(lambda j: place(j, load(paths[j])), range(1, len(paths))))
+    if float_cols:                                        # np.column_stack of mixed int / float columns is float64 in the reference
+        counts = counts.astype(np.float64)
+        for j, c in float_cols.items():
+            counts[:, j] = c
+    return meth_f, counts, ref, header
 
 
 def main(argv=None):
