@@ -125,16 +125,24 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
     ng = {1: 2, 2: 5}.get(n_u, 14)                            # Gram engine: per-row statistics, one record per warp of a row
     ntc = 1 << max(0, ((N + 3) // 4 - 1).bit_length())
     per_fit = (2 * M * (n_u + (n_u & 1)) * (8 if prob.precision == "fp64" else 4) + M * ng * ((ntc + 31) // 32) * 8 * (n_u <= 4)
-               + 64 * (prob.K + n_u) * N * 8 + 4096)
+               + 64 * (prob.K + n_u) * N * 8 + 4096
+               + M * (44 + 24 * n_u))                          # wave-level stacks: resample index, order, rows, mult, offs, u0 / results
     wave = int(max(1, min(n_bootstrap, (device_free_bytes(prob.device) // 2) // max(per_fit, 1), 4096)))
     mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
     use_mult = prob.K <= 6 and n_u <= 4 and prob.K + (prob.K & 1) + n_u + (n_u & 1) <= 8
     dev = prob.device
     for w0 in range(0, n_bootstrap, wave):
         chunk = seeds[w0:w0 + wave]
-        rows, U0, A0, inv, mults, offs = [], [], [], [], [], []
 
-        def prepare(s):
+        # host staging for the wave: the worker threads draw straight into it, one H2D copy per array (pageable on purpose:
+        # page-locking gigabytes per wave costs more than the copy saves)
+        Bw = len(chunk)
+        idx_np = np.empty((Bw, M), dtype=np.int64)
+        u0_np = np.empty((Bw, M, n_u), dtype=np.float64)
+        A0 = np.empty((Bw, prob.K + n_u, N))
+
+        def prepare(k):
+            s = chunk[k]
             idx = resample_indices(s, M)
             if data_dependent_init:      # `uniform` / SVD look at the resampled data and use the global stream: sequential
                 Xb, Db, Rb = meth_f[idx], np.asarray(counts)[idx], np.asarray(ref)[idx]
@@ -145,46 +153,46 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
             else:                        # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
                 opt = init_option if init_option in ("uniform_", "beta") and (init_option == "uniform_" or n_u <= N) else "uniform_"
                 u0, a0 = _shape_only_init(s, opt, M, prob.K, N, n_u, with_zero_guard=purity is None)
-            return idx, u0, a0
+            idx_np[k], u0_np[k], A0[k] = idx, np.asarray(u0).reshape(M, n_u), a0
         if data_dependent_init or init_option not in ("uniform_", "beta"):
-            prepared = [prepare(s) for s in chunk]
+            for k in range(Bw):
+                prepare(k)
         else:                            # numpy's legacy generators release the GIL: draw the resamples of the wave in parallel
             from concurrent.futures import ThreadPoolExecutor
             import os
             with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-                prepared = list(ex.map(prepare, chunk))
-        for idx, u0, a0 in prepared:
-            # order the resampled positions by source row (stable sort on the device); u is position-indexed, so permute it along
-            idx_d = torch.from_numpy(idx).to(dev)
-            order_d = torch.sort(idx_d, stable=True).indices
-            u0_d = torch.from_numpy(np.ascontiguousarray(u0)).to(dev)[order_d]
-            rows.append(idx_d[order_d].to(torch.int32))
-            if use_mult:
-                cnt = torch.bincount(idx_d, minlength=M)
-                mults.append(cnt.to(torch.int32))
-                offs.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]).to(torch.int32))
-            U0.append(u0_d)
-            A0.append(a0)
-            inv.append(order_d)
+                list(ex.map(prepare, range(Bw)))
+        # batched device ops: order the resampled positions of every fit by source row (stable sort); u is position-indexed, so it is
+        # permuted along; multiplicities and CSR offsets per source row
+        idx_d = torch.from_numpy(idx_np).to(dev)                                                    # (Bw, M) int64
+        u0_d = torch.from_numpy(u0_np).to(dev)                                                      # (Bw, M, n_u)
+        order_d = torch.sort(idx_d, dim=1, stable=True).indices
+        rows_d = torch.gather(idx_d, 1, order_d).to(torch.int32)
+        U0 = torch.gather(u0_d, 1, order_d.unsqueeze(-1).expand(-1, -1, n_u))
+        del u0_d
         if use_mult:
-            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows, mult=mults, offs=offs)
+            Mp = (M + 3) // 4 * 4                     # the multiplicities are streamed with 16-byte bulk copies: aligned rows
+            cnt = torch.zeros((Bw, Mp), dtype=torch.int32, device=dev)[:, :M]
+            cnt.scatter_add_(1, idx_d, torch.ones_like(idx_d, dtype=torch.int32))
+            offs_d = torch.zeros((Bw, M + 1), dtype=torch.int32, device=dev)
+            offs_d[:, 1:] = torch.cumsum(cnt, 1)
+            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d, mult=cnt, offs=offs_d)
         else:
-            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows)
+            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d)
+        del idx_d
         states = batch.fit(n_iter1, n_iter2, tol)
-        for k, st in enumerate(states):
-            u_d, a_d = batch.current(k, states)
-            if on_device:
-                alphas[w0 + k] = a_d.to(torch.float64)
-                if keep_u:                       # back to the resampled-position order of the reference (Q6)
-                    us[w0 + k][inv[k]] = u_d.to(torch.float64)
-                n_outer.append(st.n_outer)
-                continue
-            alphas[w0 + k] = a_d.to(torch.float64).cpu().numpy()
-            if keep_u:                           # back to the resampled-position order of the reference (Q6)
-                back = torch.empty((M, n_u), dtype=torch.float64, device=dev)
-                back[inv[k]] = u_d.to(torch.float64)
-                us[w0 + k] = back.cpu().numpy()
-            n_outer.append(st.n_outer)
+        U_d, A_d = batch.stacked_current(states)
+        n_outer.extend(st.n_outer for st in states)
+        if on_device:
+            alphas[w0:w0 + Bw] = A_d.to(torch.float64)
+            if keep_u:                               # back to the resampled-position order of the reference (Q6)
+                us[w0:w0 + Bw].scatter_(1, order_d.unsqueeze(-1).expand(-1, -1, n_u), U_d.to(torch.float64))
+        else:
+            alphas[w0:w0 + Bw] = A_d.to(torch.float64).cpu().numpy()
+            if keep_u:
+                back = torch.empty((Bw, M, n_u), dtype=torch.float64, device=dev)
+                back.scatter_(1, order_d.unsqueeze(-1).expand(-1, -1, n_u), U_d.to(torch.float64))
+                us[w0:w0 + Bw] = back.cpu().numpy()
         batch.close()
     return alphas, us, n_outer
 

@@ -517,6 +517,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         const dmf_fit_desc_t& d = fits[i];
         if ((d.mult != nullptr) != (d.offs != nullptr)) return fail(DMF_E_ARG, "fit descriptor: mult and offs go together");
         if (d.mult && !d.rows) return fail(DMF_E_ARG, "fit descriptor: the multiplicity form needs rows (source row of every position, sorted)");
+        if (d.mult && (reinterpret_cast<uintptr_t>(d.mult) & 15)) return fail(DMF_E_ARG, "fit descriptor: mult must be 16-byte aligned (it is streamed with bulk copies)");
         n_mult += d.mult ? 1 : 0;
         shared_inputs &= (d.X == fits[0].X && d.D == fits[0].D && d.Rk == fits[0].Rk);
         if (!d.X || !d.D || !d.U || !d.A || (s.K && !d.Rk)) return fail(DMF_E_ARG, "fit descriptor has a NULL matrix");

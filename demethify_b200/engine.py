@@ -191,11 +191,19 @@ class FitBatch:
         self.u_slot = (self.M * self.ldu + 31) // 32 * 32          # slot stride keeps bulk copies 16-byte aligned
         self.U = torch.zeros((self.n_fits, 2, self.u_slot), dtype=dt, device=dev)
         self.A = torch.empty((self.n_fits, 2, self.Kt, self.N), dtype=dt, device=dev)
-        for i in range(self.n_fits):
-            u = to_device(U0[i], dt, dev).reshape(self.M, self.n_u)
-            a = to_device(A0[i], dt, dev).reshape(self.Kt, self.N)
-            self.u_view(i, 0).copy_(u); self.u_view(i, 1).copy_(u)
-            self.A[i, 0].copy_(a); self.A[i, 1].copy_(a)
+        if isinstance(U0, torch.Tensor) and U0.ndim == 3:
+            # stacked initial iterates (n_fits, M, n_u) / (n_fits, Kt, N): a handful of copies for the whole batch
+            u = to_device(U0, dt, dev).reshape(self.n_fits, self.M, self.n_u)
+            a = to_device(np.ascontiguousarray(A0) if not isinstance(A0, torch.Tensor) else A0, dt, dev).reshape(self.n_fits, self.Kt, self.N)
+            for slot in (0, 1):
+                self.U[:, slot, :self.M * self.ldu].view(self.n_fits, self.M, self.ldu)[:, :, :self.n_u] = u
+                self.A[:, slot] = a
+        else:
+            for i in range(self.n_fits):
+                u = to_device(U0[i], dt, dev).reshape(self.M, self.n_u)
+                a = to_device(A0[i], dt, dev).reshape(self.Kt, self.N)
+                self.u_view(i, 0).copy_(u); self.u_view(i, 1).copy_(u)
+                self.A[i, 0].copy_(a); self.A[i, 1].copy_(a)
         self.purity = None
         if mode == _lib.DMF_MODE_PURITY:
             self.purity = to_device(np.asarray(purity, dtype=np.float64).reshape(-1), torch.float64, dev)
@@ -203,7 +211,10 @@ class FitBatch:
                 raise ValueError("purity needs one value per sample")
         self.rows = None
         if rows is not None:
-            self.rows = [to_device(r if isinstance(r, torch.Tensor) else np.asarray(r, dtype=np.int32), torch.int32, dev) for r in rows]
+            if isinstance(rows, torch.Tensor) and rows.ndim == 2:           # stacked (n_fits, M) int32 device tensor
+                self.rows = to_device(rows, torch.int32, dev)
+            else:
+                self.rows = [to_device(r if isinstance(r, torch.Tensor) else np.asarray(r, dtype=np.int32), torch.int32, dev) for r in rows]
         # bootstrap resamples in multiplicity form: per fit int32 device tensors mult (M) and offs (M + 1)
         self.mult, self.offs = mult, offs
         if (mult is None) != (offs is None) or (mult is not None and rows is None):
@@ -228,7 +239,7 @@ class FitBatch:
             d.X, d.D = p.X.data_ptr(), p.D.data_ptr()
             d.Rk = p.Rk.data_ptr() if p.Rk is not None else None
             d.rows = self.rows[i].data_ptr() if self.rows is not None else None
-            if self.mult is not None:
+            if self.mult is not None:      # rows of a stacked tensor are views: no .contiguous() copies, the pointers must stay valid
                 d.mult, d.offs = self.mult[i].data_ptr(), self.offs[i].data_ptr()
             d.U, d.A = self.U[i].data_ptr(), self.A[i].data_ptr()
             d.purity = self.purity.data_ptr() if self.purity is not None else None
@@ -312,6 +323,15 @@ class FitBatch:
         """Device tensors (U, alpha) holding fit i's current iterate."""
         st = (states or self.states())[i]
         return self.u_view(i, st.u_slot), self.A[i, st.a_slot]
+
+    def stacked_current(self, states=None):
+        """(U (n_fits, M, n_u), alpha (n_fits, Kt, N)) device tensors holding every fit's current iterate."""
+        states = states or self.states()
+        ar = torch.arange(self.n_fits, device=self.device)
+        us = torch.tensor([s.u_slot for s in states], device=self.device)
+        as_ = torch.tensor([s.a_slot for s in states], device=self.device)
+        U = self.U[ar, us][:, :self.M * self.ldu].view(self.n_fits, self.M, self.ldu)[:, :, :self.n_u]
+        return U, self.A[ar, as_]
 
     def results(self, states=None):
         """[(u ndarray Mxn_u, alpha ndarray KtxN, n_outer, cost)] as float64 host arrays."""

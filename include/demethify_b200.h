@@ -88,7 +88,7 @@ typedef struct dmf_fit_desc {
      * (offs has M + 1 entries, offs[M] == M: the resample has as many rows as the source, sklearn.utils.resample,
      * bootstrap.py:28).  u is thus ordered by source row, and `rows` must hold the nondecreasing source row of every position
      * (the sorted resample index).  The streaming passes then read X, D, Rk contiguously instead of gathering rows.
-     * Device pointers, int32. */
+     * Device pointers, int32; mult 16-byte aligned. */
     const int32_t* mult;
     const int32_t* offs;
 } dmf_fit_desc_t;
