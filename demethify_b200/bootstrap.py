@@ -19,7 +19,7 @@ from .deconvolution import init_BSSMF_md, init_BSSMF_md_p
 from .engine import DeviceProblem, FitBatch, device_free_bytes
 from .init_func import wls_all_samples
 
-__all__ = ["bt_ci", "bootstrap_seeds", "resample_indices", "bootstrap_fits", "shard_of", "merge_resample_stacks",
+__all__ = ["bt_ci", "bootstrap_seeds", "resample_indices", "resample_layout", "bootstrap_fits", "shard_of", "merge_resample_stacks",
            "percentile_bounds_device"]
 
 
@@ -94,6 +94,24 @@ def percentile_bounds_device(stack, lower_percentile, upper_percentile):
     return out[0].reshape(shape).cpu().numpy(), out[1].reshape(shape).cpu().numpy()
 
 
+def resample_layout(idx, M, with_csr=True):
+    """Stacked resample indices (B, M) (sklearn.utils.resample, bootstrap.py:28) -> the layout the library wants:
+    order (B, M): stable argsort of every resample by source row (position p of the sorted resample was position order[p] of the
+    reference's), rows (B, M) int32: the sorted source rows, and — multiplicity form — mult (B, M) int32: how often every source
+    row was drawn (16-byte aligned rows), offs (B, M + 1) int32: CSR offsets of the positions of every source row."""
+    B = idx.shape[0]
+    order = torch.sort(idx, dim=1, stable=True).indices
+    rows = torch.gather(idx, 1, order).to(torch.int32)
+    if not with_csr:
+        return order, rows, None, None
+    Mp = (M + 3) // 4 * 4                             # the multiplicities are streamed with 16-byte bulk copies: aligned rows
+    mult = torch.zeros((B, Mp), dtype=torch.int32, device=idx.device)[:, :M]
+    mult.scatter_add_(1, idx, torch.ones_like(idx, dtype=torch.int32))
+    offs = torch.zeros((B, M + 1), dtype=torch.int32, device=idx.device)
+    offs[:, 1:] = torch.cumsum(mult, 1)
+    return order, rows, mult, offs
+
+
 def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, purity, seed, prob=None,
                    keep_u=True, on_device=False, seeds=None):
     """All resample fits -> (alphas (B, Kt, N), us (B, M, n_u) or None, n_outer list).
@@ -166,16 +184,10 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         # permuted along; multiplicities and CSR offsets per source row
         idx_d = torch.from_numpy(idx_np).to(dev)                                                    # (Bw, M) int64
         u0_d = torch.from_numpy(u0_np).to(dev)                                                      # (Bw, M, n_u)
-        order_d = torch.sort(idx_d, dim=1, stable=True).indices
-        rows_d = torch.gather(idx_d, 1, order_d).to(torch.int32)
+        order_d, rows_d, cnt, offs_d = resample_layout(idx_d, M, with_csr=use_mult)
         U0 = torch.gather(u0_d, 1, order_d.unsqueeze(-1).expand(-1, -1, n_u))
         del u0_d
         if use_mult:
-            Mp = (M + 3) // 4 * 4                     # the multiplicities are streamed with 16-byte bulk copies: aligned rows
-            cnt = torch.zeros((Bw, Mp), dtype=torch.int32, device=dev)[:, :M]
-            cnt.scatter_add_(1, idx_d, torch.ones_like(idx_d, dtype=torch.int32))
-            offs_d = torch.zeros((Bw, M + 1), dtype=torch.int32, device=dev)
-            offs_d[:, 1:] = torch.cumsum(cnt, 1)
             batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d, mult=cnt, offs=offs_d)
         else:
             batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d)

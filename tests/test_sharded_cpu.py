@@ -201,3 +201,24 @@ def test_ic_sweep_sharding_merge_gloo(tmp_path, values, world):
         z = np.load(tmp_path / f"sweep{r}.npz")
         assert list(z["vals"]) == values and int(z["best"]) == want
         assert np.array_equal(z["u"], np.full(3, want)) and np.array_equal(z["a"], np.full((2, 2), values[want]))
+
+
+def test_resample_layout_matches_per_fit_numpy():
+    """The stacked device-side layout of a wave of resamples (order, sorted rows, multiplicities, CSR offsets) against the
+    obvious per-fit numpy construction; positions of one source row keep the reference's order (stable sort)."""
+    from demethify_b200.bootstrap import bootstrap_seeds, resample_indices, resample_layout
+    M = 1013
+    seeds = bootstrap_seeds(1, 6)
+    idx = np.stack([resample_indices(s, M) for s in seeds])
+    order, rows, mult, offs = resample_layout(torch.from_numpy(idx), M)
+    for b in range(len(seeds)):
+        o = np.argsort(idx[b], kind="stable")
+        assert np.array_equal(order[b].numpy(), o) and np.array_equal(rows[b].numpy(), idx[b][o])
+        cnt = np.bincount(idx[b], minlength=M)
+        assert np.array_equal(mult[b].numpy(), cnt) and np.array_equal(offs[b].numpy(), np.concatenate([[0], np.cumsum(cnt)]))
+        assert int(offs[b, -1]) == M and mult[b].data_ptr() % 16 == 0
+        for m in np.flatnonzero(cnt > 1)[:20]:            # the positions offs[m] .. offs[m+1] are exactly the draws of source row m
+            p0, p1 = int(offs[b, m]), int(offs[b, m + 1])
+            assert np.all(rows[b, p0:p1].numpy() == m) and np.array_equal(np.sort(o[p0:p1]), np.flatnonzero(idx[b] == m))
+    order2, rows2, none1, none2 = resample_layout(torch.from_numpy(idx), M, with_csr=False)
+    assert none1 is None and none2 is None and torch.equal(order2, order) and torch.equal(rows2, rows)
