@@ -200,3 +200,41 @@ def test_cli_drop_in(pkg, shipped, tmp_path):
         assert np.abs(got.values - shipped["unsup_alpha"]).max() <= 1e-5
     finally:
         os.chdir(cwd)
+
+
+def test_fp32_mode_multiplicity_form_and_many_unknowns(pkg):
+    """fp32 storage / arithmetic (north-star bar: max |d alpha| <= 1e-4) on the two Gram-engine variants that the fp64 tests do not
+    reach in fp32: a bootstrap resample in multiplicity form and a 5-unknown fit (one register row per batch)."""
+    import torch
+    import demethify_b200
+    from demethify_b200 import deconvolution as dec
+    from demethify_b200.bootstrap import resample_layout
+    from demethify_b200.engine import DeviceProblem, FitBatch
+    from oracle import bssmf_numpy as orc
+    rs = np.random.RandomState(23)
+    M, N, K = 4001, 24, 5
+    Rf = rs.beta(0.5, 0.5, size=(M, K + 5))
+    A = rs.dirichlet(np.ones(K + 5), N).T
+    D = rs.poisson(40, size=(M, N)) + 1
+    X = rs.binomial(D, np.clip(Rf @ A, 0, 1)) / D
+    Rk = np.ascontiguousarray(Rf[:, :K])
+    demethify_b200.set_precision("fp32")
+    try:
+        # (a) multiplicity form, n_u = 1
+        idx = np.random.RandomState(5).randint(0, M, size=(M,))
+        u0 = np.random.RandomState(6).uniform(size=(M, 1)); a0 = np.random.RandomState(7).dirichlet(np.ones(K + 1), N).T
+        prob = DeviceProblem(X, D, Rk)
+        order, rows, mult, offs = resample_layout(torch.from_numpy(idx[None]).to(prob.device), M)
+        U0 = torch.from_numpy(u0[None]).to(prob.device).gather(1, order.unsqueeze(-1))
+        b = FitBatch(prob, 1, U0, a0[None], rows=rows, mult=mult, offs=offs)
+        (u, a, n_o, _), = b.results(b.fit(5, 20, 0.0))
+        uo, ao = orc.solve_partial_reference(u0.copy(), np.c_[Rk[idx], u0], a0.copy(), X[idx], D[idx].astype(float), Rk[idx], 1, 5, 20, 0.0)
+        back = np.empty_like(u); back[order[0].cpu().numpy()] = u
+        assert n_o == 5 and np.abs(a - ao).max() <= 1e-4 and np.abs(back - uo).max() <= 1e-3
+        # (b) 5 unknown types
+        u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, 5, seed=3)
+        uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, 5, 4, 10, 0.0)
+        u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, 5, n_iter1=4, n_iter2=10, tol=0.0)
+        assert dec.last_fit_info()["engine"] == "gram" and np.abs(a - ao).max() <= 1e-4 and np.abs(u - uo).max() <= 1e-3
+    finally:
+        demethify_b200.set_precision("fp64")
