@@ -55,6 +55,9 @@ struct dmf_batch_s {
     int kb_g, nub_g, c_g, ntc_g, pb_g, c_p, ntc_p, ktb_in;
     int n_parts_u, n_groups_u;
     unsigned smem_rg, smem_panel;
+    int p1_ok;                      // own geometry of the one-unknown multiplicity-form panel kernel (two CTAs per SM)
+    Geom gp1;
+    unsigned smem_p1;
     int n_active;                   // fits_dev holds the descriptors of the first n_active still-running fits (compacted at every poll)
     // peer exchange (row-sharded runs): symmetric buffers of all ranks, see peer_allreduce_kernel
     double** peers_dev;             // device array [world]
@@ -107,6 +110,9 @@ struct Plan {
     int n_parts_u, n_groups_u;     // u_inner_kernel: one thread per row, many more CTAs than the streaming passes
     unsigned g_offX, g_offD, g_offR, g_offU, g_offUp, g_stage_bytes, smem_rg, smem_panel;
     int mult_ok;                   // multiplicity form (bootstrap resamples) available for this shape
+    // the 128-register panel variant of the multiplicity form (one unknown type) gets smaller tiles of its own: two CTAs per SM
+    int p1_ok, p1_tile_rows, p1_n_tiles, p1_stages;
+    unsigned p1_offX, p1_offD, p1_offR, p1_offU, p1_offUp, p1_stage_bytes, p1_smem;
     size_t off_usum, per_fit_usum;
     size_t off_rowgram, off_stats, off_gstats, off_red, per_fit_rowgram, per_fit_stats, per_fit_red;
     size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
@@ -208,6 +214,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     p.gram_ok = 0;
     p.n_parts_g = p.n_groups_g = p.n_parts_u = p.n_groups_u = 0;
     p.mult_ok = 0;
+    p.p1_ok = 0;
     p.per_fit_usum = 0;
     p.per_fit_rowgram = p.per_fit_stats = p.per_fit_red = 0;
     p.stats_gbx = p.stats_scal = 0;
@@ -263,6 +270,26 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
                 p.g_stage_bytes = (unsigned)a128g(p.g_offUp + trg * 4);
                 p.mult_ok = (p.c_g == 4 && p.pb_g == 8 && p.nub_g <= 4 && trg % 4 == 0 && s.mode != DMF_MODE_UNSUPERVISED) ? 1 : 0;
                 p.per_fit_usum = p.mult_ok ? align_up((size_t)s.M * p.ng_g * 8, 256) : 0;
+                p.p1_ok = 0;
+                if (p.mult_ok && s.n_u == 1) {
+                    const size_t budget1 = std::min<size_t>(smem_cap, 112 * 1024) - kCtlBytes - 1024;
+                    for (long long tr1 = trg / 2; tr1 >= 4 && !p.p1_ok; tr1 /= 2) {
+                        if (tr1 % ra || tr1 % 4) continue;
+                        for (int stg = kStages; stg >= 3; --stg)
+                            if (stage_g(tr1) * stg <= budget1 && epi_panel <= budget1 + kCtlBytes) {
+                                p.p1_ok = 1; p.p1_tile_rows = (int)tr1; p.p1_stages = stg;
+                                p.p1_n_tiles = (int)((s.M + tr1 - 1) / tr1);
+                                p.p1_offX = 0;
+                                p.p1_offD = (unsigned)a128g(tr1 * px);
+                                p.p1_offR = (unsigned)a128g(p.p1_offD + tr1 * pd);
+                                p.p1_offU = (unsigned)a128g(p.p1_offR + tr1 * pr);
+                                p.p1_offUp = (unsigned)a128g(p.p1_offU + tr1 * pu_stage);
+                                p.p1_stage_bytes = (unsigned)a128g(p.p1_offUp + tr1 * 4);
+                                p.p1_smem = (unsigned)std::max(kCtlBytes + (size_t)stg * p.p1_stage_bytes, epi_panel);
+                                break;
+                            }
+                    }
+                }
                 long long per_fit_g = std::max<long long>(kMinParts, (long long)h->sm_count * p.occ_g / s.n_fits);
                 if (s.max_ctas_per_fit > 0) per_fit_g = std::min<long long>(per_fit_g, s.max_ctas_per_fit);
                 p.n_parts_g = (int)std::min<long long>(per_fit_g, p.n_tiles_g);
@@ -388,10 +415,11 @@ kern_t k_ainner(dmf_batch_s* b) { return by_types(b->shape, g_ainner, b->ktb_in,
 
 // Gram-engine launch: geometry gg; ntc selects the thread mapping of the kernel; grid_x CTAs per fit (0: one CTA per fit on grid.x)
 int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_inner, double tol, int ca0, int cb0, int with_x,
-             int grid_mode /* 0: pass grid, 1: one CTA per fit, 2: wide row grid of u_inner_kernel */, cudaStream_t st) {
+             int grid_mode /* 0: pass grid, 1: one CTA per fit, 2: wide row grid of u_inner_kernel */, cudaStream_t st,
+             const Geom* geom = nullptr) {
     if (!k) return fail(DMF_E_SHAPE, "no Gram-engine kernel instantiation for this shape");
     PassArgs a;
-    a.g = b->gg;
+    a.g = geom ? *geom : b->gg;
     a.g.ntc = ntc;
     a.g.rg = kConsumers / ntc;
     a.fits = b->fits_dev;
@@ -401,7 +429,7 @@ int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_
     a.ca0 = ca0; a.cb0 = cb0; a.with_x = with_x; a.pad = 0;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
     // grid_mode 1 (alpha_inner_kernel): one warp per 32 samples of a fit
-    dim3 grid = grid_mode == 1 ? dim3(b->n_active, (b->shape.N + 31) / 32, 1) : dim3(b->gg.n_parts, b->n_active, 1);
+    dim3 grid = grid_mode == 1 ? dim3(b->n_active, (b->shape.N + 31) / 32, 1) : dim3(a.g.n_parts, b->n_active, 1);
     if (grid_mode == 2) {
         a.g.n_parts = b->n_parts_u;
         a.g.n_groups = b->n_groups_u;
@@ -615,11 +643,27 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         b->kb_g = p.kb_g; b->nub_g = p.nub_g; b->c_g = p.c_g; b->ntc_g = p.ntc_g; b->pb_g = p.pb_g; b->c_p = p.c_p; b->ntc_p = p.ntc_p;
         b->ktb_in = p.ktb_in; b->smem_rg = p.smem_rg; b->smem_panel = p.smem_panel;
         b->n_parts_u = p.n_parts_u; b->n_groups_u = p.n_groups_u;
+        b->p1_ok = (b->multmode && p.p1_ok) ? 1 : 0;
+        if (b->p1_ok) {
+            Geom& r = b->gp1;
+            r = q;
+            r.tile_rows = p.p1_tile_rows; r.n_tiles = p.p1_n_tiles; r.stages = p.p1_stages;
+            r.rpt = 1;                                  // unused by the panel kernel (it strides over the rows of a tile)
+            r.n_parts = std::min(q.n_parts, p.p1_n_tiles); r.n_groups = (r.n_parts + kGroup - 1) / kGroup;
+            r.offX = p.p1_offX; r.offD = p.p1_offD; r.offR = p.p1_offR; r.offU = p.p1_offU; r.offUp = p.p1_offUp; r.stage_bytes = p.p1_stage_bytes;
+            const unsigned sT1 = s.dtype == DMF_F64 ? 8 : 4, sW1 = s.wtype == DMF_W_U16 ? 2 : sT1;
+            r.tile_tx[0] = (unsigned)(p.p1_tile_rows * s.ldx * sT1);
+            r.tile_tx[1] = (unsigned)(p.p1_tile_rows * s.ldd * sW1);
+            r.tile_tx[2] = s.K ? (unsigned)(p.p1_tile_rows * s.ldr * sT1) : 0u;
+            r.tile_tx[3] = (unsigned)(p.p1_tile_rows * p.ng_g * 8);
+            r.tile_tx[4] = (unsigned)(p.p1_tile_rows * 4);
+            b->smem_p1 = p.p1_smem;
+        }
         if ((long long)p.n_parts_u * 8 > (long long)std::max(p.n_parts, p.n_parts_g) * p.part_stride || (long long)p.n_groups_u * 8 > (long long)std::max(p.n_groups, p.n_groups_g) * p.part_stride) {
             b->n_parts_u = p.n_parts_g; b->n_groups_u = p.n_groups_g;     // partial-sum buffers too small for the wide grid (tiny N): use the pass grid
         }
         if ((rc = set_smem(k_rowgram(b, 0), b->smem_rg)) || (rc = set_smem(k_rowgram(b, 1), b->smem_rg)) || (rc = set_smem(k_panel(b), b->smem_panel)) ||
-            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0)) || (b->multmode && ((rc = set_smem(k_costcross(b), 0)) || (rc = set_smem(k_panel_u1(b), b->smem_panel))))) {
+            (rc = set_smem(k_uinner(b), 0)) || (rc = set_smem(k_ainner(b), 0)) || (b->multmode && ((rc = set_smem(k_costcross(b), 0)) || (rc = set_smem(k_panel_u1(b), std::max(b->smem_panel, b->p1_ok ? b->smem_p1 : 0u)))))) {
             delete b;
             return rc;
         }
@@ -731,10 +775,12 @@ int dmf_gram_panels(dmf_batch_t b, int32_t known_block, void* stream) {
     const int ca_lo = known_block ? 0 : nR, ca_hi = known_block ? nR : nR + nU;
     const int cb_hi = known_block ? nR : nR + nU;
     int rc;
+    const bool u1 = b->multmode && !known_block && b->shape.n_u == 1;
+    const bool own = u1 && b->p1_ok;                    // smaller tiles, two CTAs per SM
     for (int ca = ca_lo; ca < ca_hi; ++ca)
         for (int cb = 0; cb < cb_hi; cb += nb)
-            if ((rc = launch_g(b, (b->multmode && !known_block && b->shape.n_u == 1) ? k_panel_u1(b) : k_panel(b), b->ntc_p, b->smem_panel, 0, b->nub_g, 0.0,
-                               ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream))) return rc;
+            if ((rc = launch_g(b, u1 ? k_panel_u1(b) : k_panel(b), b->ntc_p, own ? b->smem_p1 : b->smem_panel, 0, b->nub_g, 0.0,
+                               ca, cb, cb == 0 ? 1 : 0, 0, (cudaStream_t)stream, own ? &b->gp1 : nullptr))) return rc;
     return DMF_OK;
 }
 int dmf_gram_alpha_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
