@@ -99,6 +99,7 @@ def _worker(rank, world, port, case, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.parametrize("mode", ["partial", "purity"])
 def test_row_sharded_fit_world2_gloo(tmp_path, mode):
     X, D, Rk = synth(11, 901, 6, 3, 2)
@@ -159,6 +160,7 @@ def _merge_worker(rank, world, port, n_total, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.parametrize("n_total,world", [(7, 2), (1, 2), (8, 3)])
 def test_fit_sharded_bootstrap_merge_gloo(tmp_path, n_total, world):
     """Fit sharding of the bootstrap (bootstrap.py:26): rank r fits resamples r, r + world, ...; the all-gathered stack holds every
@@ -191,6 +193,7 @@ def _sweep_worker(rank, world, port, values, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.parametrize("values,world", [([5.0, 3.0, 4.0, 3.0, 9.0], 2), ([2.0, 2.0, 1.0, 1.0, 1.0, 7.0, 0.5], 3), ([1.0], 2)])
 def test_ic_sweep_sharding_merge_gloo(tmp_path, values, world):
     """evaluate_best_ic shards the n_u sweep over the ranks (ic.py:192-216); the merged criteria are in sweep order and the winner is
