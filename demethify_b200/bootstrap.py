@@ -187,9 +187,13 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         order_d, rows_d, cnt, offs_d = resample_layout(idx_d, M, with_csr=use_mult)
         U0 = torch.gather(u0_d, 1, order_d.unsqueeze(-1).expand(-1, -1, n_u))
         del u0_d
+        batch = None
         if use_mult:
-            batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d, mult=cnt, offs=offs_d)
-        else:
+            try:
+                batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d, mult=cnt, offs=offs_d)
+            except _lib.DmfError:                     # shape outside the multiplicity form (tile geometry): gather form from now on
+                use_mult = False
+        if batch is None:
             batch = FitBatch(prob, n_u, U0, A0, mode=mode, purity=purity, rows=rows_d)
         del idx_d
         states = batch.fit(n_iter1, n_iter2, tol)
