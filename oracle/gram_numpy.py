@@ -163,3 +163,75 @@ class NumpyShardBackend:
 
     def close(self):
         pass
+
+
+def fit_multiplicity_form(X, D, Rk, idx, U0, A0, n_iter1, n_iter2, tol):
+    """A bootstrap resample (rows idx of X, D, Rk; bootstrap.py:28) fitted WITHOUT materialising it — the algebra of the library's
+    multiplicity form (csrc/dmf_gram.cuh: rowgram4 with row multiplicities, u_inner_mult, usum, MULT panel, cost_cross), in numpy.
+    U0 is position-indexed (one row per resampled position, reference order).  Returns (U (positions), A, n_outer, cost)."""
+    X = np.asarray(X, dtype=np.float64)
+    D = np.asarray(D, dtype=np.float64)
+    M, N = X.shape
+    K = Rk.shape[1]
+    n_u = U0.shape[1]
+    mult = np.bincount(idx, minlength=M).astype(np.float64)
+    row_of = np.asarray(idx)                                   # source row of every position
+    u, up = np.array(U0, dtype=np.float64), np.array(U0, dtype=np.float64)
+    A, Ap = np.array(A0, dtype=np.float64), np.array(A0, dtype=np.float64)
+    mom_a, mom_m = momentum_table((n_iter1 + 1) * max(n_iter2, 1) + 1)
+    live = mult > 0
+    dmax2 = float(D[live].max()) ** 2
+    ssq_rk = float(np.sum(mult[:, None] * Rk ** 2))
+    # known x known statistics, once: sum_p d R R^T = sum_m mult_m d_m R_m R_m^T
+    Gkk = np.einsum("m,mj,mk,ml->klj", mult, D, Rk, Rk)
+    bk = np.einsum("m,mj,mk->kj", mult, D * X, Rk)
+
+    def row_stats():
+        c = X - Rk @ A[:K]
+        b = (D * c) @ A[K:].T                                  # per SOURCE row
+        H = np.einsum("mj,qj,rj->mqr", D, A[K:], A[K:])
+        cc = np.sum(D * c * c, axis=1)
+        cross = -2 * np.einsum("pq,pq->p", u, b[row_of]) + np.einsum("pq,pqr,pr->p", u, H[row_of], u)
+        return b, H, float(np.sum(mult * cc) + np.sum(cross))
+
+    b, H, cf = row_stats()
+    l_w = l_w_old = np.linalg.norm(A[K:]) ** 2 * dmax2
+    l_h = l_h_old = np.sqrt(ssq_rk + np.sum(u ** 2)) ** 2 * dmax2
+    t_u = t_a = n_outer = 0
+    for _ in range(n_iter1):
+        cf0 = cf
+        caps = [0.9999 * np.sqrt(l_w_old / l_w), 0.9999]
+        for it in range(n_iter2):                              # update_u per position on the statistics of its source row
+            beta = min(mom_m[t_u + it], caps[0 if it == 0 else 1])
+            ut = u + beta * (u - up)
+            g = b[row_of] - np.einsum("pqr,pr->pq", H[row_of], ut)
+            up, u = u, np.clip(ut + g / l_w, 0, 1)
+        t_u += n_iter2
+        if n_iter2 > 0:
+            l_w_old = l_w
+        l_h = np.sqrt(ssq_rk + np.sum(u ** 2)) ** 2 * dmax2
+        # per-source-row sums of the positions: s_m = sum u_p, S_m = sum u_p u_p^T; then the alpha statistics from the SHARED matrices
+        s = np.zeros((M, n_u)); np.add.at(s, row_of, u)
+        S = np.zeros((M, n_u, n_u)); np.add.at(S, row_of, np.einsum("pq,pr->pqr", u, u))
+        Kt = K + n_u
+        G = np.zeros((Kt, Kt, N)); bx = np.zeros((Kt, N))
+        G[:K, :K], bx[:K] = Gkk, bk
+        G[K:, :K] = np.einsum("mj,mq,mk->qkj", D, s, Rk)
+        G[:K, K:] = np.transpose(G[K:, :K], (1, 0, 2))
+        G[K:, K:] = np.einsum("mj,mqr->qrj", D, S)
+        bx[K:] = np.einsum("mj,mq->qj", D * X, s)
+        caps = [0.9999 * np.sqrt(l_h_old / l_h), 0.9999]
+        for it in range(n_iter2):
+            beta = min(mom_m[t_a + it], caps[0 if it == 0 else 1])
+            At = A + beta * (A - Ap)
+            grad = bx - np.einsum("klj,lj->kj", G, At)
+            Ap, A = A, simplex_project_columns(At + grad / l_h)
+        t_a += n_iter2
+        if n_iter2 > 0:
+            l_h_old = l_h
+        l_w = np.linalg.norm(A[K:]) ** 2 * dmax2
+        b, H, cf = row_stats()
+        n_outer += 1
+        if abs(cf - cf0) < tol:
+            break
+    return u, A, n_outer, cf

@@ -225,3 +225,19 @@ def test_resample_layout_matches_per_fit_numpy():
             assert np.all(rows[b, p0:p1].numpy() == m) and np.array_equal(np.sort(o[p0:p1]), np.flatnonzero(idx[b] == m))
     order2, rows2, none1, none2 = resample_layout(torch.from_numpy(idx), M, with_csr=False)
     assert none1 is None and none2 is None and torch.equal(order2, order) and torch.equal(rows2, rows)
+
+
+@pytest.mark.parametrize("n_u", [1, 2])
+def test_multiplicity_form_algebra_equals_materialised_resample(n_u):
+    """The multiplicity form of a bootstrap resample (shared source matrices + row multiplicities + per-position u; the library's
+    csrc/dmf_gram.cuh MULT kernels) against the reference-shaped oracle on the materialised resample X[idx] (bootstrap.py:28)."""
+    from oracle.gram_numpy import fit_multiplicity_form
+    X, D, Rk = synth(21, 600, 7, 4, n_u)
+    idx = np.random.RandomState(9).randint(0, X.shape[0], size=(X.shape[0],))
+    u0 = np.random.RandomState(10).uniform(size=(X.shape[0], n_u))
+    a0 = np.random.RandomState(11).dirichlet(np.ones(4 + n_u), 7).T
+    tr = {}
+    uo, ao = orc.solve_partial_reference(u0.copy(), np.c_[Rk[idx], u0], a0.copy(), X[idx], D[idx], Rk[idx], n_u, 12, 10, 1e-3, trace=tr)
+    u, a, n_outer, cost = fit_multiplicity_form(X, D, Rk, idx, u0, a0, 12, 10, 1e-3)
+    assert n_outer == tr["n_outer"] and abs(cost - tr["costs"][-1]) <= 1e-9 * cost
+    assert np.abs(a - ao).max() <= 1e-10 and np.abs(u - uo).max() <= 1e-10
