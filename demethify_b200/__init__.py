@@ -29,10 +29,12 @@ def set_engine(mode):
     'stream' = one streaming pass over X, d_x per reference inner iteration;
     'gram'   = two streaming passes per OUTER iteration build per-row / per-sample sufficient statistics and the
                n_iter2 inner iterations run on those (n_u <= 4, or n_u <= 8 with K <= 6);
-    'auto'   = 'gram' where the library supports the shape, else 'stream' (default)."""
+    'fused'  = ONE streaming pass per outer iteration: row statistics -> U iterations -> Gram panel on a single visit of every
+               row tile (FP64, n_u <= 2, K <= 8, N <= 256, n_iter2 <= 64);
+    'auto'   = 'fused' where the library supports the shape, else 'gram', else 'stream' (default)."""
     global _ENGINE
-    if mode not in ("auto", "gram", "stream"):
-        raise ValueError("engine must be 'auto', 'gram' or 'stream'")
+    if mode not in ("auto", "fused", "gram", "stream"):
+        raise ValueError("engine must be 'auto', 'fused', 'gram' or 'stream'")
     _ENGINE = mode
 
 

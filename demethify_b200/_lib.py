@@ -12,14 +12,15 @@ LIB_PATH = os.path.join(HERE, "libdemethify_sm100.so")
 DMF_F64, DMF_F32 = 0, 1
 DMF_W_FLOAT, DMF_W_U16 = 0, 1
 DMF_MODE_PARTIAL, DMF_MODE_PURITY, DMF_MODE_UNSUPERVISED = 0, 1, 2
-DMF_ENGINE_STREAM, DMF_ENGINE_GRAM = 0, 1
-ABI_VERSION = 3
+DMF_ENGINE_STREAM, DMF_ENGINE_GRAM, DMF_ENGINE_FUSED = 0, 1, 2
+ABI_VERSION = 4
 
 
 class Shape(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("n_u", C.c_int32), ("dtype", C.c_int32),
                 ("wtype", C.c_int32), ("mode", C.c_int32), ("n_fits", C.c_int32), ("max_ctas_per_fit", C.c_int32),
-                ("ldx", C.c_int64), ("ldd", C.c_int64), ("ldr", C.c_int64), ("ldu", C.c_int64), ("u_slot", C.c_int64)]
+                ("ldx", C.c_int64), ("ldd", C.c_int64), ("ldr", C.c_int64), ("ldu", C.c_int64), ("u_slot", C.c_int64),
+                ("u_slots", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FitDesc(C.Structure):
@@ -72,6 +73,9 @@ EXPORTS = {
     "dmf_batch_reserve_momentum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "dmf_gram_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dmf_gram_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
+    "dmf_fused_pass": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
+    "dmf_fused_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
+    "dmf_fused_finish": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "dmf_enqueue_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_fit_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_batch_read_state": (C.c_int, [C.c_void_p, C.POINTER(FitState), C.c_int32, C.c_void_p]),

@@ -10,6 +10,7 @@
 #include "dmf_device.cuh"
 #include "dmf_inst.h"
 #include "dmf_gram.cuh"
+#include "dmf_fused.cuh"
 
 using namespace dmf;
 
@@ -65,6 +66,12 @@ struct dmf_batch_s {
     int peer_rank, peer_world;
     long long peer_slot_stride, peer_flag_off;
     unsigned xchg_epoch;
+    // fused engine (dmf_fused.cuh)
+    int fused_ok;                   // this shape / layout has a fused-pass instantiation
+    int kb_f, nub_f, s_f;
+    FusedArgs fa;                   // launch template (geometry, stage layout); fits / iteration arguments are filled per launch
+    unsigned smem_f;
+    int fused_pending;              // a dmf_fused_outer ran since the cost of the current iterate was last evaluated
     int multmode;                   // fits are bootstrap resamples in multiplicity form
     int sharded;                    // CpG rows sharded over GPUs: kernels publish partial sums, finalize runs on all-reduced sums
     std::vector<FitDev> fits_host;
@@ -92,6 +99,12 @@ kern_t (*g_rowgram[4])(int, int, int) = {pick_rowgram_f64_f64, pick_rowgram_f64_
 kern_t (*g_panel[4])(int, int, int) = {pick_panel_f64_f64, pick_panel_f64_u16, pick_panel_f32_f32, pick_panel_f32_u16};
 kern_t (*g_uinner[4])(int, int, int) = {pick_uinner_f64_f64, pick_uinner_f64_u16, pick_uinner_f32_f32, pick_uinner_f32_u16};
 kern_t (*g_ainner[4])(int, int, int) = {pick_ainner_f64_f64, pick_ainner_f64_u16, pick_ainner_f32_f32, pick_ainner_f32_u16};
+fused_kern_t (*g_fused[4])(int, int, int) = {pick_fused_f64_f64, pick_fused_f64_u16, pick_fused_f32_f32, pick_fused_f32_u16};
+
+fused_kern_t by_types_f(const dmf_shape_t& s, int kb, int nub, int sblk) {
+    const int i = (s.dtype == DMF_F64 ? 0 : 2) + (s.wtype == DMF_W_U16 ? 1 : 0);
+    return g_fused[i](kb, nub, sblk);
+}
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -116,6 +129,9 @@ struct Plan {
     size_t off_usum, per_fit_usum;
     size_t off_rowgram, off_stats, off_gstats, off_red, per_fit_rowgram, per_fit_stats, per_fit_red;
     size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
+    // fused engine
+    int fused_ok, kb_f, nub_f, s_f, n_tiles_f, n_parts_f, n_groups_f;
+    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_offBm, f_bm_pitch, f_rowX, f_rowD, smem_f;
 };
 
 constexpr int pow2ceil_h(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -138,6 +154,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
     const size_t sT = s.dtype == DMF_F64 ? 8 : 4;
     const size_t sW = s.wtype == DMF_W_U16 ? 2 : sT;
     if (s.u_slot < s.M * s.ldu || (s.u_slot * sT) % 16) return fail(DMF_E_SHAPE, "u_slot must be >= M*ldu and a multiple of 16 bytes");
+    if (s.u_slots != 0 && s.u_slots != 2 && s.u_slots != 4) return fail(DMF_E_SHAPE, "u_slots must be 2 (or 0) or 4");
     const int Kt = s.K + s.n_u;
     const int rowlen = p.Kp + p.nup;
     if (rowlen > kMaxKt || Kt > kMaxKt) return fail(DMF_E_SHAPE, "K + n_u (even padded) > 32 is not supported by this build");
@@ -309,7 +326,40 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
             }
         }
     }
-    const int parts_max = std::max(p.n_parts, p.n_parts_g), groups_max = std::max(std::max(p.n_groups, p.n_groups_g), p.n_groups_u);
+    // ---- fused engine (dmf_fused.cuh): FP64, n_u <= 2, K <= 8, N <= 256, four U slots, rows that bulk copies can place one by one
+    p.fused_ok = 0;
+    p.n_parts_f = p.n_groups_f = 0;
+    if (p.gram_ok && s.dtype == DMF_F64 && s.n_u <= 2 && s.K <= 8 && s.N <= 256 && s.u_slots >= 4 && (s.ldd * sW) % 16 == 0) {
+        p.kb_f = s.K == 0 ? 0 : (s.K <= 4 ? 4 : (s.K <= 6 ? 6 : 8));
+        p.nub_f = s.n_u;
+        p.s_f = s.N <= 64 ? 1 : (s.N <= 128 ? 2 : 4);
+        const int ng = ng_of_h(p.nub_f), ncol = p.nub_f * p.kb_f + (ng - p.nub_f), nblk = (ncol + 7) / 8;
+        auto a128f = [](size_t v) { return (unsigned)align_up(v, 128); };
+        p.f_rowX = (unsigned)px; p.f_rowD = (unsigned)pd;
+        p.f_pitchX = (unsigned)px + 32u;
+        p.f_pitchD = (unsigned)pd + (sW == 2 ? 16u : 32u);
+        p.f_offD = a128f((size_t)kFusedRows * p.f_pitchX);
+        p.f_offR = a128f(p.f_offD + (size_t)kFusedRows * p.f_pitchD);
+        p.f_offU = a128f(p.f_offR + (size_t)kFusedRows * pr);
+        p.f_offUp = a128f(p.f_offU + (size_t)kFusedRows * pu);
+        p.f_stage_bytes = a128f(p.f_offUp + (size_t)kFusedRows * pu);
+        p.f_offStats = kFusedCtlBytes + kFusedStages * p.f_stage_bytes;
+        p.f_offBm = p.f_offStats + 2u * kFA * kFusedRows * ng * 8u;
+        p.f_bm_pitch = nblk * 64u + 32u;
+        p.smem_f = p.f_offBm + 2u * kFusedRows * p.f_bm_pitch;
+        const size_t n_rec = 2 + (size_t)(ncol + p.nub_f) * s.N;
+        if (p.smem_f <= smem_cap && kFusedCtlBytes + n_rec * 8 <= p.f_offStats) {
+            p.n_tiles_f = (int)((s.M + kFusedRows - 1) / kFusedRows);
+            long long per_fit_f = std::max<long long>(kMinParts, (long long)h->sm_count / s.n_fits);
+            if (s.max_ctas_per_fit > 0) per_fit_f = std::min<long long>(per_fit_f, s.max_ctas_per_fit);
+            p.n_parts_f = (int)std::min<long long>(per_fit_f, p.n_tiles_f);
+            p.n_groups_f = (p.n_parts_f + kGroup - 1) / kGroup;
+            p.part_stride = std::max(p.part_stride, (int)align_up(n_rec, 2));
+            p.per_fit_red = align_up((size_t)p.part_stride * 8, 256);
+            p.fused_ok = 1;
+        }
+    }
+    const int parts_max = std::max(std::max(p.n_parts, p.n_parts_g), p.n_parts_f), groups_max = std::max(std::max(std::max(p.n_groups, p.n_groups_g), p.n_groups_u), p.n_groups_f);
     // u_inner_kernel records are 8 doubles apart: n_parts_u * 8 <= parts_max * part_stride holds because part_stride >= 2 * 9 * N
 
     // workspace layout
@@ -623,6 +673,26 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
     b->states_dev = reinterpret_cast<FitState*>(base + p.off_states);
     b->gram_ok = p.gram_ok;
     b->engine = p.gram_ok ? DMF_ENGINE_GRAM : DMF_ENGINE_STREAM;      // multiplicity form implies gram (checked above)
+    b->fused_ok = (p.fused_ok && !gather && !n_mult) ? 1 : 0;
+    b->fused_pending = 0;
+    if (b->fused_ok) {
+        b->kb_f = p.kb_f; b->nub_f = p.nub_f; b->s_f = p.s_f; b->smem_f = p.smem_f;
+        FusedArgs& fa = b->fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.g = g;
+        fa.g.n_parts = p.n_parts_f; fa.g.n_groups = p.n_groups_f; fa.g.fit_major = 0; fa.g.multmode = 0;
+        fa.n_tiles = p.n_tiles_f;
+        fa.pitchX = p.f_pitchX; fa.pitchD = p.f_pitchD; fa.offD = p.f_offD; fa.offR = p.f_offR; fa.offU = p.f_offU; fa.offUp = p.f_offUp;
+        fa.stage_bytes = p.f_stage_bytes; fa.offStats = p.f_offStats; fa.offBm = p.f_offBm; fa.bm_pitch = p.f_bm_pitch;
+        fa.rowX_bytes = p.f_rowX; fa.rowD_bytes = p.f_rowD;
+        fused_kern_t kf = by_types_f(s, p.kb_f, p.nub_f, p.s_f);
+        if (!kf || cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_f) != cudaSuccess) {
+            cudaGetLastError();
+            b->fused_ok = 0;
+        } else {
+            b->engine = DMF_ENGINE_FUSED;
+        }
+    }
     if (p.gram_ok) {
         Geom& q = b->gg;
         q = g;
@@ -698,9 +768,15 @@ int dmf_batch_destroy(dmf_batch_t b) {
 
 int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows, int32_t* smem_bytes) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
-    if (ctas_per_fit) *ctas_per_fit = b->g.n_parts;
-    if (tile_rows) *tile_rows = b->g.tile_rows;
-    if (smem_bytes) *smem_bytes = (int32_t)std::max(b->smem_alpha, b->smem_u);
+    if (b->engine == DMF_ENGINE_FUSED) {
+        if (ctas_per_fit) *ctas_per_fit = b->fa.g.n_parts;
+        if (tile_rows) *tile_rows = kFusedRows;
+        if (smem_bytes) *smem_bytes = (int32_t)b->smem_f;
+        return DMF_OK;
+    }
+    if (ctas_per_fit) *ctas_per_fit = b->engine == DMF_ENGINE_GRAM ? b->gg.n_parts : b->g.n_parts;
+    if (tile_rows) *tile_rows = b->engine == DMF_ENGINE_GRAM ? b->gg.tile_rows : b->g.tile_rows;
+    if (smem_bytes) *smem_bytes = b->engine == DMF_ENGINE_GRAM ? (int32_t)std::max(b->smem_rg, b->smem_panel) : (int32_t)std::max(b->smem_alpha, b->smem_u);
     return DMF_OK;
 }
 
@@ -732,7 +808,10 @@ int dmf_pass_fw(dmf_batch_t b, int32_t k_inner, void* stream) {
 
 int dmf_batch_set_engine(dmf_batch_t b, int32_t engine) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
-    if (engine != DMF_ENGINE_STREAM && engine != DMF_ENGINE_GRAM) return fail(DMF_E_ARG, "engine must be DMF_ENGINE_STREAM or DMF_ENGINE_GRAM");
+    if (engine != DMF_ENGINE_STREAM && engine != DMF_ENGINE_GRAM && engine != DMF_ENGINE_FUSED) return fail(DMF_E_ARG, "engine must be DMF_ENGINE_STREAM, DMF_ENGINE_GRAM or DMF_ENGINE_FUSED");
+    if (engine == DMF_ENGINE_FUSED && !b->fused_ok)
+        return fail(DMF_E_SHAPE, "the fused engine needs FP64 storage, n_u <= 2, K <= 8, N <= 256, four U slots, no row gather and a weight pitch of a multiple of 16 bytes");
+    if (b->fused_pending) return fail(DMF_E_STATE, "the cost of the current iterate is pending (dmf_fused_finish) - engines can be switched after it");
     if (engine == DMF_ENGINE_GRAM && !b->gram_ok)
         return fail(DMF_E_SHAPE, "the Gram-form engine supports n_u <= 4 (n_u <= 8 when K <= 6) and needs its tile to fit in shared memory");
     if (engine == DMF_ENGINE_STREAM && b->multmode) return fail(DMF_E_STATE, "fits in multiplicity form run on the Gram-form engine only");
@@ -750,6 +829,7 @@ int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream) {
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
     if (initial) {
         b->t_hi = 0;
+        b->fused_pending = 0;
         if (b->n_active != b->shape.n_fits) { int rc0 = upload_fits(b, nullptr, (cudaStream_t)stream); if (rc0) return rc0; }
     }
     int rc = launch_g(b, k_rowgram(b, initial ? 1 : 0), b->ntc_g, b->smem_rg, initial ? kFlagInitial : 0, 0, tol, 0, 0, 0, 0, (cudaStream_t)stream);
@@ -760,6 +840,7 @@ int dmf_gram_rowgram(dmf_batch_t b, int32_t initial, double tol, void* stream) {
 int dmf_gram_u_inner(dmf_batch_t b, int32_t n_iter2, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->gram_ok) return fail(DMF_E_SHAPE, "no Gram-engine instantiation for this shape");
+    if (b->fused_pending) return fail(DMF_E_STATE, "the row statistics are stale after dmf_fused_outer: dmf_fused_finish first");
     if (n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
     b->t_hi += n_iter2;
     int rc = ensure_mom(b, b->t_hi, (cudaStream_t)stream);
@@ -902,10 +983,56 @@ int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
     return dmf_gram_rowgram(b, 0, tol, stream);
 }
 
+int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->fused_ok) return fail(DMF_E_SHAPE, "no fused-engine instantiation for this shape / layout");
+    if (b->sharded || b->multmode) return fail(DMF_E_STATE, "the fused engine does not run row-sharded or multiplicity-form batches");
+    if (n_iter2 < 1 || n_iter2 > kFusedMaxInner) return fail(DMF_E_ARG, "the fused pass runs 1 .. 64 update_u iterations per visit");
+    b->t_hi += n_iter2;
+    int rc = ensure_mom(b, b->t_hi + n_iter2, (cudaStream_t)stream);
+    if (rc) return rc;
+    fused_kern_t k = by_types_f(b->shape, b->kb_f, b->nub_f, b->s_f);
+    FusedArgs a = b->fa;
+    a.fits = b->fits_dev;
+    a.n_iter2 = n_iter2;
+    a.flags = 0;
+    a.tol = tol;
+    a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
+    k<<<dim3(a.g.n_parts, b->n_active, 1), kFusedThreads, b->smem_f, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    b->fused_pending = 1;
+    return DMF_OK;
+}
+int dmf_fused_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
+    int rc = dmf_fused_pass(b, n_iter2, tol, stream);
+    if (rc) return rc;
+    return dmf_gram_alpha_inner(b, n_iter2, stream);
+}
+int dmf_fused_finish(dmf_batch_t b, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->fused_pending) return DMF_OK;
+    b->fused_pending = 0;
+    return dmf_gram_rowgram(b, 0, tol, stream);          // cost-only use of the rowgram pass: counts the outer iteration, runs the test
+}
+
+// engine actually used for a call with n_iter2 inner iterations
+static int effective_engine(const dmf_batch_s* b, int n_iter2) {
+    if (b->engine == DMF_ENGINE_FUSED && (n_iter2 < 1 || n_iter2 > kFusedMaxInner || b->sharded || b->multmode)) return DMF_ENGINE_GRAM;
+    return b->engine;
+}
+
 int dmf_enqueue_outer(dmf_batch_t b, int32_t n_outer, int32_t n_iter2, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     int rc;
-    if (b->engine == DMF_ENGINE_GRAM) {
+    const int eng = effective_engine(b, n_iter2);
+    if (eng == DMF_ENGINE_FUSED) {        // leaves the cost of the last iterate pending: dmf_fused_finish
+        for (int o = 0; o < n_outer; ++o)
+            if ((rc = dmf_fused_outer(b, n_iter2, tol, stream))) return rc;
+        return DMF_OK;
+    }
+    if (b->fused_pending && (rc = dmf_fused_finish(b, tol, stream))) return rc;
+    if (eng == DMF_ENGINE_GRAM) {
         for (int o = 0; o < n_outer; ++o)
             if ((rc = dmf_gram_outer(b, n_iter2, tol, stream))) return rc;
         return DMF_OK;
@@ -939,7 +1066,9 @@ int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol,
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (n_iter1 < 0 || n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = b->engine == DMF_ENGINE_GRAM ? dmf_gram_init(b, stream) : dmf_pass_init(b, stream);
+    const int eng = effective_engine(b, n_iter2);
+    b->fused_pending = 0;
+    int rc = eng != DMF_ENGINE_STREAM ? dmf_gram_init(b, stream) : dmf_pass_init(b, stream);
     if (rc) return rc;
     // Outer iterations are enqueued in chunks; after each chunk the per-fit `done` flags come back through
     // pinned memory.  Terminated fits skip their launches on the device, so over-enqueueing is harmless.
@@ -949,6 +1078,7 @@ int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol,
         const int todo = std::min(chunk, n_iter1 - issued);
         if ((rc = dmf_enqueue_outer(b, todo, n_iter2, tol, stream))) return rc;
         issued += todo;
+        if (issued == n_iter1 && eng == DMF_ENGINE_FUSED && (rc = dmf_fused_finish(b, tol, stream))) return rc;    // cost of the last iterate
         CUDA_TRY(cudaMemcpyAsync(b->pinned, b->states_dev, sizeof(FitState) * n, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         std::vector<int> active;
@@ -956,7 +1086,7 @@ int dmf_fit_batched(dmf_batch_t b, int32_t n_iter1, int32_t n_iter2, double tol,
             if (b->pinned[i].done == 3) return fail(DMF_E_STATE, "non-finite values reached the simplex projection (fit " + std::to_string(i) + ")");
             if (b->pinned[i].done == 0) active.push_back(i);
         }
-        if (active.empty()) break;
+        if (active.empty()) { b->fused_pending = 0; break; }
         // launch only the still-running fits from now on (terminated fits would return at once, but their CTAs still cost a launch slot)
         if ((int)active.size() != b->n_active && (rc = upload_fits(b, &active, st))) return rc;
         chunk = std::min(chunk * 2, 16);

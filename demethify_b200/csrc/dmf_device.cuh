@@ -26,7 +26,8 @@ struct FitState {
     int u_cur, a_cur;              // ping-pong slots holding the current iterate
     int n_outer, done;             // done: 0 running, 1 converged, 3 numerical failure (NaN in projection)
     int t_u, t_a;                  // inner iterations of update_u / update_alpha executed so far (index into the momentum table)
-    int pad[2];
+    int phase;                     // fused engine: 1 = the cost of the current iterate has not been evaluated yet (dmf_fused.cuh)
+    int pad;
 };
 
 struct FitDev {

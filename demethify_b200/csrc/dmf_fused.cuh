@@ -1,0 +1,562 @@
+// dmf_fused.cuh — "fused" engine: ONE streaming pass over X, d_x, R_trunc, u per OUTER iteration of
+// deconvolution.py:206-221 (SURVEY.md 7.1 #1-#3, 8 d4 "fused outer iteration").
+//
+// The Gram-form engine (dmf_gram.cuh) needs two passes per outer iteration because the panel statistics of the alpha step
+// need the u that the U step produces.  The U step is row-local, so a row tile can go through all three stages on one visit:
+//
+//   A  row statistics   c = x - R_trunc a_k,  b_m = (d o c) a_u^T,  H_m = a_u diag(d_m) a_u^T   (+ sum d c^2 for the cost)
+//   U  n_iter2 update_u iterations per row on (b_m, H_m)  (deconvolution.py:82-89 / :157-164), the row's cost cross terms
+//      -2 u^T b_m + u^T H_m u of the INCOMING iterate, the new (u, u_) written to the other slot pair
+//   C  Gram panel with the NEW u:  G_uk += d (u (x) R_trunc),  G_uu += d (u (x) u),  bx_u += (d o x) u
+//
+// The cost of the incoming iterate (u_k, alpha_k) is complete at the end of the pass; the last CTA then runs the termination
+// test of deconvolution.py:218-221 for outer iteration k and COMMITS the U step (flips the slot pair, publishes the panel,
+// updates l_h, a1) only if the fit did not just terminate - so a terminated fit returns exactly the iterate whose cost passed
+// the test.  alpha_inner_kernel (dmf_gram.cuh) follows and produces alpha_{k+1}.
+//
+// One CTA = 18 warps with three roles (warp specialised, tiles flow A -> U -> C through a 5-stage shared-memory ring):
+//   8 A-warps   each owns 8 S samples; c comes from FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, SASS DMMA) with the samples on
+//               the M side, so a lane owns ONE sample and two rows per 8 x 8 block and keeps only its own alpha values
+//   2 U-warps   lane = row; they also drive the TMA ring (per-row bulk copies into bank-conflict-free padded rows)
+//   8 C-warps   the panel is the GEMM  [N x rows] (d) x [rows x NCOL] (u (x) [R_trunc | u]) : DMMA again, accumulators stay in
+//               the MMA C fragments for the whole kernel; bx_u on the FMA pipe
+// FP64 only (tcgen05 has no FP64 kind; DMMA and DFMA share one pipe at 64 FMA/clk/SM - tools/fp64_peak.cu), which is the
+// binding roofline of this kernel: ~39 FMA per (row, sample) against 10 bytes.
+#pragma once
+#include "dmf_gram.cuh"
+
+namespace dmf {
+
+constexpr int kFA = 8, kFC = 8, kFU = 4;
+constexpr int kFusedThreads = (kFA + kFC + kFU) * 32;
+constexpr int kFusedRows = 16;           // rows per tile (two 8-row MMA blocks, four 4-row k-steps)
+constexpr int kFusedStages = 5;
+constexpr int kFusedAhead = 3;           // tiles requested ahead of the U stage
+constexpr int kFusedMaxInner = 64;       // beyond this the U-warps (16 rows at a time) would bound the pass: Gram engine instead
+constexpr unsigned kFusedCtlBytes = 1024;
+
+struct FusedArgs {
+    Geom g;                  // problem sizes, pitches, n_parts / n_groups / part_stride of this launch
+    const FitDev* fits;
+    int n_iter2, flags;
+    double tol;
+    const double* mom_a;
+    const double* mom_m;
+    int n_tiles;
+    unsigned pitchX, pitchD;                          // bytes per row inside a stage (padded)
+    unsigned offD, offR, offU, offUp, stage_bytes;    // stage layout, X at 0
+    unsigned offStats, offBm;                         // from the start of dynamic shared memory
+    unsigned bm_pitch;                                // bytes per row of the u (x) [R_trunc | u] table
+    unsigned rowX_bytes, rowD_bytes;                  // bytes copied per row
+};
+typedef void (*fused_kern_t)(const FusedArgs);
+
+struct FusedCtl {
+    unsigned long long full[8], empty[8], stats[8], udone[8];
+    double wsum[2][kFA + kFC + kFU];
+    int flag, commit;
+};
+static_assert(sizeof(FusedCtl) <= kFusedCtlBytes, "fused control block too large");
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename WT>
+__device__ __forceinline__ double lds_weight(uint32_t addr);
+template <>
+__device__ __forceinline__ double lds_weight<uint16_t>(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (double)(unsigned)v;
+}
+template <>
+__device__ __forceinline__ double lds_weight<double>(uint32_t addr) {
+    double v;
+    lds1(addr, v);
+    return v;
+}
+
+// sum over the 8 lanes that share (lane & 3): halving butterfly over lane bits 2, 3, 4.  NV is a multiple of 8; on return lane
+// holds the totals of slots base .. base + NV / 8 - 1 in v[0 .. NV / 8).
+template <int NV>
+__device__ __forceinline__ int reduce_over_groups(double (&v)[NV], int lane) {
+    static_assert(NV % 8 == 0, "NV must be a multiple of 8");
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int o = 4 << s;
+        const int half = NV >> (s + 1);
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        base += up ? half : 0;
+    }
+    return base;
+}
+
+template <typename WT, int KB, int NUB, int S>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const FusedArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int KS = (KB + 3) / 4;                  // k-steps of the c = x - R_trunc a_k MMA
+    constexpr int NG = ng_of(NUB);
+    constexpr int NTRI = NG - NUB;
+    constexpr int NCOL = NUB * KB + NTRI;             // panel columns: u_q R_k (q major), then the upper triangle of u u^T
+    constexpr int NBLK = (NCOL + 7) / 8;
+    constexpr int NS = kFusedStages, TR = kFusedRows;
+    constexpr int NV = ((2 * 2 * NG + 7) / 8) * 8;    // per-lane row partials of one tile: 2 row blocks x 2 rows x NG, padded
+    const Geom& g = a.g;
+    const FitDev f = a.fits[fit_id(g)];
+    FitState* st = f.st;
+    if (st->done) return;
+    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gi = lane >> 2, ti = lane & 3;
+    const uint32_t smem32 = smem_u32(smem);
+    const uint32_t stages32 = smem32 + kFusedCtlBytes;
+    const int part = part_id(g);
+    const int n_my = (a.n_tiles > part) ? (a.n_tiles - part + g.n_parts - 1) / g.n_parts : 0;
+    const int ucur = st->u_cur, acur = st->a_cur;
+    const double* Acur = reinterpret_cast<const double*>(f.A) + (size_t)acur * g.Kt * g.N;
+    const int N = g.N, K = g.K;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 1);
+            mbar_init(smem_u32(&ctl->empty[s]), kFC);
+            mbar_init(smem_u32(&ctl->stats[s]), kFA);
+            mbar_init(smem_u32(&ctl->udone[s]), 1);
+        }
+        mbar_fence_init();
+    }
+    // every stage starts as finite data: rows beyond the end of the last tile and samples beyond N are weighted with d = 0,
+    // which only works on finite values
+    {
+        const unsigned n16 = (a.offStats - kFusedCtlBytes) / 16;
+        for (unsigned i = tid; i < n16; i += kFusedThreads)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(stages32 + i * 16u), "r"(0u) : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    auto tile_rows = [&](int it) {
+        const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
+        const long long left = g.M - r0;
+        return (int)(left < TR ? left : TR);
+    };
+
+    double cost = 0.0, ssq = 0.0;       // per-thread partials (A-warps: sum d c^2; U-warps: cross terms, ||u_new||^2)
+    // C-warp state (declared here because it is stored after the CTA-wide barrier that follows the role loops)
+    double pacc[S][NBLK][2], paccx[S][NUB];
+    int jcC[S];
+    bool validC[S];
+
+    if (warp >= kFA + kFC) {
+        // =========================================================================== U-warps (+ TMA producer)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int uw = warp - (kFA + kFC);
+        const char* Ucur_g = f.U + (size_t)ucur * g.uslot_bytes;
+        const char* Uprv_g = f.U + (size_t)(ucur ^ 1) * g.uslot_bytes;
+        double* Unew_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 2) * g.uslot_bytes);
+        double* Unpv_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 3) * g.uslot_bytes);
+        auto produce = [&](int it) {
+            const int s = it % NS;
+            const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
+            const int nrows = tile_rows(it);
+            const uint32_t full = smem_u32(&ctl->full[s]);
+            const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
+            const unsigned rbytes = (unsigned)(g.ldr * 8), ubytes = (unsigned)(g.ldu * 8);
+            if (lane == 0) {
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(full, (unsigned)nrows * (a.rowX_bytes + a.rowD_bytes + rbytes + 2u * ubytes));
+            }
+            __syncwarp();
+            if (lane < nrows) {
+                bulk_g2s(sb + (uint32_t)lane * a.pitchX, f.X + (r0 + lane) * (long long)a.rowX_bytes, a.rowX_bytes, full);
+                bulk_g2s(sb + a.offD + (uint32_t)lane * a.pitchD, f.D + (r0 + lane) * (long long)a.rowD_bytes, a.rowD_bytes, full);
+            } else if (lane == 16) {
+                if (K) bulk_g2s(sb + a.offR, f.Rk + r0 * (long long)rbytes, (unsigned)nrows * rbytes, full);
+            } else if (lane == 17) {
+                bulk_g2s(sb + a.offU, Ucur_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
+            } else if (lane == 18) {
+                bulk_g2s(sb + a.offUp, Uprv_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
+            }
+            __syncwarp();
+        };
+        const int n2 = a.n_iter2;
+        const double l_w = st->l_w, lwo_in = st->l_w_old;
+        const double inv_lw = 1.0 / l_w;       // as u_inner_kernel: reciprocal multiply (<= 1 ulp of a ~1e-4-sized step vs the division of :88)
+        const double* mm = a.mom_m + st->t_u;
+        const double cap0 = 0.9999 * sqrt(lwo_in / l_w), cap1 = 0.9999 * sqrt(l_w / l_w);
+        const bool at_current = (g.mode == 2);
+        if (uw == 0)
+            for (int t = 0; t < kFusedAhead && t < n_my; ++t) produce(t);
+        for (int it = uw; it < n_my; it += kFU) {
+            // The stage of tile it + 3 held tile it - 2: free once the C-warps released it, which also frees Bm[it & 1].  Requested
+            // here when that already happened, else after the iterations below (they do not need it), so that the U stage of
+            // this tile overlaps the C stage of the two tiles before it.
+            const int itp = it + kFusedAhead;
+            const uint32_t ebar = smem_u32(&ctl->empty[itp % NS]);
+            const unsigned epar = (((unsigned)(itp / NS)) & 1u) ^ 1u;
+            const bool requested = __shfl_sync(0xffffffffu, (int)mbar_try_wait(ebar, epar), 0) != 0;      // one decision for the warp
+            if (requested && itp < n_my) produce(itp);
+            const int s = it % NS;
+            const unsigned ph = ((unsigned)(it / NS)) & 1u;
+            mbar_wait(smem_u32(&ctl->stats[s]), ph);
+            mbar_wait(smem_u32(&ctl->full[s]), ph);        // complete long ago; orders this warp after the bulk copies
+            const int nrows = tile_rows(it);
+            const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
+            const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
+            const bool live = lane < nrows;
+            const int row = lane < TR ? lane : 0;
+            // row statistics: the 8 A-warp partials in warp order
+            double v[NG];
+#pragma unroll
+            for (int i = 0; i < NG; ++i) v[i] = 0.0;
+            {
+                const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFA * TR * NG * 8u) + (uint32_t)row * (NG * 8u);
+#pragma unroll
+                for (int w = 0; w < kFA; ++w)
+#pragma unroll
+                    for (int i = 0; i < NG; ++i) {
+                        double t;
+                        lds1(sbase + (uint32_t)w * (TR * NG * 8u) + (uint32_t)i * 8u, t);
+                        v[i] += t;
+                    }
+            }
+            double u[NUB], up[NUB];
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                lds1(sb + a.offU + (uint32_t)row * (unsigned)(g.ldu * 8) + (uint32_t)q * 8u, u[q]);
+                lds1(sb + a.offUp + (uint32_t)row * (unsigned)(g.ldu * 8) + (uint32_t)q * 8u, up[q]);
+            }
+            if (live) {      // cost of the incoming iterate: -2 u^T b + u^T H u of this row (rowgram4_kernel, writer lanes)
+                double ct = 0.0;
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    double hq = 0.0;
+#pragma unroll
+                    for (int q2 = 0; q2 < NUB; ++q2) hq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], u[q2], hq);
+                    ct = fma(u[q], hq - 2.0 * v[q], ct);
+                }
+                cost += ct;
+            }
+            for (int itn = 0; itn < n2; ++itn) {           // update_u, deconvolution.py:82-89 (same arithmetic as u_inner_kernel)
+                const double beta = fmin(__ldg(mm + itn), itn == 0 ? cap0 : cap1);
+                double ut[NUB], ug[NUB];
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    ut[q] = u[q] + beta * (u[q] - up[q]);
+                    ug[q] = at_current ? u[q] : ut[q];
+                }
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    double sq = 0.0;
+#pragma unroll
+                    for (int q2 = 0; q2 < NUB; ++q2) sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], ug[q2], sq);
+                    const double gq = v[q] - sq;
+                    double un = ut[q] + gq * inv_lw;
+                    un = clip01(un);
+                    up[q] = u[q];
+                    u[q] = un;
+                }
+            }
+            if (!requested) {
+                mbar_wait(ebar, epar);
+                if (itp < n_my) produce(itp);
+            }
+            // new iterate: global (other slot pair), the stage (bx_u of the C-warps) and the panel's B operand
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    if (q < g.nu) {
+                        Unew_g[(size_t)(r0 + lane) * g.ldu + q] = u[q];
+                        Unpv_g[(size_t)(r0 + lane) * g.ldu + q] = up[q];
+                        ssq = fma(u[q], u[q], ssq);
+                    }
+                }
+            }
+            if (lane < TR) {
+                const uint32_t bm = smem32 + a.offBm + (uint32_t)(it & 1) * (TR * a.bm_pitch) + (uint32_t)lane * a.bm_pitch;
+                double un[NUB];
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) {
+                    un[q] = (live && q < g.nu) ? u[q] : 0.0;
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + a.offU + (uint32_t)lane * (unsigned)(g.ldu * 8) + (uint32_t)q * 8u), "d"(un[q]) : "memory");
+                }
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    double rk = 0.0;
+                    if (k < K) lds1(sb + a.offR + (uint32_t)lane * (unsigned)(g.ldr * 8) + (uint32_t)k * 8u, rk);
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q)
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(bm + (uint32_t)(q * KB + k) * 8u), "d"(un[q] * rk) : "memory");
+                }
+#pragma unroll
+                for (int q = 0; q < NUB; ++q)
+#pragma unroll
+                    for (int q2 = q; q2 < NUB; ++q2)
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(bm + (uint32_t)(NUB * KB + tri_index(q, q2, NUB)) * 8u), "d"(un[q] * un[q2]) : "memory");
+#pragma unroll
+                for (int c = NCOL; c < NBLK * 8; ++c)
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(bm + (uint32_t)c * 8u), "d"(0.0) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->udone[s]));
+        }
+    } else if (warp < kFA) {
+        // =========================================================================== A-warps: row statistics
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        double na[S][KS > 0 ? KS : 1], au[S][NUB], P[S][NTRI];
+        int jc[S];
+        bool valid[S];
+#pragma unroll
+        for (int sb = 0; sb < S; ++sb) {
+            const int j = 8 * (warp * S + sb) + gi;
+            valid[sb] = j < N;
+            jc[sb] = valid[sb] ? j : 0;
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const int k = 4 * kk + ti;
+                na[sb][kk] = (valid[sb] && k < K) ? -Acur[(size_t)k * N + j] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) au[sb][q] = (valid[sb] && q < g.nu) ? Acur[(size_t)(K + q) * N + j] : 0.0;
+#pragma unroll
+            for (int q = 0; q < NUB; ++q)
+#pragma unroll
+                for (int q2 = q; q2 < NUB; ++q2) P[sb][tri_index(q, q2, NUB)] = au[sb][q] * au[sb][q2];
+        }
+        const unsigned rpitch = (unsigned)(g.ldr * 8);
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % NS;
+            const unsigned ph = ((unsigned)(it / NS)) & 1u;
+            mbar_wait(smem_u32(&ctl->full[s]), ph);
+            if (it >= 2) mbar_wait(smem_u32(&ctl->udone[(it - 2) % NS]), ((unsigned)((it - 2) / NS)) & 1u);     // stats[it & 1] free
+            const int nrows = tile_rows(it);
+            const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
+            double acc[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+                const int ra = 8 * rb + ti, rbw = ra + 4;          // the two rows of this lane's C fragment
+                const bool la = ra < nrows, lb = rbw < nrows;
+                // B operand: R_trunc[row_of_n(gi)][4 kk + ti], MMA column n = 2 t + e  <->  tile row 8 rb + t + 4 e
+                double rfrag[KS > 0 ? KS : 1];
+                const int rown = 8 * rb + (gi >> 1) + 4 * (gi & 1);
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    const int k = 4 * kk + ti;
+                    double t = 0.0;
+                    if (k < K) lds1(sb32 + a.offR + (uint32_t)rown * rpitch + (uint32_t)k * 8u, t);
+                    rfrag[kk] = t;
+                }
+#pragma unroll
+                for (int sb = 0; sb < S; ++sb) {
+                    double c0, c1;
+                    lds1(sb32 + (uint32_t)ra * a.pitchX + (uint32_t)jc[sb] * 8u, c0);
+                    lds1(sb32 + (uint32_t)rbw * a.pitchX + (uint32_t)jc[sb] * 8u, c1);
+                    double d0 = lds_weight<WT>(sb32 + a.offD + (uint32_t)ra * a.pitchD + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
+                    double d1 = lds_weight<WT>(sb32 + a.offD + (uint32_t)rbw * a.pitchD + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
+                    if (!valid[sb]) { c0 = 0.0; c1 = 0.0; }
+                    if (!(valid[sb] && la)) d0 = 0.0;
+                    if (!(valid[sb] && lb)) d1 = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, na[sb][kk], rfrag[kk]);     // c = x - R_trunc a_k
+                    const double z0 = d0 * c0, z1 = d1 * c1;
+                    cost = fma(z0, c0, cost);
+                    cost = fma(z1, c1, cost);
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q) {
+                        acc[(rb * 2 + 0) * NG + q] = fma(z0, au[sb][q], acc[(rb * 2 + 0) * NG + q]);
+                        acc[(rb * 2 + 1) * NG + q] = fma(z1, au[sb][q], acc[(rb * 2 + 1) * NG + q]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < NTRI; ++e) {
+                        acc[(rb * 2 + 0) * NG + NUB + e] = fma(d0, P[sb][e], acc[(rb * 2 + 0) * NG + NUB + e]);
+                        acc[(rb * 2 + 1) * NG + NUB + e] = fma(d1, P[sb][e], acc[(rb * 2 + 1) * NG + NUB + e]);
+                    }
+                }
+            }
+            // sum over the 8 samples of a block row (lanes sharing ti), then one partial per (warp, row, value)
+            const int base = reduce_over_groups<NV>(acc, lane);
+            const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFA * TR * NG * 8u) + (uint32_t)warp * (TR * NG * 8u);
+#pragma unroll
+            for (int i = 0; i < NV / 8; ++i) {
+                const int slot = base + i;
+                if (slot < 4 * NG) {
+                    const int re = slot / NG, vi = slot - re * NG;       // re = rb * 2 + e
+                    const int row = 8 * (re >> 1) + ti + 4 * (re & 1);
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbase + (uint32_t)(row * NG + vi) * 8u), "d"(acc[i]) : "memory");
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->stats[s]));
+        }
+    } else {
+        // =========================================================================== C-warps: Gram panel with the new u
+        const int cw = warp - kFA;
+#pragma unroll
+        for (int mb = 0; mb < S; ++mb) {
+            const int j = 8 * (cw * S + mb) + gi;
+            validC[mb] = j < N;
+            jcC[mb] = validC[mb] ? j : 0;
+#pragma unroll
+            for (int nb = 0; nb < NBLK; ++nb) { pacc[mb][nb][0] = 0.0; pacc[mb][nb][1] = 0.0; }
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) paccx[mb][q] = 0.0;
+        }
+        const unsigned upitch = (unsigned)(g.ldu * 8);
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % NS;
+            const unsigned ph = ((unsigned)(it / NS)) & 1u;
+            mbar_wait(smem_u32(&ctl->udone[s]), ph);
+            mbar_wait(smem_u32(&ctl->full[s]), ph);
+            const int nrows = tile_rows(it);
+            const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
+            const uint32_t bm = smem32 + a.offBm + (uint32_t)(it & 1) * (TR * a.bm_pitch);
+#pragma unroll
+            for (int ks = 0; ks < TR / 4; ++ks) {
+                const int row = 4 * ks + ti;
+                const bool lrow = row < nrows;
+                double bfrag[NBLK], un[NUB];
+#pragma unroll
+                for (int nb = 0; nb < NBLK; ++nb) lds1(bm + (uint32_t)row * a.bm_pitch + (uint32_t)(8 * nb + gi) * 8u, bfrag[nb]);
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
+#pragma unroll
+                for (int mb = 0; mb < S; ++mb) {
+                    double x;
+                    lds1(sb32 + (uint32_t)row * a.pitchX + (uint32_t)jcC[mb] * 8u, x);
+                    double d = lds_weight<WT>(sb32 + a.offD + (uint32_t)row * a.pitchD + (uint32_t)jcC[mb] * (unsigned)sizeof(WT));
+                    if (!(validC[mb] && lrow)) { d = 0.0; x = 0.0; }
+                    const double dx = d * x;
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q) paccx[mb][q] = fma(dx, un[q], paccx[mb][q]);
+#pragma unroll
+                    for (int nb = 0; nb < NBLK; ++nb) dmma884(pacc[mb][nb][0], pacc[mb][nb][1], d, bfrag[nb]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[s]));
+        }
+    }
+    __syncthreads();
+    if (warp >= kFA && warp < kFA + kFC) {
+        const int cw = warp - kFA;
+        // CTA record: [cost, ||u||^2, panel NCOL x N, bx NUB x N] - the stage ring is free once every role left its loop
+        double* rec = reinterpret_cast<double*>(smem + kFusedCtlBytes);
+#pragma unroll
+        for (int mb = 0; mb < S; ++mb) {
+            const int j = 8 * (cw * S + mb) + gi;
+#pragma unroll
+            for (int nb = 0; nb < NBLK; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * nb + 2 * ti + e;
+                    if (validC[mb] && c < NCOL) rec[2 + (size_t)c * N + j] = pacc[mb][nb][e];
+                }
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                double t = paccx[mb][q];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if (validC[mb] && ti == 0) rec[2 + (size_t)(NCOL + q) * N + j] = t;
+            }
+        }
+    }
+    // scalar partials: warp sums, then the warps in order
+    {
+        double c = cost, q = ssq;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) { ctl->wsum[0][warp] = c; ctl->wsum[1][warp] = q; }
+    }
+    __syncthreads();
+    double* rec = reinterpret_cast<double*>(smem + kFusedCtlBytes);
+    if (tid == 0) {
+        double c = 0.0, q = 0.0;
+        for (int w = 0; w < kFA + kFC + kFU; ++w) { c += ctl->wsum[0][w]; q += ctl->wsum[1][w]; }
+        rec[0] = c;
+        rec[1] = q;
+    }
+    __syncthreads();
+    const int n = 2 + (NCOL + NUB) * N;
+    {
+        double* p = f.part + (size_t)part * g.part_stride;
+        for (int e = tid; e < n; e += kFusedThreads) p[e] = rec[e];
+    }
+    if (!hier_reduce(g, f, f.red, n, &ctl->flag)) return;
+    __threadfence();
+    __syncthreads();
+    // ------------------------------------------------------------------------------- last CTA of the fit: test, then commit
+    if (tid == 0) {
+        const double cf = f.red[0], su = f.red[1];
+        int commit = 1;
+        if (a.flags & kFlagPartial) {
+            // CpG rows sharded over GPUs: publish this GPU's sums; alpha_inner_kernel tests and commits on the all-reduced sums
+            f.scal[0] = cf;
+            f.scal[4] = su;
+        } else {
+            if (st->phase == 1) {              // the incoming iterate closes an outer iteration: deconvolution.py:218-221
+                const double prev = st->cf;
+                st->cf_prev = prev;
+                st->cf = cf;
+                const int no = st->n_outer + 1;
+                st->n_outer = no;
+                if (f.trace && no < f.trace_cap) f.trace[no] = cf;
+                st->phase = 0;
+                if (fabs(cf - prev) < a.tol) { st->done = 1; commit = 0; }
+                if (!(cf == cf)) { st->done = 3; commit = 0; }
+            }
+            if (commit) {
+                const int t0 = st->t_u, n2 = a.n_iter2;
+                st->u_cur = ucur ^ 2;
+                st->a1 = a.mom_a[t0 + n2];
+                st->t_u = t0 + n2;
+                if (n2 > 0) st->l_w_old = st->l_w;               // deconvolution.py:89
+                st->ssq_u = su;
+                const double nr = sqrt(st->ssq_rk + su);
+                st->l_h = (nr * nr) * st->dmax2;                 // deconvolution.py:212
+                st->phase = 1;
+            }
+        }
+        ctl->commit = commit;
+    }
+    __syncthreads();
+    if (!ctl->commit) return;
+    for (int e = tid; e < (NCOL + NUB) * N; e += kFusedThreads) {
+        const int c = e / N, j = e - c * N;
+        const double v = f.red[2 + e];
+        if (c >= NCOL) {
+            const int q = c - NCOL;
+            if (q < g.nu) f.gbx[(size_t)(K + q) * N + j] = v;
+        } else if (c < NUB * KB) {
+            const int q = c / KB, k = c - q * KB;
+            if (q < g.nu && k < K) {
+                f.gram[((size_t)(K + q) * g.Kt + k) * N + j] = v;
+                f.gram[((size_t)k * g.Kt + (K + q)) * N + j] = v;
+            }
+        } else {
+            int e2 = c - NUB * KB, q = 0;
+            while (e2 >= NUB - q) { e2 -= NUB - q; ++q; }
+            const int q2 = q + e2;
+            if (q2 < g.nu) {
+                f.gram[((size_t)(K + q) * g.Kt + (K + q2)) * N + j] = v;
+                f.gram[((size_t)(K + q2) * g.Kt + (K + q)) * N + j] = v;
+            }
+        }
+    }
+}
+
+}  // namespace dmf

@@ -71,11 +71,13 @@ __device__ __forceinline__ void cost_state_update(const Geom& g, const FitDev& f
         st->n_outer = 0;
         st->t_u = 0;
         st->t_a = 0;
+        st->phase = 0;
         if (f.trace && f.trace_cap > 0) f.trace[0] = cf;
     } else {
         const double prev = st->cf;
         st->cf_prev = prev;
         st->cf = cf;
+        st->phase = 0;                                 // the cost of the current iterate is known (dmf_fused.cuh)
         const int n = st->n_outer + 1;
         st->n_outer = n;
         if (f.trace && n < f.trace_cap) f.trace[n] = cf;

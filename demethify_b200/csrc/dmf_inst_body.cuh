@@ -3,6 +3,7 @@
 #include "dmf_kernels.cuh"
 #include "dmf_wls.cuh"
 #include "dmf_gram.cuh"
+#include "dmf_fused.cuh"
 namespace dmf {
 #define DMF_CAT2(a, b) a##b
 #define DMF_CAT(a, b) DMF_CAT2(a, b)
@@ -78,5 +79,23 @@ kern_t DMF_CAT(pick_ainner_, DMF_TAG)(int ktb, int, int) {
     if (ktb == 32) return alpha_inner_kernel<DMF_T, 32>;
     return nullptr;
 }
+// fused engine (dmf_fused.cuh): FP64 storage only; (known bucket, unknown types, 8-sample blocks per warp)
+template <typename T, typename WT>
+struct FusedPick {
+    static fused_kern_t get(int, int, int) { return nullptr; }
+};
+template <typename WT>
+struct FusedPick<double, WT> {
+    static fused_kern_t get(int kb, int nub, int s) {
+#define DMF_F(KB_, NUB_, S_) \
+    if (kb == KB_ && nub == NUB_ && s == S_) return fused_outer_kernel<WT, KB_, NUB_, S_>;
+#define DMF_FS(KB_, NUB_) DMF_F(KB_, NUB_, 1) DMF_F(KB_, NUB_, 2) DMF_F(KB_, NUB_, 4)
+        DMF_FS(0, 1) DMF_FS(0, 2) DMF_FS(4, 1) DMF_FS(4, 2) DMF_FS(6, 1) DMF_FS(6, 2) DMF_FS(8, 1) DMF_FS(8, 2)
+#undef DMF_FS
+#undef DMF_F
+        return nullptr;
+    }
+};
+fused_kern_t DMF_CAT(pick_fused_, DMF_TAG)(int kb, int nub, int s) { return FusedPick<DMF_T, DMF_WT>::get(kb, nub, s); }
 wls_kern_t DMF_CAT(pick_wls_, DMF_TAG)() { return wls_moments_kernel<DMF_T, DMF_WT>; }
 }  // namespace dmf

@@ -15,6 +15,10 @@ from . import _lib, get_engine, get_precision
 
 _handles = {}
 
+# FitBatch gives the fused engine its four U slots wherever the shape qualifies; tests switch this off to exercise the
+# Gram-form engine on the same shapes
+FUSED_SLOTS = True
+
 
 def _handle(device_index):
     if device_index not in _handles:
@@ -88,7 +92,7 @@ class DeviceProblem:
         self.dtype = _tdtype(self.precision)
         X = to_device(X, self.dtype, self.device)
         self.M, self.N = X.shape
-        self.ldx = _even(self.N)
+        self.ldx = (self.N + 7) // 8 * 8            # rows of X (and of the u16 weights) start 16-byte aligned: per-row bulk copies
         self.X = _pad_cols(X, self.ldx)
         self.K = 0
         self.Rk = None
@@ -189,7 +193,9 @@ class FitBatch:
         # ping-pong buffers: both slots start at the initial iterate (u_ = u.copy(), deconvolution.py:194-195)
         self.ldu = _even(self.n_u)
         self.u_slot = (self.M * self.ldu + 31) // 32 * 32          # slot stride keeps bulk copies 16-byte aligned
-        self.U = torch.zeros((self.n_fits, 2, self.u_slot), dtype=dt, device=dev)
+        # the fused engine writes the new (u, u_) pair next to the current one: 4 slots where it can apply
+        self.u_slots = 4 if (FUSED_SLOTS and dt == torch.float64 and self.n_u <= 2 and rows is None and mult is None) else 2
+        self.U = torch.zeros((self.n_fits, self.u_slots, self.u_slot), dtype=dt, device=dev)
         self.A = torch.empty((self.n_fits, 2, self.Kt, self.N), dtype=dt, device=dev)
         if isinstance(U0, torch.Tensor) and U0.ndim == 3:
             # stacked initial iterates (n_fits, M, n_u) / (n_fits, Kt, N): a handful of copies for the whole batch
@@ -227,7 +233,7 @@ class FitBatch:
         self.shape = _lib.Shape(M=self.M, N=self.N, K=self.K, n_u=self.n_u,
                                 dtype=_lib.DMF_F64 if dt == torch.float64 else _lib.DMF_F32, wtype=p0.wtype, mode=mode,
                                 n_fits=self.n_fits, max_ctas_per_fit=max_ctas_per_fit, ldx=p0.ldx, ldd=p0.ldx, ldr=_even(self.K),
-                                ldu=self.ldu, u_slot=self.u_slot)
+                                ldu=self.ldu, u_slot=self.u_slot, u_slots=self.u_slots)
         nbytes = C.c_size_t()
         _lib.check(lib.dmf_batch_workspace_bytes(self.h, C.byref(self.shape), C.byref(nbytes)))
         self.ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
@@ -250,13 +256,14 @@ class FitBatch:
         _lib.check(lib.dmf_batch_create(self.h, C.byref(self.shape), descs, C.c_void_p(ws_ptr), nbytes.value, _stream_ptr(), C.byref(self.b)))
         engine = engine or get_engine()
         if engine != "auto":
-            _lib.check(lib.dmf_batch_set_engine(self.b, _lib.DMF_ENGINE_GRAM if engine == "gram" else _lib.DMF_ENGINE_STREAM))
+            _lib.check(lib.dmf_batch_set_engine(self.b, {"gram": _lib.DMF_ENGINE_GRAM, "stream": _lib.DMF_ENGINE_STREAM,
+                                                         "fused": _lib.DMF_ENGINE_FUSED}[engine]))
 
     @property
     def engine(self):
         e = C.c_int32()
         _lib.check(_lib.lib().dmf_batch_get_engine(self.b, C.byref(e)))
-        return "gram" if e.value == _lib.DMF_ENGINE_GRAM else "stream"
+        return {_lib.DMF_ENGINE_GRAM: "gram", _lib.DMF_ENGINE_FUSED: "fused"}.get(e.value, "stream")
 
     def u_view(self, i, slot):
         return self.U[i, slot, :self.M * self.ldu].view(self.M, self.ldu)[:, :self.n_u]
@@ -295,6 +302,16 @@ class FitBatch:
 
     def gram_outer(self, n_iter2, tol):
         _lib.check(_lib.lib().dmf_gram_outer(self.b, int(n_iter2), float(tol), _stream_ptr()))
+
+    # -- fused engine steps
+    def fused_pass(self, n_iter2, tol):
+        _lib.check(_lib.lib().dmf_fused_pass(self.b, int(n_iter2), float(tol), _stream_ptr()))
+
+    def fused_outer(self, n_iter2, tol):
+        _lib.check(_lib.lib().dmf_fused_outer(self.b, int(n_iter2), float(tol), _stream_ptr()))
+
+    def fused_finish(self, tol):
+        _lib.check(_lib.lib().dmf_fused_finish(self.b, float(tol), _stream_ptr()))
 
     def enqueue_outer(self, n_outer, n_iter2, tol):
         _lib.check(_lib.lib().dmf_enqueue_outer(self.b, int(n_outer), int(n_iter2), float(tol), _stream_ptr()))

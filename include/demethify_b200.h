@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DMF_ABI_VERSION 3
+#define DMF_ABI_VERSION 4
 
 enum { DMF_OK = 0, DMF_E_ARG = 1, DMF_E_CUDA = 2, DMF_E_SHAPE = 3, DMF_E_STATE = 4 };
 
@@ -47,8 +47,12 @@ enum {
 /* how the inner iterations are executed (results agree to ~1e-15 on alpha; both are pinned by the same golden vectors)
  *   STREAM: one launch per reference inner iteration, each a streaming pass over X, d_x (dmf_pass_u / _alpha / _fw / _cost)
  *   GRAM  : per outer iteration two streaming passes build the sufficient statistics of the U step (per CpG row) and of the
- *           alpha step (per sample); the n_iter2 inner iterations then run on those (dmf_gram_*).  Default when n_u <= 4, or n_u <= 8 with K <= 6. */
-enum { DMF_ENGINE_STREAM = 0, DMF_ENGINE_GRAM = 1 };
+ *           alpha step (per sample); the n_iter2 inner iterations then run on those (dmf_gram_*).  n_u <= 4, or n_u <= 8 with K <= 6.
+ *   FUSED : ONE streaming pass per outer iteration (dmf_fused_outer): a row tile goes through row statistics -> the n_iter2
+ *           update_u iterations -> the Gram panel with the new u on a single visit; the cost of the incoming iterate is taken on
+ *           the same visit and the U step is committed only if the fit did not just terminate.  FP64 storage, n_u <= 2, K <= 8,
+ *           N <= 256, n_iter2 <= 64, four U slots (dmf_shape_t.u_slots); the default where it applies. */
+enum { DMF_ENGINE_STREAM = 0, DMF_ENGINE_GRAM = 1, DMF_ENGINE_FUSED = 2 };
 
 typedef struct dmf_shape {
     int64_t M;      /* CpG rows                         */
@@ -66,7 +70,10 @@ typedef struct dmf_shape {
     int64_t ldd;    /* row pitch of D  (>= N, even)      */
     int64_t ldr;    /* row pitch of Rk (>= K, even)      */
     int64_t ldu;    /* row pitch of U  (>= n_u, even)    */
-    int64_t u_slot; /* elements between the two ping-pong slots of U (>= M*ldu, u_slot*sizeof(T) % 16 == 0) */
+    int64_t u_slot; /* elements between consecutive slots of U (>= M*ldu, u_slot*sizeof(T) % 16 == 0) */
+    int32_t u_slots; /* slots of U behind dmf_fit_desc_t.U: 2 (or 0), or 4 - the FUSED engine writes the new (u, u_) pair next to
+                        the current one and needs 4; slots 2 and 3 must start zeroed */
+    int32_t reserved;
 } dmf_shape_t;
 
 /* Per-fit buffers (host array of n_fits of these is passed to dmf_batch_create). */
@@ -77,7 +84,7 @@ typedef struct dmf_fit_desc {
     const int32_t* rows;   /* optional gather: fit row p reads source row rows[p] of X, D, Rk
                               (bootstrap.py:28 resample); NULL = identity.  U stays position-indexed.
                               With mult / offs (below): the sorted position -> source row map, nothing is gathered */
-    void* U;               /* two slots of M x n_u (pitch ldu), shape.u_slot elements apart; BOTH hold the initial u */
+    void* U;               /* shape.u_slots slots of M x n_u (pitch ldu), shape.u_slot elements apart; slots 0 and 1 BOTH hold the initial u */
     void* A;               /* [2][Kt][N]; BOTH slots hold the initial alpha (alpha_ = alpha.copy())    */
     const double* purity;  /* [N] internal purity vector (DMF_MODE_PURITY) else NULL            */
     double* cost_trace;    /* optional [trace_cap] cost after every outer iteration, or NULL    */
@@ -102,7 +109,7 @@ typedef struct dmf_fit_state {
     double dmax;       /* max d_x over the fit's rows                                 */
     int32_t n_outer;   /* outer iterations executed                                   */
     int32_t done;      /* 1 once |cf-cf_0| < tol fired                                */
-    int32_t u_slot;    /* which slot of U / A holds the current iterate               */
+    int32_t u_slot;    /* which slot of U (0..3) / A (0..1) holds the current iterate   */
     int32_t a_slot;
 } dmf_fit_state_t;
 
@@ -176,6 +183,16 @@ int dmf_batch_reserve_momentum(dmf_batch_t b, int64_t n_inner_total, void* strea
 /* set-up (rowgram initial + known panels) and one whole outer iteration (u_inner, panels, alpha_inner, rowgram) */
 int dmf_gram_init(dmf_batch_t b, void* stream);
 int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
+
+/* Fused engine: one outer iteration of deconvolution.py:206-221 / :320-335 as ONE streaming pass + the per-sample kernel.
+ * dmf_fused_outer = [cost_f_w of the incoming iterate and, when that iterate closes an outer iteration, the |cf - cf_0| < tol
+ * test (:218-221); update_u x n_iter2 (:82-89); Gram panel with the new u] + dmf_gram_alpha_inner.  Set-up is dmf_gram_init.
+ * After the last dmf_fused_outer the cost of the final iterate is still pending: dmf_fused_finish evaluates it (one cost-only
+ * pass; counts the outer iteration, runs the test).  dmf_fit_batched does all of this.  fused_pass alone (no alpha step) is
+ * exposed for timing. */
+int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
+int dmf_fused_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
+int dmf_fused_finish(dmf_batch_t b, double tol, void* stream);
 
 /* whole loops --------------------------------------------------------------------------------- */
 /* enqueue n_outer outer iterations (n_iter2 U steps, n_iter2 alpha/FW steps, cost) without host sync;

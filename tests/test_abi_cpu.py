@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, f"symbols declared in the header but not exported: {missing}"
     assert declared == set(built.EXPORTS), "ctypes EXPORTS table and header prototypes differ"
-    assert lib.dmf_abi_version() == built.ABI_VERSION == 3
+    assert lib.dmf_abi_version() == built.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header(built, tmp_path):

@@ -11,25 +11,40 @@ TOL64 = 1e-6
 TOL32 = 1e-4
 
 
-@pytest.fixture(scope="module", params=["stream", "auto"])
+@pytest.fixture(scope="module", params=["stream", "gram", "auto"])
 def dec(request):
-    """The reference-shaped API with both device engines: 'stream' = one pass per inner iteration,
-    'auto' = Gram-form engine wherever the library supports the shape (n_u <= 4)."""
+    """The reference-shaped API with every device engine: 'stream' = one pass per inner iteration, 'gram' = two passes per
+    outer iteration (stream where the Gram form has no instantiation), 'auto' = the fused one-pass engine where the library
+    supports the shape (FP64, n_u <= 2, K <= 8, N <= 256), else gram, else stream."""
     import torch
     assert torch.cuda.is_available()
     import __graft_entry__ as g
     g.build()
     import demethify_b200
     from demethify_b200 import deconvolution
-    demethify_b200.set_engine(request.param)
+    demethify_b200.set_engine("auto" if request.param == "gram" else request.param)
     deconvolution.engine_mode = request.param
+    if request.param == "gram":                     # 'auto' minus the fused engine: hide the 4-slot layout it needs
+        from demethify_b200 import engine as eng
+        deconvolution._saved_fused = eng.FUSED_SLOTS
+        eng.FUSED_SLOTS = False
     yield deconvolution
     demethify_b200.set_engine("auto")
+    if request.param == "gram":
+        from demethify_b200 import engine as eng
+        eng.FUSED_SLOTS = True
 
 
-def check_engine(dec, n_u, K=5):
-    want = "gram" if (dec.engine_mode == "auto" and (n_u <= 4 or (n_u <= 8 and K <= 6))) else "stream"
-    assert dec.last_fit_info()["engine"] == want
+def expected_engine(mode, n_u, K=5, N=10, fp64=True):
+    if mode == "stream":
+        return "stream"
+    if mode == "auto" and fp64 and n_u <= 2 and K <= 8 and N <= 256:
+        return "fused"
+    return "gram" if (n_u <= 4 or (n_u <= 8 and K <= 6)) else "stream"
+
+
+def check_engine(dec, n_u, K=5, N=10):
+    assert dec.last_fit_info()["engine"] == expected_engine(dec.engine_mode, n_u, K, N)
 
 
 @pytest.fixture(scope="module")
@@ -85,7 +100,7 @@ def test_purity_two_unknowns(dec, live):
 
 def test_unsupervised_fixture(dec, shipped, live):
     u, a = dec.unsupervised_deconv(shipped["X"], 4, shipped["D"], "uniform_", n_iter1=10000, n_iter2=20, tol=1e-2, seed=1)
-    check_engine(dec, 4)
+    check_engine(dec, 4, 0)
     assert dec.last_fit_info()["n_outer"] == len(live["unsup_costs"]) - 1
     assert np.abs(a - shipped["unsup_alpha"]).max() <= TOL64 and np.abs(u - shipped["unsup_u"]).max() <= TOL64
 
@@ -119,7 +134,7 @@ def test_partial_reference_vs_oracle(dec, orc, M, N, K, n_u, it1, it2):
     uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, n_u, it1, it2, 1e-9, trace=tr)
     u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, n_u, n_iter1=it1, n_iter2=it2, tol=1e-9)
     info = dec.last_fit_info()
-    check_engine(dec, n_u, K)
+    check_engine(dec, n_u, K, N)
     assert info["n_outer"] == tr["n_outer"]
     assert abs(info["cost"] - tr["costs"][-1]) <= 1e-9 * tr["costs"][-1]
     assert np.abs(a - ao).max() <= TOL64 and np.abs(u - uo).max() <= TOL64
@@ -186,7 +201,7 @@ def test_size_independent_properties_full_scale(dec):
     u0 = rs.uniform(size=(X.shape[0], 2)); a0 = rs.dirichlet(np.ones(8), 16).T
     prob = DeviceProblem(X, D, Rk)
     b = FitBatch(prob, 2, [u0], [a0], trace_cap=16)
-    assert b.engine == ("gram" if dec.engine_mode == "auto" else "stream")
+    assert b.engine == expected_engine(dec.engine_mode, 2, 6, 16)
     st = b.fit(8, 20, 0.0)
     (u, a, n_outer, cost), = b.results(st)
     tr = b.trace[0, :9].cpu().numpy()
