@@ -8,13 +8,17 @@ M = 1,000,000 CpGs x N = 256 samples, K = 6 known + n_u = 2 unknown cell types, 
 tol = 0 so no step stops early (the reference's fixture fits need 54-166 outer iterations at its default tolerance).
 metric = update iterations / second (inner iterations of U and alpha); fits/s = value / 4000.
 
-  value     : inputs resident in HBM when the timed region starts; the library's default engine (Gram-form: per
-              outer iteration rowgram pass -> u_inner -> Gram panel pass -> alpha_inner, see csrc/dmf_gram.cuh)
+  value     : inputs resident in HBM when the timed region starts; the library's default engine (fused: per outer iteration
+              ONE streaming pass - row statistics -> 20 update_u iterations -> Gram panel on a single visit of every row tile,
+              csrc/dmf_fused.cuh - followed by the per-sample alpha kernel)
   e2e       : the public call demethify_b200.deconvolution.mdwbssmf_deconv with HOST (pinned) numpy buffers;
               H2D of X, d_x, R_trunc, u0, alpha0 and D2H of u, alpha inside the timed region
-  roofline  : dominant kernel of the timed region (the slower of the two streaming passes), algorithmic bytes
-               / CUDA-event duration; `stream_passes` = the reference-shaped
-              one-launch-per-inner-iteration kernels (update_u / update_alpha / cost) timed in the same run
+  roofline  : dominant kernel of the timed region (the fused pass): algorithmic bytes (SURVEY 8 d4 "fused outer iteration")
+              and algorithmic FP64 flops / CUDA-event duration against the measured HBM and FP64 peaks; `bound` names the larger
+              fraction; `stream_passes` = the reference-shaped one-launch-per-inner-iteration kernels timed in the
+              same run
+  parity_sample : the SAME arrays and initial iterate as the GPU arm, first CPU_SAMPLE_ROWS rows: one outer iteration by the
+              oracle on the host and by the library on the GPU -> max |d alpha|, max |d u|, cost
   cpu_baseline / --impl reference : the numpy port of the reference loop (oracle/) on the host cores, on a
               bounded row sample of the same workload (cost is linear in M; the sample and the scaling are stated)
 
@@ -28,6 +32,10 @@ import subprocess
 import sys
 import threading
 import time
+
+if "reference" in sys.argv:          # torchrun exports OMP_NUM_THREADS=1: the CPU arm is meant to use every host core
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -53,7 +61,7 @@ def parse():
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--profile", action="store_true", help="resident arm only (for runs under ncu): no e2e, no CPU leg")
     ap.add_argument("--outer", type=int, default=OUTER_PER_STEP, help="outer iterations per step (default: one 100-iteration fit)")
-    ap.add_argument("--engine", default="auto", choices=["auto", "gram", "stream"], help="device engine of the timed region")
+    ap.add_argument("--engine", default="auto", choices=["auto", "fused", "gram", "stream"], help="device engine of the timed region")
     return ap.parse_args()
 
 
@@ -80,22 +88,42 @@ def synth_host(M, seed=0):
     return X, D.astype(np.int64), np.ascontiguousarray(Rf[:, :K_KNOWN])
 
 
-def cpu_reference_leg(steps, warmup, rows=CPU_SAMPLE_ROWS):
+def blas_threads():
+    """Use every host core for the CPU arm whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    n = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        used = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        used = n
+    return used
+
+
+def cpu_reference_leg(steps, warmup, rows=CPU_SAMPLE_ROWS, data=None):
     """The reference algorithm's numpy port (oracle/bssmf_numpy.py, pinned to the reference by
-    tests/test_oracle_golden.py) timed on the host cores.  One step = ONE outer iteration on a row sample."""
+    tests/test_oracle_golden.py) timed on the host cores.  One step = ONE outer iteration on a row sample.
+    `data` = (X, D, Rk, u0, a0) host arrays of the GPU arm (first `rows` rows); else a problem of the same recipe is drawn."""
     from oracle import bssmf_numpy as orc
-    X, D, Rk = synth_host(rows)
+    threads = blas_threads()
+    if data is None:
+        X, D, Rk = synth_host(rows)
+        u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, N_UNK, seed=1)
+    else:
+        X, D, Rk, u0, a0 = data
+        R0 = np.c_[Rk, u0]
     Df = D.astype(np.float64)
-    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, N_UNK, seed=1)
-    times = []
+    times, out = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, Df, Rk, N_UNK, 1, N_ITER2, 0.0)
+        tr = {}
+        out = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, Df, Rk, N_UNK, 1, N_ITER2, 0.0, trace=tr)
         times.append(time.perf_counter() - t0)
+        out = out + (tr,)
     t = float(np.mean(times[warmup:]))
     its_sample = 2 * N_ITER2 / t
-    cores = os.cpu_count()
-    return {"value": its_sample * rows / M_FULL, "unit": UNIT, "cores": cores, "kind": "port",
+    cores = threads
+    return {"result": out, "value": its_sample * rows / M_FULL, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{rows} of {M_FULL} CpG rows x {N_S} samples, 1 outer iteration (40 inner updates + cost) per step, "
                       f"{its_sample:.2f} it/s on the sample scaled by {rows}/{M_FULL} (cost linear in M); numpy/OpenBLAS threads",
             "s_per_step_sample": t}
@@ -212,6 +240,11 @@ def run_b200(args, rank, world, local_rank):
     bytes_a = M * (sT * (N_S + Kt) + sW * N_S)                             # alpha inner iteration / cost
     bytes_rowgram = M * (sT * (N_S + Kt) + sW * N_S + 8 * NG)              # read X, d_x, R_trunc, u; write b_m, H_m
     bytes_panel = M * (sT * (N_S + Kt) + sW * N_S)                         # read X, d_x, R_trunc, u
+    bytes_fused = M * (sT * (N_S + K_KNOWN + 4 * N_UNK) + sW * N_S)        # SURVEY 8 d4 fused outer iteration: + u, u_ read, u, u_ written
+    tri = N_UNK * (N_UNK + 1) // 2
+    # algorithmic FP64 work of the fused pass per (row, sample): c (K) + d c (1) + cost (1) + b (n_u) + H (tri) | d x (1) + bx_u (n_u)
+    # + G_uk (n_u K) + G_uu (tri) multiply-adds
+    flops_fused = 2.0 * M * N_S * (K_KNOWN + 2 + N_UNK + tri + 1 + N_UNK + N_UNK * K_KNOWN + tri)
 
     def barrier():
         torch.cuda.synchronize()
@@ -226,7 +259,14 @@ def run_b200(args, rank, world, local_rank):
 
     def one_step(evs=None):
         for _ in range(OUTER_PER_STEP):
-            if engine == "gram":
+            if engine == "fused":
+                e0 = ev() if evs is not None else None
+                batch.fused_pass(N_ITER2, 0.0)
+                e1 = ev() if evs is not None else None
+                batch.gram_alpha_inner(N_ITER2)
+                e2 = ev() if evs is not None else None
+                e3 = e4 = e2
+            elif engine == "gram":
                 e0 = ev() if evs is not None else None
                 batch.gram_u_inner(N_ITER2)
                 e1 = ev() if evs is not None else None
@@ -250,7 +290,7 @@ def run_b200(args, rank, world, local_rank):
             if evs is not None:
                 evs.append((e0, e1, e2, e3, e4))
 
-    if engine == "gram":
+    if engine in ("gram", "fused"):
         batch.gram_init()
     else:
         batch.pass_init()
@@ -271,16 +311,20 @@ def run_b200(args, rank, world, local_rank):
     elapsed_ms = t_start.elapsed_time(t_end)
     launches = batch.launch_count() - launches0
     seg = [float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k in range(4)]
+    if engine == "fused":
+        batch.fused_finish(0.0)           # cost of the last iterate (outside the timed region: one extra pass per FIT, not per step)
     st = batch.states()[0]
     assert st.n_outer == (args.warmup + args.steps) * OUTER_PER_STEP and np.isfinite(st.cost)
-    if engine == "gram":
+    if engine == "fused":
+        kern = {"fused_outer_kernel": seg[0], "alpha_inner_kernel": seg[1]}
+    elif engine == "gram":
         kern = {"u_inner_kernel": seg[0], "gram_panel_kernel": seg[1], "alpha_inner_kernel": seg[2], "rowgram4_kernel": seg[3]}
     else:
         kern = {"u_pass_kernel": seg[0] / N_ITER2, "alpha_pass_kernel": seg[1] / N_ITER2, "cost_kernel": seg[3]}
 
     # ---- the reference-shaped one-launch-per-inner-iteration passes, same data, timed on their own
     stream = None
-    if engine == "gram" and not args.profile:
+    if engine in ("gram", "fused") and not args.profile:
         sb = FitBatch(prob, N_UNK, [hU], [hA], engine="stream")
         sb.pass_init()
         for fn in (sb.pass_u, sb.pass_alpha, lambda: sb.pass_cost(0.0)):
@@ -305,7 +349,7 @@ def run_b200(args, rank, world, local_rank):
     # ---- CpG-row sharding of ONE 1M-row fit over the ranks (strong scaling; NCCL all-reduce of the per-sample statistics
     # and of the cost every outer iteration): rank r contributes M / world of its own rows, alpha is replicated
     row_sharded = None
-    if world > 1 and engine == "gram" and not args.profile:
+    if world > 1 and engine in ("gram", "fused") and not args.profile:
         from demethify_b200.sharded import GpuShardBackend, RowShardedFit
         m_loc = M // world
         sprob = prob.row_slice(0, m_loc)
@@ -358,7 +402,17 @@ def run_b200(args, rank, world, local_rank):
     # ---- end-to-end arm: public API, host buffers in, host arrays out
     nX, nD, nR, nU, nA = hX.numpy(), hD.numpy(), hR.numpy(), hU.numpy(), hA.numpy()
     batch.close()
-    del batch, prob
+    del batch
+    # ---- parity sample: the first rows of the SAME arrays / initial iterate, one outer iteration on the GPU (CPU side below)
+    parity_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ms = min(CPU_SAMPLE_ROWS, M)
+        pb = FitBatch(prob.row_slice(0, ms), N_UNK, [nU[:ms]], [nA])
+        (pu, pa, pn, pc), = pb.results(pb.fit(1, N_ITER2, 0.0))
+        parity_gpu = (ms, pu, pa, pn, pc, pb.engine)
+        pb.close()
+        del pb
+    del prob
     torch.cuda.empty_cache()
     e2e_times = []
     for i in range(2 + min(args.steps, 3)):
@@ -386,25 +440,45 @@ def run_b200(args, rank, world, local_rank):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        if engine == "gram":
+        flops = {}
+        if engine == "fused":
+            passes = {"fused_outer_kernel": (kern["fused_outer_kernel"], bytes_fused)}
+            flops = {"fused_outer_kernel": flops_fused}
+        elif engine == "gram":
             passes = {"rowgram4_kernel": (kern["rowgram4_kernel"], bytes_rowgram), "gram_panel_kernel": (kern["gram_panel_kernel"], bytes_panel)}
         else:
             passes = {"u_pass_kernel": (kern["u_pass_kernel"], bytes_u), "alpha_pass_kernel": (kern["alpha_pass_kernel"], bytes_a)}
         dom = max(passes, key=lambda k: passes[k][0])
         dom_ms, dom_bytes = passes[dom]
         ach = dom_bytes / (dom_ms * 1e-3) / 1e9
-        traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very shape
+        # FP64 peak of this pool's B200, measured by tools/fp64_peak.cu (DMMA; DFMA reaches 34.1): the second roofline
+        fp64_peak, fp64_src = 37.1, "fallback: B200 FP64 37 TFLOP/s"
+        fpath = os.path.join(ROOT, "profiles", "fp64_peak.json")
+        if os.path.exists(fpath):
+            fj = json.load(open(fpath))
+            fp64_peak, fp64_src = fj["fp64_tflops"], fj["source"]
+        traffic, traffic_src = None, None     # DRAM bytes per launch of the dominant kernel: ncu capture of this build and shape
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             same = tj["shape"] == {"M_cpg": M, "N_samples": N_S, "K_known": K_KNOWN, "n_unknown": N_UNK,
                                    "dtype": "f64" if args.precision == "fp64" else "f32", "weights_storage": "u16" if sW == 2 else "float"}
             traffic = tj["kernels"].get(dom) if same else None
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-                "kernels_ms_per_launch": kern,
+            traffic_src = tj.get("capture") if traffic is not None else None
+        frac_hbm = ach / peak
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": frac_hbm, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
+                "frac_hbm": frac_hbm, "kernels_ms_per_launch": kern,
                 "passes": {k: {"ms_per_launch": v[0], "achieved": v[1] / (v[0] * 1e-3) / 1e9, "frac": v[1] / (v[0] * 1e-3) / 1e9 / peak,
                                "algorithmic_bytes_per_launch": int(v[1])} for k, v in passes.items()}}
+        if dom in flops:
+            tf = flops[dom] / (dom_ms * 1e-3) / 1e12
+            roof.update({"frac_fp64": tf / fp64_peak, "achieved_fp64_tflops": tf, "peak_fp64_tflops": fp64_peak, "peak_fp64_source": fp64_src,
+                         "algorithmic_fp64_flops_per_launch": flops[dom]})
+            if tf / fp64_peak > frac_hbm:       # the binding roofline is the larger fraction
+                roof.update({"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                             "note": "bound/achieved/peak/frac describe the FP64 (DFMA + DMMA) pipe, the binding roofline of the fused "
+                                     "pass; frac_hbm and algorithmic_bytes_per_launch give the HBM side"})
         if stream is not None:
             for k in ("u_pass_kernel", "alpha_pass_kernel", "cost_kernel"):
                 stream[k]["frac"] = stream[k]["achieved"] / peak
@@ -426,8 +500,16 @@ def run_b200(args, rank, world, local_rank):
         if row_sharded is not None:
             line["row_sharded"] = row_sharded
         if not args.no_cpu and world == 1:
-            leg = cpu_reference_leg(2, 1)
+            ms = parity_gpu[0]
+            leg = cpu_reference_leg(2, 1, rows=ms, data=(nX[:ms], nD[:ms], nR[:ms], nU[:ms], nA))
             line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cu, ca, ctr = leg["result"]
+            _, pu, pa, pn, pc, peng = parity_gpu
+            line["parity_sample"] = {"rows": ms, "outer_iterations": 1, "engine": peng, "same_arrays_and_init_as_gpu_arm": True,
+                                     "max_abs_d_alpha": float(np.abs(pa - ca).max()), "max_abs_d_u": float(np.abs(pu - cu).max()),
+                                     "n_outer_gpu": int(pn), "n_outer_cpu": int(ctr["n_outer"]),
+                                     "cost_gpu": float(pc), "cost_cpu": float(ctr["costs"][-1]),
+                                     "cost_rel_diff": float(abs(pc - ctr["costs"][-1]) / ctr["costs"][-1])}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

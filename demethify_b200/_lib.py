@@ -76,6 +76,7 @@ EXPORTS = {
     "dmf_fused_pass": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_fused_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_fused_finish": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "dmf_fused_alpha_commit": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_enqueue_outer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_fit_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "dmf_batch_read_state": (C.c_int, [C.c_void_p, C.POINTER(FitState), C.c_int32, C.c_void_p]),

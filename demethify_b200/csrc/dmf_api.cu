@@ -131,7 +131,7 @@ struct Plan {
     size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
     // fused engine
     int fused_ok, kb_f, nub_f, s_f, n_tiles_f, n_parts_f, n_groups_f;
-    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_offBm, f_bm_pitch, f_rowX, f_rowD, smem_f;
+    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_rowX, f_rowD, smem_f;
 };
 
 constexpr int pow2ceil_h(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -344,9 +344,8 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
         p.f_offUp = a128f(p.f_offU + (size_t)kFusedRows * pu);
         p.f_stage_bytes = a128f(p.f_offUp + (size_t)kFusedRows * pu);
         p.f_offStats = kFusedCtlBytes + kFusedStages * p.f_stage_bytes;
-        p.f_offBm = p.f_offStats + 2u * kFA * kFusedRows * ng * 8u;
-        p.f_bm_pitch = nblk * 64u + 32u;
-        p.smem_f = p.f_offBm + 2u * kFusedRows * p.f_bm_pitch;
+        p.smem_f = p.f_offStats + 2u * kFA * kFusedRows * ng * 8u;
+        (void)nblk;
         const size_t n_rec = 2 + (size_t)(ncol + p.nub_f) * s.N;
         if (p.smem_f <= smem_cap && kFusedCtlBytes + n_rec * 8 <= p.f_offStats) {
             p.n_tiles_f = (int)((s.M + kFusedRows - 1) / kFusedRows);
@@ -683,7 +682,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         fa.g.n_parts = p.n_parts_f; fa.g.n_groups = p.n_groups_f; fa.g.fit_major = 0; fa.g.multmode = 0;
         fa.n_tiles = p.n_tiles_f;
         fa.pitchX = p.f_pitchX; fa.pitchD = p.f_pitchD; fa.offD = p.f_offD; fa.offR = p.f_offR; fa.offU = p.f_offU; fa.offUp = p.f_offUp;
-        fa.stage_bytes = p.f_stage_bytes; fa.offStats = p.f_offStats; fa.offBm = p.f_offBm; fa.bm_pitch = p.f_bm_pitch;
+        fa.stage_bytes = p.f_stage_bytes; fa.offStats = p.f_offStats;
         fa.rowX_bytes = p.f_rowX; fa.rowD_bytes = p.f_rowD;
         fused_kern_t kf = by_types_f(s, p.kb_f, p.nub_f, p.s_f);
         if (!kf || cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_f) != cudaSuccess) {
@@ -888,7 +887,7 @@ int dmf_batch_set_sharded(dmf_batch_t b, int32_t on, void* stream) {
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
     b->sharded = on ? 1 : 0;
-    b->engine = DMF_ENGINE_GRAM;
+    b->engine = b->fused_ok ? DMF_ENGINE_FUSED : DMF_ENGINE_GRAM;
     return DMF_OK;
 }
 int dmf_batch_stats_buffers(dmf_batch_t b, void** local_dev, void** global_dev, int64_t* doubles_per_fit, int64_t* scal_offset) {
@@ -953,7 +952,8 @@ int dmf_gram_exchange(dmf_batch_t b, int32_t which, void* stream) {
     a.per_fit = (long long)b->stats_doubles; a.slot_stride = b->peer_slot_stride; a.flag_off = b->peer_flag_off;
     a.scal_off = (long long)b->stats_scal;
     a.n_fits = b->shape.n_fits; a.rank = b->peer_rank; a.world = b->peer_world; a.which = which;
-    a.epoch = ++b->xchg_epoch;
+    a.epoch_dev = b->xchg_ticket + 16;            // the exchange count lives on the device: CUDA-graph replays advance it
+    ++b->xchg_epoch;
     const long long n = which == 0 ? (long long)a.n_fits * a.per_fit : (long long)a.n_fits * 8;
     const int ctas = (int)std::max<long long>(1, std::min<long long>(32, (n + kThreads * 4 - 1) / (kThreads * 4)));
     peer_allreduce_kernel<<<ctas, kThreads, 0, (cudaStream_t)stream>>>(a);
@@ -986,7 +986,7 @@ int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
 int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (!b->fused_ok) return fail(DMF_E_SHAPE, "no fused-engine instantiation for this shape / layout");
-    if (b->sharded || b->multmode) return fail(DMF_E_STATE, "the fused engine does not run row-sharded or multiplicity-form batches");
+    if (b->multmode) return fail(DMF_E_STATE, "the fused engine does not run multiplicity-form batches");
     if (n_iter2 < 1 || n_iter2 > kFusedMaxInner) return fail(DMF_E_ARG, "the fused pass runs 1 .. 64 update_u iterations per visit");
     b->t_hi += n_iter2;
     int rc = ensure_mom(b, b->t_hi + n_iter2, (cudaStream_t)stream);
@@ -995,7 +995,7 @@ int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
     FusedArgs a = b->fa;
     a.fits = b->fits_dev;
     a.n_iter2 = n_iter2;
-    a.flags = 0;
+    a.flags = b->sharded ? kFlagPartial : 0;      // row-sharded: publish this GPU's sums, dmf_fused_alpha_commit decides on the reduced ones
     a.tol = tol;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
     k<<<dim3(a.g.n_parts, b->n_active, 1), kFusedThreads, b->smem_f, (cudaStream_t)stream>>>(a);
@@ -1005,9 +1005,19 @@ int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
     return DMF_OK;
 }
 int dmf_fused_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
+    if (b && b->sharded) return fail(DMF_E_STATE, "row-sharded batches: dmf_fused_pass, all-reduce of the statistics blocks, dmf_fused_alpha_commit");
     int rc = dmf_fused_pass(b, n_iter2, tol, stream);
     if (rc) return rc;
     return dmf_gram_alpha_inner(b, n_iter2, stream);
+}
+int dmf_fused_alpha_commit(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
+    if (!b) return fail(DMF_E_ARG, "NULL batch");
+    if (!b->sharded || !b->fused_ok) return fail(DMF_E_STATE, "dmf_fused_alpha_commit follows dmf_fused_pass on a row-sharded batch");
+    if (n_iter2 < 0) return fail(DMF_E_ARG, "negative iteration count");
+    int rc = ensure_mom(b, b->t_hi + n_iter2, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_g(b, k_ainner(b), b->ntc_p, 0, (b->shape.mode == DMF_MODE_PURITY ? kFlagFW : 0) | kFlagFusedCommit, n_iter2, tol, 0, 0, 0, 1,
+                    (cudaStream_t)stream);
 }
 int dmf_fused_finish(dmf_batch_t b, double tol, void* stream) {
     if (!b) return fail(DMF_E_ARG, "NULL batch");
@@ -1018,7 +1028,7 @@ int dmf_fused_finish(dmf_batch_t b, double tol, void* stream) {
 
 // engine actually used for a call with n_iter2 inner iterations
 static int effective_engine(const dmf_batch_s* b, int n_iter2) {
-    if (b->engine == DMF_ENGINE_FUSED && (n_iter2 < 1 || n_iter2 > kFusedMaxInner || b->sharded || b->multmode)) return DMF_ENGINE_GRAM;
+    if (b->engine == DMF_ENGINE_FUSED && (n_iter2 < 1 || n_iter2 > kFusedMaxInner || b->sharded || b->multmode)) return DMF_ENGINE_GRAM;      // (sharded fits are driven step by step by the caller)
     return b->engine;
 }
 
@@ -1258,6 +1268,11 @@ int dmf_wls_fit(dmf_handle_t h, const dmf_wls_desc_t* dd, void* ws, size_t ws_by
         wls_nnls_kernel<<<(ns + 63) / 64, 64, 0, st>>>(a.mom, a.Kfull, ns, d.M, d.out + j0, (long long)d.N, reinterpret_cast<int*>(base + p.off_status));
         CUDA_TRY(cudaGetLastError());
     }
+    int status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&status, base + p.off_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (status & 1) return fail(DMF_E_STATE, "wls: a sample produced non-finite proportions (all of its weights zero, or non-finite inputs)");
+    if (status & 2) return fail(DMF_E_STATE, "wls: the regressors of a sample are collinear (non-positive pivot in the normal equations)");
     return DMF_OK;
 }
 

@@ -107,6 +107,8 @@ constexpr int kFlagFW = 2;        // alpha_pass_kernel: Frank-Wolfe step instead
 constexpr int kFlagPartial = 4;   // Gram engine, CpG rows sharded over GPUs: publish this GPU's sums to FitDev::scal, leave the state to
                                   // finalize_cost_kernel / alpha_inner_kernel, which run on the all-reduced sums
 constexpr int kFlagF32 = 8;       // finalize_cost_kernel: alpha is stored as float
+constexpr int kFlagFusedCommit = 16;   // alpha_inner_kernel after a kFlagPartial fused pass (row-sharded): run the termination test and commit
+                                       // the U step on the all-reduced sums (what the fused pass's last CTA does on one GPU)
 
 struct TileSrc {
     const char* base;      // global base of the matrix (fit-specific), nullptr = absent

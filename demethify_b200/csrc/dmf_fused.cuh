@@ -14,10 +14,12 @@
 // updates l_h, a1) only if the fit did not just terminate - so a terminated fit returns exactly the iterate whose cost passed
 // the test.  alpha_inner_kernel (dmf_gram.cuh) follows and produces alpha_{k+1}.
 //
-// One CTA = 18 warps with three roles (warp specialised, tiles flow A -> U -> C through a 5-stage shared-memory ring):
+// One CTA = 20 warps with four roles (warp specialised, tiles flow A -> U -> C through a 5-stage shared-memory ring):
 //   8 A-warps   each owns 8 S samples; c comes from FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, SASS DMMA) with the samples on
 //               the M side, so a lane owns ONE sample and two rows per 8 x 8 block and keeps only its own alpha values
-//   2 U-warps   lane = row; they also drive the TMA ring (per-row bulk copies into bank-conflict-free padded rows)
+//   3 U-warps   lane = row, tile t goes to U-warp t mod 3 (the 20 dependent iterations of a tile take about as long as the
+//               A and C stages of a tile together, so consecutive tiles must overlap)
+//   1 producer  drives the TMA ring: per-row bulk copies into bank-conflict-free padded rows
 //   8 C-warps   the panel is the GEMM  [N x rows] (d) x [rows x NCOL] (u (x) [R_trunc | u]) : DMMA again, accumulators stay in
 //               the MMA C fragments for the whole kernel; bx_u on the FMA pipe
 // FP64 only (tcgen05 has no FP64 kind; DMMA and DFMA share one pipe at 64 FMA/clk/SM - tools/fp64_peak.cu), which is the
@@ -27,13 +29,12 @@
 
 namespace dmf {
 
-constexpr int kFA = 8, kFC = 8, kFU = 4;
-constexpr int kFusedThreads = (kFA + kFC + kFU) * 32;
+constexpr int kFA = 8, kFC = 8, kFU = 3, kFP = 1;
+constexpr int kFusedThreads = (kFA + kFC + kFU + kFP) * 32;
 constexpr int kFusedRows = 16;           // rows per tile (two 8-row MMA blocks, four 4-row k-steps)
 constexpr int kFusedStages = 5;
-constexpr int kFusedAhead = 3;           // tiles requested ahead of the U stage
 constexpr int kFusedMaxInner = 64;       // beyond this the U-warps (16 rows at a time) would bound the pass: Gram engine instead
-constexpr unsigned kFusedCtlBytes = 1024;
+constexpr unsigned kFusedCtlBytes = 2048;
 
 struct FusedArgs {
     Geom g;                  // problem sizes, pitches, n_parts / n_groups / part_stride of this launch
@@ -45,15 +46,15 @@ struct FusedArgs {
     int n_tiles;
     unsigned pitchX, pitchD;                          // bytes per row inside a stage (padded)
     unsigned offD, offR, offU, offUp, stage_bytes;    // stage layout, X at 0
-    unsigned offStats, offBm;                         // from the start of dynamic shared memory
-    unsigned bm_pitch;                                // bytes per row of the u (x) [R_trunc | u] table
+    unsigned offStats;                                // from the start of dynamic shared memory
     unsigned rowX_bytes, rowD_bytes;                  // bytes copied per row
 };
 typedef void (*fused_kern_t)(const FusedArgs);
 
 struct FusedCtl {
-    unsigned long long full[8], empty[8], stats[8], udone[8];
-    double wsum[2][kFA + kFC + kFU];
+    unsigned long long full[8], empty[8], stats[8], udone[8], sfree[2];
+    double wsum[2][kFA + kFC + kFU + kFP];
+    double beta[kFusedMaxInner];          // extrapolation weights of this launch's update_u iterations (the same for every row)
     int flag, commit;
 };
 static_assert(sizeof(FusedCtl) <= kFusedCtlBytes, "fused control block too large");
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             mbar_init(smem_u32(&ctl->stats[s]), kFA);
             mbar_init(smem_u32(&ctl->udone[s]), 1);
         }
+        mbar_init(smem_u32(&ctl->sfree[0]), 1);
+        mbar_init(smem_u32(&ctl->sfree[1]), 1);
         mbar_fence_init();
     }
     // every stage starts as finite data: rows beyond the end of the last tile and samples beyond N are weighted with d = 0,
@@ -141,6 +144,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const unsigned n16 = (a.offStats - kFusedCtlBytes) / 16;
         for (unsigned i = tid; i < n16; i += kFusedThreads)
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(stages32 + i * 16u), "r"(0u) : "memory");
+    }
+    if (tid < a.n_iter2) {
+        // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
+        const double l_w = st->l_w;
+        const double cap = 0.9999 * sqrt((tid == 0 ? st->l_w_old : l_w) / l_w);
+        ctl->beta[tid] = fmin(a.mom_m[st->t_u + tid], cap);
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -157,55 +166,63 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     int jcC[S];
     bool validC[S];
 
-    if (warp >= kFA + kFC) {
-        // =========================================================================== U-warps (+ TMA producer)
+    if (warp >= kFA + kFC + kFU) {
+        // =========================================================================== producer warp: the TMA ring
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        const int uw = warp - (kFA + kFC);
         const char* Ucur_g = f.U + (size_t)ucur * g.uslot_bytes;
         const char* Uprv_g = f.U + (size_t)(ucur ^ 1) * g.uslot_bytes;
-        double* Unew_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 2) * g.uslot_bytes);
-        double* Unpv_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 3) * g.uslot_bytes);
-        auto produce = [&](int it) {
+        const unsigned rbytes = (unsigned)(g.ldr * 8), ubytes = (unsigned)(g.ldu * 8);
+        for (int it = 0; it < n_my; ++it) {
             const int s = it % NS;
+            mbar_wait(smem_u32(&ctl->empty[s]), (((unsigned)(it / NS)) & 1u) ^ 1u);      // the C-warps released tile it - NS
             const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
             const int nrows = tile_rows(it);
             const uint32_t full = smem_u32(&ctl->full[s]);
             const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
-            const unsigned rbytes = (unsigned)(g.ldr * 8), ubytes = (unsigned)(g.ldu * 8);
             if (lane == 0) {
-                fence_proxy_async_smem();
+                fence_proxy_async_smem();      // the U-warps wrote the new u into this stage through the generic proxy
                 mbar_arrive_expect_tx(full, (unsigned)nrows * (a.rowX_bytes + a.rowD_bytes + rbytes + 2u * ubytes));
             }
             __syncwarp();
             if (lane < nrows) {
                 bulk_g2s(sb + (uint32_t)lane * a.pitchX, f.X + (r0 + lane) * (long long)a.rowX_bytes, a.rowX_bytes, full);
-                bulk_g2s(sb + a.offD + (uint32_t)lane * a.pitchD, f.D + (r0 + lane) * (long long)a.rowD_bytes, a.rowD_bytes, full);
-            } else if (lane == 16) {
-                if (K) bulk_g2s(sb + a.offR, f.Rk + r0 * (long long)rbytes, (unsigned)nrows * rbytes, full);
-            } else if (lane == 17) {
-                bulk_g2s(sb + a.offU, Ucur_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
-            } else if (lane == 18) {
-                bulk_g2s(sb + a.offUp, Uprv_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
+            } else if (lane >= 16 && lane - 16 < nrows) {
+                bulk_g2s(sb + a.offD + (uint32_t)(lane - 16) * a.pitchD, f.D + (r0 + lane - 16) * (long long)a.rowD_bytes, a.rowD_bytes, full);
             }
+            if (lane == 0 && K) bulk_g2s(sb + a.offR, f.Rk + r0 * (long long)rbytes, (unsigned)nrows * rbytes, full);
+            if (lane == 1) bulk_g2s(sb + a.offU, Ucur_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
+            if (lane == 2) bulk_g2s(sb + a.offUp, Uprv_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
             __syncwarp();
-        };
+        }
+    } else if (warp >= kFA + kFC) {
+        // =========================================================================== U-warps: update_u on the row statistics
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int uw = warp - (kFA + kFC);
+        double* Unew_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 2) * g.uslot_bytes);
+        double* Unpv_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 3) * g.uslot_bytes);
         const int n2 = a.n_iter2;
-        const double l_w = st->l_w, lwo_in = st->l_w_old;
+        const double l_w = st->l_w;
         const double inv_lw = 1.0 / l_w;       // as u_inner_kernel: reciprocal multiply (<= 1 ulp of a ~1e-4-sized step vs the division of :88)
-        const double* mm = a.mom_m + st->t_u;
-        const double cap0 = 0.9999 * sqrt(lwo_in / l_w), cap1 = 0.9999 * sqrt(l_w / l_w);
         const bool at_current = (g.mode == 2);
-        if (uw == 0)
-            for (int t = 0; t < kFusedAhead && t < n_my; ++t) produce(t);
+        const unsigned upitch = (unsigned)(g.ldu * 8);
+        // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
+        const uint32_t beta32 = smem_u32(&ctl->beta[0]);
+        // one step of deconvolution.py:82-89 (gradient at u for the unsupervised variant, :163): (prev, cur) -> next
+        auto step = [&](const double (&pv)[NUB], const double (&cu)[NUB], const double (&v)[NG], double beta, double (&nx)[NUB]) {
+            double ut[NUB];
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) ut[q] = cu[q] + beta * (cu[q] - pv[q]);
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                double sq = 0.0;
+#pragma unroll
+                for (int q2 = 0; q2 < NUB; ++q2)
+                    sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], at_current ? cu[q2] : ut[q2], sq);
+                const double gq = v[q] - sq;
+                nx[q] = clip01(ut[q] + gq * inv_lw);
+            }
+        };
         for (int it = uw; it < n_my; it += kFU) {
-            // The stage of tile it + 3 held tile it - 2: free once the C-warps released it, which also frees Bm[it & 1].  Requested
-            // here when that already happened, else after the iterations below (they do not need it), so that the U stage of
-            // this tile overlaps the C stage of the two tiles before it.
-            const int itp = it + kFusedAhead;
-            const uint32_t ebar = smem_u32(&ctl->empty[itp % NS]);
-            const unsigned epar = (((unsigned)(itp / NS)) & 1u) ^ 1u;
-            const bool requested = __shfl_sync(0xffffffffu, (int)mbar_try_wait(ebar, epar), 0) != 0;      // one decision for the warp
-            if (requested && itp < n_my) produce(itp);
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
             mbar_wait(smem_u32(&ctl->stats[s]), ph);
@@ -215,7 +232,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
             const bool live = lane < nrows;
             const int row = lane < TR ? lane : 0;
-            // row statistics: the 8 A-warp partials in warp order
+            // row statistics: the 8 A-warp partials in warp order; the buffer is free for tile it + 2 as soon as they are in registers
             double v[NG];
 #pragma unroll
             for (int i = 0; i < NG; ++i) v[i] = 0.0;
@@ -229,12 +246,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                         lds1(sbase + (uint32_t)w * (TR * NG * 8u) + (uint32_t)i * 8u, t);
                         v[i] += t;
                     }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sfree[it & 1]));
             }
             double u[NUB], up[NUB];
 #pragma unroll
             for (int q = 0; q < NUB; ++q) {
-                lds1(sb + a.offU + (uint32_t)row * (unsigned)(g.ldu * 8) + (uint32_t)q * 8u, u[q]);
-                lds1(sb + a.offUp + (uint32_t)row * (unsigned)(g.ldu * 8) + (uint32_t)q * 8u, up[q]);
+                lds1(sb + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, u[q]);
+                lds1(sb + a.offUp + (uint32_t)row * upitch + (uint32_t)q * 8u, up[q]);
             }
             if (live) {      // cost of the incoming iterate: -2 u^T b + u^T H u of this row (rowgram4_kernel, writer lanes)
                 double ct = 0.0;
@@ -247,31 +266,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 }
                 cost += ct;
             }
-            for (int itn = 0; itn < n2; ++itn) {           // update_u, deconvolution.py:82-89 (same arithmetic as u_inner_kernel)
-                const double beta = fmin(__ldg(mm + itn), itn == 0 ? cap0 : cap1);
-                double ut[NUB], ug[NUB];
+            // n_iter2 iterations, two at a time so that (u_, u) rotate without register copies
+            int itn = 0;
+            for (; itn + 2 <= n2; itn += 2) {
+                double b0, b1, n1[NUB], n3[NUB];
+                lds2(beta32 + (uint32_t)itn * 8u, b0, b1);
+                step(up, u, v, b0, n1);
+                step(u, n1, v, b1, n3);
 #pragma unroll
-                for (int q = 0; q < NUB; ++q) {
-                    ut[q] = u[q] + beta * (u[q] - up[q]);
-                    ug[q] = at_current ? u[q] : ut[q];
-                }
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) {
-                    double sq = 0.0;
-#pragma unroll
-                    for (int q2 = 0; q2 < NUB; ++q2) sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], ug[q2], sq);
-                    const double gq = v[q] - sq;
-                    double un = ut[q] + gq * inv_lw;
-                    un = clip01(un);
-                    up[q] = u[q];
-                    u[q] = un;
-                }
+                for (int q = 0; q < NUB; ++q) { up[q] = n1[q]; u[q] = n3[q]; }
             }
-            if (!requested) {
-                mbar_wait(ebar, epar);
-                if (itp < n_my) produce(itp);
+            if (itn < n2) {
+                double b0, n1[NUB];
+                lds1(beta32 + (uint32_t)itn * 8u, b0);
+                step(up, u, v, b0, n1);
+#pragma unroll
+                for (int q = 0; q < NUB; ++q) { up[q] = u[q]; u[q] = n1[q]; }
             }
-            // new iterate: global (other slot pair), the stage (bx_u of the C-warps) and the panel's B operand
+            // new iterate: global (other slot pair) and the stage (the C-warps form u (x) [R_trunc | u] and bx_u from it)
             if (live) {
 #pragma unroll
                 for (int q = 0; q < NUB; ++q) {
@@ -283,29 +295,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 }
             }
             if (lane < TR) {
-                const uint32_t bm = smem32 + a.offBm + (uint32_t)(it & 1) * (TR * a.bm_pitch) + (uint32_t)lane * a.bm_pitch;
-                double un[NUB];
 #pragma unroll
                 for (int q = 0; q < NUB; ++q) {
-                    un[q] = (live && q < g.nu) ? u[q] : 0.0;
-                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + a.offU + (uint32_t)lane * (unsigned)(g.ldu * 8) + (uint32_t)q * 8u), "d"(un[q]) : "memory");
+                    const double un = (live && q < g.nu) ? u[q] : 0.0;
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + a.offU + (uint32_t)lane * upitch + (uint32_t)q * 8u), "d"(un) : "memory");
                 }
-#pragma unroll
-                for (int k = 0; k < KB; ++k) {
-                    double rk = 0.0;
-                    if (k < K) lds1(sb + a.offR + (uint32_t)lane * (unsigned)(g.ldr * 8) + (uint32_t)k * 8u, rk);
-#pragma unroll
-                    for (int q = 0; q < NUB; ++q)
-                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(bm + (uint32_t)(q * KB + k) * 8u), "d"(un[q] * rk) : "memory");
-                }
-#pragma unroll
-                for (int q = 0; q < NUB; ++q)
-#pragma unroll
-                    for (int q2 = q; q2 < NUB; ++q2)
-                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(bm + (uint32_t)(NUB * KB + tri_index(q, q2, NUB)) * 8u), "d"(un[q] * un[q2]) : "memory");
-#pragma unroll
-                for (int c = NCOL; c < NBLK * 8; ++c)
-                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(bm + (uint32_t)c * 8u), "d"(0.0) : "memory");
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->udone[s]));
@@ -338,7 +332,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
             mbar_wait(smem_u32(&ctl->full[s]), ph);
-            if (it >= 2) mbar_wait(smem_u32(&ctl->udone[(it - 2) % NS]), ((unsigned)((it - 2) / NS)) & 1u);     // stats[it & 1] free
+            if (it >= 2) mbar_wait(smem_u32(&ctl->sfree[it & 1]), ((unsigned)((it >> 1) - 1)) & 1u);     // tile it - 2's partials were read
             const int nrows = tile_rows(it);
             const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
             double acc[NV];
@@ -413,7 +407,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
 #pragma unroll
             for (int q = 0; q < NUB; ++q) paccx[mb][q] = 0.0;
         }
-        const unsigned upitch = (unsigned)(g.ldu * 8);
+        const unsigned upitch = (unsigned)(g.ldu * 8), rpitch = (unsigned)(g.ldr * 8);
+        // B operand of the panel MMA: column c = 8 nb + gi of  u (x) [R_trunc | u]  =  (first factor u_q) x (second factor R_k or u_q2),
+        // formed per k-step from the stage (the U-warp left the new u there)
+        unsigned fa_off[NBLK], fb_off[NBLK], fb_pitch[NBLK];
+        bool fzero[NBLK];
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) {
+            const int c = 8 * nb + gi;
+            int q = 0, q2 = 0, k = -1;
+            if (c < NUB * KB) { q = c / (KB > 0 ? KB : 1); k = c - q * KB; }
+            else if (c < NCOL) {
+                int e2 = c - NUB * KB;
+                while (e2 >= NUB - q) { e2 -= NUB - q; ++q; }
+                q2 = q + e2;
+            }
+            fzero[nb] = c >= NCOL || q >= g.nu || (k >= 0 ? k >= K : q2 >= g.nu);
+            fa_off[nb] = a.offU + (unsigned)q * 8u;
+            fb_off[nb] = (k >= 0 && !fzero[nb]) ? a.offR + (unsigned)k * 8u : a.offU + (unsigned)q2 * 8u;
+            fb_pitch[nb] = (k >= 0 && !fzero[nb]) ? rpitch : upitch;
+        }
         for (int it = 0; it < n_my; ++it) {
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
@@ -421,14 +434,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             mbar_wait(smem_u32(&ctl->full[s]), ph);
             const int nrows = tile_rows(it);
             const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
-            const uint32_t bm = smem32 + a.offBm + (uint32_t)(it & 1) * (TR * a.bm_pitch);
-#pragma unroll
+#pragma unroll 2
             for (int ks = 0; ks < TR / 4; ++ks) {
                 const int row = 4 * ks + ti;
                 const bool lrow = row < nrows;
                 double bfrag[NBLK], un[NUB];
 #pragma unroll
-                for (int nb = 0; nb < NBLK; ++nb) lds1(bm + (uint32_t)row * a.bm_pitch + (uint32_t)(8 * nb + gi) * 8u, bfrag[nb]);
+                for (int nb = 0; nb < NBLK; ++nb) {
+                    double fa, fb;
+                    lds1(sb32 + fa_off[nb] + (uint32_t)row * upitch, fa);
+                    lds1(sb32 + fb_off[nb] + (uint32_t)row * fb_pitch[nb], fb);
+                    bfrag[nb] = fzero[nb] ? 0.0 : fa * fb;
+                }
 #pragma unroll
                 for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
 #pragma unroll
@@ -486,7 +503,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     double* rec = reinterpret_cast<double*>(smem + kFusedCtlBytes);
     if (tid == 0) {
         double c = 0.0, q = 0.0;
-        for (int w = 0; w < kFA + kFC + kFU; ++w) { c += ctl->wsum[0][w]; q += ctl->wsum[1][w]; }
+        for (int w = 0; w < kFA + kFC + kFU + kFP; ++w) { c += ctl->wsum[0][w]; q += ctl->wsum[1][w]; }
         rec[0] = c;
         rec[1] = q;
     }

@@ -1134,6 +1134,14 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
         const double nr = sqrt(st->ssq_rk + f.rscal[4]);
         l_h = (nr * nr) * st->dmax2;
     }
+    // Row-sharded fused engine: the fused pass published this GPU's cost / ||u||^2 / panel; on the all-reduced copies every CTA
+    // takes the same termination decision (deconvolution.py:218-221), the last CTA commits it (dmf_fused.cuh, last-CTA logic)
+    const bool fcommit = (a.flags & kFlagFusedCommit) != 0;
+    const int phase_in = st->phase;
+    const double cf_new = fcommit ? f.rscal[0] : 0.0;
+    const bool fstop = fcommit && phase_in == 1 && ((fabs(cf_new - st->cf) < a.tol) || !(cf_new == cf_new));
+    const double lw_pass = st->l_w;                      // the l_w the fused pass stepped with
+    const int tu_in = st->t_u, ucur_in = st->u_cur;
     const double lho_in = st->l_h_old;
     const int t0 = st->t_a;
     const double* mm = a.mom_m + t0;
@@ -1145,7 +1153,7 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
     const int n_cta = gridDim.y;
     {
         const int j = blockIdx.y * blockDim.x + threadIdx.x;
-        if (j < g.N) {
+        if (j < g.N && !fstop) {
         double G[KTB][KTB], b[KTB], ac[KTB], ap[KTB];
 #pragma unroll(KTB <= 8 ? KTB : 1)
         for (int k = 0; k < KTB; ++k) {
@@ -1225,6 +1233,23 @@ __global__ void __launch_bounds__(kThreads) alpha_inner_kernel(const PassArgs a)
         f.tickets[0] = 0u;                               // re-arm for the next launch
         bool bad = false;
         for (int cta = 0; cta < n_cta; ++cta) bad |= __ldcg(&f.part[g.N + cta]) != 0.0;
+        if (fcommit) {
+            if (phase_in == 1) {                         // the incoming iterate closes an outer iteration
+                const double prev = st->cf;
+                st->cf_prev = prev;
+                st->cf = cf_new;
+                const int no = st->n_outer + 1;
+                st->n_outer = no;
+                if (f.trace && no < f.trace_cap) f.trace[no] = cf_new;
+                st->phase = 0;
+                if (fstop) { st->done = (cf_new == cf_new) ? 1 : 3; return; }
+            }
+            st->u_cur = ucur_in ^ 2;                     // commit the U step of the fused pass
+            st->a1 = a.mom_a[tu_in + n2];
+            st->t_u = tu_in + n2;
+            if (n2 > 0) st->l_w_old = lw_pass;
+            st->phase = 1;
+        }
         if (bad) st->done = 3;
         if (sharded) {
             st->ssq_u = f.rscal[4];
@@ -1279,7 +1304,8 @@ struct XchgArgs {
     long long scal_off;       // offset of the 8 scalars inside a fit's block
     int n_fits, rank, world;
     int which;                // 0: whole blocks; 1: the 8 scalars of every fit (sum); 2: the same at set-up (slot 3 = max d_x: max)
-    unsigned epoch;
+    unsigned* epoch_dev;      // exchanges completed so far (device memory, so that a captured launch advances with every replay);
+                              // ticket[1] counts the CTAs that finished the exchange
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -1291,7 +1317,8 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 
 static __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(const XchgArgs a) {
     __shared__ int s_last;
-    const int parity = a.epoch & 1u;
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(a.epoch_dev) + 1u;     // the last CTA to leave publishes it (below)
+    const int parity = epoch & 1u;
     const long long n = a.which == 0 ? (long long)a.n_fits * a.per_fit : (long long)a.n_fits * 8;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
     auto src_index = [&](long long e) { return a.which == 0 ? e : (e >> 3) * a.per_fit + a.scal_off + (e & 7); };
@@ -1309,14 +1336,14 @@ static __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(const X
         __threadfence_system();
         if (threadIdx.x < a.world) {
             unsigned* flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.peers[threadIdx.x]) + a.flag_off);
-            st_release_sys(flags + parity * a.world + a.rank, a.epoch);
+            st_release_sys(flags + parity * a.world + a.rank, epoch);
         }
         if (threadIdx.x == 0) *a.ticket = 0u;
     }
     // 3. wait for every rank's flag in MY buffer
     if (threadIdx.x < a.world) {
         const unsigned* flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(a.peers[a.rank]) + a.flag_off);
-        while (ld_acquire_sys(flags + parity * a.world + threadIdx.x) != a.epoch) { __nanosleep(64); }
+        while (ld_acquire_sys(flags + parity * a.world + threadIdx.x) != epoch) { __nanosleep(64); }
     }
     __syncthreads();
     // 4. rank-ordered sum (L1 bypassed: the slots were written by peers)
@@ -1329,6 +1356,12 @@ static __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(const X
             s = is_max ? fmax(s, v) : s + v;
         }
         a.global[src_index(e)] = s;
+    }
+    // every CTA read the count at entry; the last one to get here advances it for the next launch (stream order separates launches)
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.ticket + 1, 1u) == gridDim.x - 1) {
+        a.ticket[1] = 0u;
+        *a.epoch_dev = epoch;
     }
 }
 

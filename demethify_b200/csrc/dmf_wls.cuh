@@ -144,7 +144,9 @@ static __global__ void wls_nnls_kernel(const double* __restrict__ mom, int K, in
     (void)ybar;
     double nb = 0.0;
     for (int p = 0; p < K; ++p) nb += fabs(b[p]);
-    const double tol = 10.0 * (double)(M > K ? M : K) * 2.220446049250313e-16 * nb;
+    const double tolx = 10.0 * (double)(M > K ? M : K) * 2.220446049250313e-16;     // threshold on the coefficients: unscaled
+    const double tol = tolx * nb;                                                     // threshold on the dual w = A^T (b - A x): scaled by |A^T b|_1
+    bool singular = false;
     // solve G_PP s_P = b_P by Cholesky on the passive set
     auto solve = [&]() {
         int idx[kMaxKt], n = 0;
@@ -153,6 +155,7 @@ static __global__ void wls_nnls_kernel(const double* __restrict__ mom, int K, in
             for (int k = 0; k <= i; ++k) {
                 double v = G[idx[i]][idx[k]];
                 for (int t = 0; t < k; ++t) v -= L[i][t] * L[k][t];
+                if (i == k && !(v > 0.0)) singular = true;       // collinear regressors on the passive set
                 L[i][k] = (i == k) ? sqrt(v > 0.0 ? v : 1e-300) : v / L[k][k];
             }
         double y[kMaxKt];
@@ -196,7 +199,7 @@ static __global__ void wls_nnls_kernel(const double* __restrict__ mom, int K, in
                 if (pas[p] && s[p] <= 0.0) { const double t = x[p] / (x[p] - s[p]); if (t < step) step = t; }
             for (int p = 0; p < K; ++p) x[p] = x[p] * (1.0 - step) + step * s[p];
             for (int p = 0; p < K; ++p)
-                if (x[p] <= tol) { pas[p] = false; }
+                if (x[p] <= tolx) { pas[p] = false; }
             for (int p = 0; p < K; ++p)
                 if (!pas[p]) x[p] = 0.0;
             solve();
@@ -208,7 +211,8 @@ static __global__ void wls_nnls_kernel(const double* __restrict__ mom, int K, in
     for (int p = 0; p < K; ++p) sum += x[p];
     const double den = sum > 1e-10 ? sum : 1e-10;
     for (int p = 0; p < K; ++p) out[(size_t)p * ldo + j] = x[p] / den;
-    if (!(sum == sum)) atomicExch(status, 1);
+    if (!(sum == sum)) atomicOr(status, 1);           // NaN proportions (e.g. a sample whose weights are all zero)
+    if (singular) atomicOr(status, 2);
 }
 
 }  // namespace dmf

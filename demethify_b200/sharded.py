@@ -36,11 +36,13 @@ def row_range(M, rank, world):
 class GpuShardBackend:
     """This rank's rows on its GPU: a one-fit (or few-fit) FitBatch in sharded Gram-engine mode."""
 
-    def __init__(self, X_local, D_local, Rk_local, n_u, U0_local, A0, mode=_lib.DMF_MODE_PARTIAL, purity=None, precision=None):
+    def __init__(self, X_local, D_local, Rk_local, n_u, U0_local, A0, mode=_lib.DMF_MODE_PARTIAL, purity=None, precision=None, engine=None):
         self.prob = X_local if isinstance(X_local, DeviceProblem) else DeviceProblem(X_local, D_local, Rk_local, precision=precision)
-        self.batch = FitBatch(self.prob, n_u, [U0_local], [A0], mode=mode, purity=purity, engine="gram")
+        self.batch = FitBatch(self.prob, n_u, [U0_local], [A0], mode=mode, purity=purity, engine=engine)
         lib, b = _lib.lib(), self.batch
         _lib.check(lib.dmf_batch_set_sharded(b.b, 1, _stream_ptr()))
+        # fused engine where the shape allows it: ONE pass and ONE all-reduce per outer iteration (RowShardedFit.outer)
+        self.fused = b.engine == "fused"
         loc, glo, per, so = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
         _lib.check(lib.dmf_batch_stats_buffers(b.b, C.byref(loc), C.byref(glo), C.byref(per), C.byref(so)))
         base = b.ws.data_ptr()
@@ -113,6 +115,12 @@ class GpuShardBackend:
     def alpha_inner(self, n_iter2):
         self.batch.gram_alpha_inner(n_iter2)
 
+    def fused_pass(self, n_iter2, tol):
+        self.batch.fused_pass(n_iter2, tol)
+
+    def fused_alpha_commit(self, n_iter2, tol):
+        _lib.check(_lib.lib().dmf_fused_alpha_commit(self.batch.b, int(n_iter2), float(tol), _stream_ptr()))
+
     def finalize_cost(self, initial, tol):
         _lib.check(_lib.lib().dmf_gram_finalize_cost(self.batch.b, int(bool(initial)), float(tol), _stream_ptr()))
 
@@ -168,8 +176,29 @@ class RowShardedFit:
         if be.has_known:
             be.panels(True)
 
+    def _reduce_blocks(self):
+        be = self.be
+        if getattr(be, "peer", None) is not None:
+            be.exchange(0)                            # G_j, bx_j, scalars over all rows, over NVLink peer memory
+            self.collectives += 1
+        else:
+            glo = be.stats_global()
+            glo.copy_(be.stats_local())
+            self._allreduce(glo)                      # the same through NCCL
+
+    def use_fused(self, n_iter2):
+        return getattr(self.be, "fused", False) and 1 <= n_iter2 <= 64
+
     def outer(self, n_iter2, tol):
         be = self.be
+        if self.use_fused(n_iter2):
+            # fused engine: cost of the incoming iterate + U step + panel in ONE pass over this rank's rows, ONE all-reduce of
+            # [G_j | bx_j | cost, ||u||^2], then the test / commit / alpha iterations identically on every rank
+            be.fused_pass(n_iter2, tol)
+            self._reduce_blocks()
+            be.fused_alpha_commit(n_iter2, tol)
+            self.pending = True
+            return
         if n_iter2 > 0:
             be.u_inner(n_iter2)                       # row-local
             be.panels(False)
@@ -184,6 +213,15 @@ class RowShardedFit:
         be.rowgram(False, tol)
         self._reduce_scal(with_max=False)
         be.finalize_cost(False, tol)                  # identical termination decision on every rank
+
+    def finish(self, tol):
+        """Fused engine: the cost of the last iterate is still pending after the last outer() - one cost-only pass."""
+        if getattr(self, "pending", False):
+            self.pending = False
+            if not self.be.all_done():
+                self.be.rowgram(False, tol)
+                self._reduce_scal(with_max=False)
+                self.be.finalize_cost(False, tol)
 
     def capture_outer(self, n_iter2, tol):
         """One outer iteration (kernels, D2D copies and both NCCL all-reduces) as a CUDA graph: a replay costs one launch
@@ -217,8 +255,10 @@ class RowShardedFit:
                     self.outer(n_iter2, tol)
             issued += todo
             if self.be.all_done():                    # the state is replicated: every rank leaves the loop together
+                self.pending = False
                 break
             chunk = min(chunk * 2, 16)
+        self.finish(tol)
         return self.be.results()
 
 

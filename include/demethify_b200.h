@@ -193,6 +193,12 @@ int dmf_gram_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
 int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
 int dmf_fused_outer(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
 int dmf_fused_finish(dmf_batch_t b, double tol, void* stream);
+/* Row-sharded batches (dmf_batch_set_sharded): dmf_fused_pass publishes THIS GPU's cost, ||u||^2 and panel in the `local`
+ * statistics block and leaves the fit state alone; after the blocks are all-reduced into `global` (dmf_gram_exchange(0) or
+ * NCCL) dmf_fused_alpha_commit runs the termination test, commits the U step and runs the alpha iterations - identically on
+ * every rank.  ONE collective per outer iteration.  dmf_fused_finish is then dmf_gram_rowgram + scalar all-reduce +
+ * dmf_gram_finalize_cost as for the Gram engine. */
+int dmf_fused_alpha_commit(dmf_batch_t b, int32_t n_iter2, double tol, void* stream);
 
 /* whole loops --------------------------------------------------------------------------------- */
 /* enqueue n_outer outer iterations (n_iter2 U steps, n_iter2 alpha/FW steps, cost) without host sync;
