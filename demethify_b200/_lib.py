@@ -84,6 +84,11 @@ EXPORTS = {
     "dmf_wls_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(WlsDesc), C.POINTER(C.c_size_t)]),
     "dmf_wls_fit": (C.c_int, [C.c_void_p, C.POINTER(WlsDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dmf_pack_weights_u16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmf_nndsvd_split": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "dmf_percentile_max_keep": (C.c_int, []),
+    "dmf_percentile_bounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmf_consensus": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmf_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -82,14 +82,26 @@ def _shape_only_init(seed, init_option, M, K, N, n_u, with_zero_guard):
 
 
 def percentile_bounds_device(stack, lower_percentile, upper_percentile):
-    """np.percentile(stack, [lo, hi], axis=0) (bootstrap.py:53-54, :77-78; default linear interpolation) on the device:
-    torch.quantile's linear rule is numpy's (virtual index q (B - 1), lerp between the two neighbours)."""
-    q = torch.tensor([lower_percentile / 100.0, upper_percentile / 100.0], dtype=stack.dtype, device=stack.device)
-    flat = stack.reshape(stack.shape[0], -1)
-    out = torch.empty((2, flat.shape[1]), dtype=stack.dtype, device=stack.device)
-    step = max(1, (1 << 24) // max(stack.shape[0], 1))          # torch.quantile caps the size of its input
-    for c0 in range(0, flat.shape[1], step):
-        out[:, c0:c0 + step] = torch.quantile(flat[:, c0:c0 + step], q, dim=0, interpolation="linear")
+    """np.percentile(stack, [lo, hi], axis=0) (bootstrap.py:53-54, :77-78; default linear interpolation) on the device, by the
+    library's selection kernel (dmf_percentile_bounds: one thread per entry keeps the few smallest / largest of the B values, no
+    sort of the B x P stack).  Confidence levels so low that more than dmf_percentile_max_keep() order statistics per tail are
+    needed fall back to torch.quantile (same linear rule)."""
+    import ctypes as C
+    from .engine import _stream_ptr
+    lib = _lib.lib()
+    B = stack.shape[0]
+    flat = stack.reshape(B, -1).to(torch.float64).contiguous()
+    P = flat.shape[1]
+    out = torch.empty((2, P), dtype=torch.float64, device=stack.device)
+    klo, khi = int(np.floor((B - 1) * (lower_percentile / 100.0))), int(np.floor((B - 1) * (upper_percentile / 100.0)))
+    if max(min(klo + 2, B), min(B - khi, B)) <= lib.dmf_percentile_max_keep():
+        _lib.check(lib.dmf_percentile_bounds(C.c_void_p(flat.data_ptr()), B, P, float(lower_percentile), float(upper_percentile),
+                                             C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), _stream_ptr()))
+    else:
+        q = torch.tensor([lower_percentile / 100.0, upper_percentile / 100.0], dtype=torch.float64, device=stack.device)
+        step = max(1, (1 << 24) // max(B, 1))          # torch.quantile caps the size of its input
+        for c0 in range(0, P, step):
+            out[:, c0:c0 + step] = torch.quantile(flat[:, c0:c0 + step], q, dim=0, interpolation="linear")
     shape = stack.shape[1:]
     return out[0].reshape(shape).cpu().numpy(), out[1].reshape(shape).cpu().numpy()
 
@@ -113,15 +125,31 @@ def resample_layout(idx, M, with_csr=True):
 
 
 def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, purity, seed, prob=None,
-                   keep_u=True, on_device=False, seeds=None):
+                   keep_u=True, on_device=False, seeds=None, restarts=1):
     """All resample fits -> (alphas (B, Kt, N), us (B, M, n_u) or None, n_outer list).
+    restarts = R > 1 (extension; BASELINE config 4): every resample is fitted R times from the initial iterates of the
+    seeds s, s + 1, ..., s + R - 1 (the convention of ic.py:196; the rows are those of seed s) in the same batch, and the fit with
+    the lowest final cost is kept (the selection rule of demethify.py:199-203).
     `purity` is the internal vector (already divided by 100, bootstrap.py:18) or None.  With on_device the two stacks
     stay torch tensors in HBM (the percentiles of bt_ci are then taken there).  `seeds` restricts the run to a
     sub-list of the reference's seed sequence (one rank's share of a fit-sharded bootstrap)."""
     meth_f = np.asarray(meth_f)
     M, N = meth_f.shape
+    if n_u > 0:
+        # the reference falls back to uniform_ when n_u > N (deconvolution.py:44-45, :234-239), then dispatches on the option;
+        # anything it would run that this path does not have is refused BEFORE a resample is drawn (never silently replaced)
+        if init_option != "uniform_" and n_u > N:
+            init_option = "uniform_"
+        if init_option == "ICA":
+            raise NotImplementedError("--init ICA forms an M x M covariance (init_func.py:120) and is out of scope of the B200 path "
+                                      "(SURVEY.md 2.1 row 4); use uniform_, uniform, beta or SVD")
+        if init_option not in ("uniform_", "uniform", "beta", "SVD"):
+            raise ValueError(f"unknown init option {init_option!r}")
     seeds = bootstrap_seeds(seed, n_bootstrap) if seeds is None else list(seeds)
     n_bootstrap = len(seeds)
+    restarts = max(1, int(restarts))
+    if restarts > 1 and n_u == 0:
+        raise ValueError("restarts apply to the iterative fits (n_u >= 1)")
     prob = prob or DeviceProblem(meth_f, counts, ref)
     alphas = np.zeros((n_bootstrap, prob.K + n_u, N))
     if on_device and n_u > 0:
@@ -145,12 +173,14 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
     per_fit = (2 * M * (n_u + (n_u & 1)) * (8 if prob.precision == "fp64" else 4) + M * ng * ((ntc + 31) // 32) * 8 * (n_u <= 4)
                + 64 * (prob.K + n_u) * N * 8 + 4096
                + M * (44 + 24 * n_u))                          # wave-level stacks: resample index, order, rows, mult, offs, u0 / results
-    wave = int(max(1, min(n_bootstrap, (device_free_bytes(prob.device) // 2) // max(per_fit, 1), 4096)))
+    wave = int(max(1, min(n_bootstrap * restarts, (device_free_bytes(prob.device) // 2) // max(per_fit, 1), 4096)))
+    wave = max(restarts, wave // restarts * restarts)           # the restarts of a resample stay in one wave
+    jobs = [(s, s + r) for s in seeds for r in range(restarts)]  # (resample seed, init seed)
     mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
     use_mult = prob.K <= 6 and n_u <= 4 and prob.K + (prob.K & 1) + n_u + (n_u & 1) <= 8
     dev = prob.device
-    for w0 in range(0, n_bootstrap, wave):
-        chunk = seeds[w0:w0 + wave]
+    for w0 in range(0, len(jobs), wave):
+        chunk = jobs[w0:w0 + wave]
 
         # host staging for the wave: the worker threads draw straight into it, one H2D copy per array (pageable on purpose:
         # page-locking gigabytes per wave costs more than the copy saves)
@@ -160,8 +190,8 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         A0 = np.empty((Bw, prob.K + n_u, N))
 
         def prepare(k):
-            s = chunk[k]
-            idx = resample_indices(s, M)
+            s_rows, s = chunk[k]
+            idx = resample_indices(s_rows, M)
             if data_dependent_init:      # `uniform` / SVD look at the resampled data and use the global stream: sequential
                 Xb, Db, Rb = meth_f[idx], np.asarray(counts)[idx], np.asarray(ref)[idx]
                 if purity is not None:
@@ -169,10 +199,9 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
                 else:
                     u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
             else:                        # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
-                opt = init_option if init_option in ("uniform_", "beta") and (init_option == "uniform_" or n_u <= N) else "uniform_"
-                u0, a0 = _shape_only_init(s, opt, M, prob.K, N, n_u, with_zero_guard=purity is None)
+                u0, a0 = _shape_only_init(s, init_option, M, prob.K, N, n_u, with_zero_guard=purity is None)
             idx_np[k], u0_np[k], A0[k] = idx, np.asarray(u0).reshape(M, n_u), a0
-        if data_dependent_init or init_option not in ("uniform_", "beta"):
+        if data_dependent_init:
             for k in range(Bw):
                 prepare(k)
         else:                            # numpy's legacy generators release the GIL: draw the resamples of the wave in parallel
@@ -198,24 +227,32 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         del idx_d
         states = batch.fit(n_iter1, n_iter2, tol)
         U_d, A_d = batch.stacked_current(states)
-        n_outer.extend(st.n_outer for st in states)
-        if on_device:
-            alphas[w0:w0 + Bw] = A_d.to(torch.float64)
-            if keep_u:                               # back to the resampled-position order of the reference (Q6)
-                us[w0:w0 + Bw].scatter_(1, order_d.unsqueeze(-1).expand(-1, -1, n_u), U_d.to(torch.float64))
+        if restarts > 1:                             # best of the R restarts of every resample: lowest final cost, first on ties
+            cost = torch.tensor([st.cost for st in states], dtype=torch.float64, device=dev).view(-1, restarts)
+            best = torch.argmin(cost, dim=1) + torch.arange(cost.shape[0], device=dev) * restarts
+            U_d, A_d, order_d = U_d[best], A_d[best], order_d[best]
+            n_outer.extend(states[int(i)].n_outer for i in best.cpu())
         else:
-            alphas[w0:w0 + Bw] = A_d.to(torch.float64).cpu().numpy()
+            n_outer.extend(st.n_outer for st in states)
+        b0, nb = w0 // restarts, Bw // restarts
+        if on_device:
+            alphas[b0:b0 + nb] = A_d.to(torch.float64)
+            if keep_u:                               # back to the resampled-position order of the reference (Q6)
+                us[b0:b0 + nb].scatter_(1, order_d.unsqueeze(-1).expand(-1, -1, n_u), U_d.to(torch.float64))
+        else:
+            alphas[b0:b0 + nb] = A_d.to(torch.float64).cpu().numpy()
             if keep_u:
-                back = torch.empty((Bw, M, n_u), dtype=torch.float64, device=dev)
+                back = torch.empty((nb, M, n_u), dtype=torch.float64, device=dev)
                 back.scatter_(1, order_d.unsqueeze(-1).expand(-1, -1, n_u), U_d.to(torch.float64))
-                us[w0:w0 + Bw] = back.cpu().numpy()
+                us[b0:b0 + nb] = back.cpu().numpy()
         batch.close()
     return alphas, us, n_outer
 
 
 def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, header, outdir, samples,
-          purity, seed):
-    """bootstrap.py:10-93 — same arguments, same two CSV files, same return value (list of DataFrames)."""
+          purity, seed, restarts=1):
+    """bootstrap.py:10-93 — same arguments, same two CSV files, same return value (list of DataFrames).  `restarts` (additive):
+    see bootstrap_fits."""
     supervised = n_u == 0
     a = 1 - confidence_level / 100
     lower_percentile = 100 * (a / 2)
@@ -229,7 +266,7 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
         # the stacks are all-gathered over NCCL, every rank takes the percentiles, rank 0 writes the files
         mine = shard_of(bootstrap_seeds(seed, n_bootstrap), rank, world)
         alphas, us, _ = bootstrap_fits(len(mine), n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True,
-                                       seeds=mine)
+                                       seeds=mine, restarts=restarts)
         if not isinstance(alphas, torch.Tensor):        # supervised path / host stacks: move to the device for the all-gather
             from .engine import current_device
             alphas = torch.from_numpy(np.ascontiguousarray(alphas)).to(current_device())
@@ -237,7 +274,8 @@ def bt_ci(confidence_level, n_bootstrap, n_u, meth_f, counts, ref, init_option, 
         alphas = merge_resample_stacks(alphas, n_bootstrap)
         us = merge_resample_stacks(us, n_bootstrap) if us is not None else None
     else:
-        alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True)
+        alphas, us, _ = bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, n_iter2, tol, pur, seed, on_device=True,
+                                       restarts=restarts)
     if isinstance(alphas, torch.Tensor):
         lo, hi = percentile_bounds_device(alphas, lower_percentile, upper_percentile)
     else:

@@ -1277,3 +1277,45 @@ int dmf_wls_fit(dmf_handle_t h, const dmf_wls_desc_t* dd, void* ws, size_t ws_by
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// the steps right before / after the path (dmf_post.cuh)
+#include "dmf_post.cuh"
+
+extern "C" {
+
+int dmf_nndsvd_split(const double* U, int64_t ldu, const double* S, const double* Vh, int64_t ldv, int64_t M, int32_t N, int32_t rank,
+                     double* W, double* H, void* stream) {
+    if (!U || !S || !Vh || !W || !H || M <= 0 || N <= 0 || rank <= 0 || ldu < rank || ldv < N) return fail(DMF_E_ARG, "nndsvd: bad argument");
+    nndsvd_split_kernel<<<rank, 256, 0, (cudaStream_t)stream>>>(U, ldu, S, Vh, ldv, M, N, rank, W, H);
+    CUDA_TRY(cudaGetLastError());
+    return DMF_OK;
+}
+
+int dmf_percentile_max_keep(void) { return 128; }
+
+int dmf_percentile_bounds(const double* stack, int32_t B, int64_t P, double q_lo, double q_hi, double* out_lo, double* out_hi, void* stream) {
+    if (!stack || !out_lo || !out_hi || B <= 0 || P < 0) return fail(DMF_E_ARG, "percentile: bad argument");
+    if (!(q_lo >= 0.0 && q_lo <= q_hi && q_hi <= 100.0)) return fail(DMF_E_ARG, "percentile: 0 <= q_lo <= q_hi <= 100 required");
+    if (P == 0) return DMF_OK;
+    const int klo = (int)floor((double)(B - 1) * (q_lo / 100.0)), khi = (int)floor((double)(B - 1) * (q_hi / 100.0));
+    const int keep = std::max(std::min(klo + 2, B), std::min(B - khi, B));
+    const int blocks = (int)((P + 127) / 128);
+    if (keep <= 32) percentile_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(stack, B, P, q_lo, q_hi, out_lo, out_hi);
+    else if (keep <= 128) percentile_kernel<128><<<blocks, 128, 0, (cudaStream_t)stream>>>(stack, B, P, q_lo, q_hi, out_lo, out_hi);
+    else return fail(DMF_E_SHAPE, "percentile: more than 128 order statistics per tail would have to be kept (dmf_percentile_max_keep)");
+    CUDA_TRY(cudaGetLastError());
+    return DMF_OK;
+}
+
+int dmf_consensus(const double* alpha_runs, int32_t n_runs, int32_t Kt, int32_t N, int32_t* labels_ws, double* consensus, void* stream) {
+    if (!alpha_runs || !labels_ws || !consensus || n_runs <= 0 || Kt <= 0 || N <= 0) return fail(DMF_E_ARG, "consensus: bad argument");
+    labels_kernel<<<(n_runs * N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(alpha_runs, n_runs, Kt, N, labels_ws);
+    CUDA_TRY(cudaGetLastError());
+    const long long nn = (long long)N * N;
+    consensus_kernel<<<(int)((nn + 127) / 128), 128, 0, (cudaStream_t)stream>>>(labels_ws, n_runs, N, consensus);
+    CUDA_TRY(cudaGetLastError());
+    return DMF_OK;
+}
+
+}  // extern "C"

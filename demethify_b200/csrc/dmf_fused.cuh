@@ -25,6 +25,7 @@
 // FP64 only (tcgen05 has no FP64 kind; DMMA and DFMA share one pipe at 64 FMA/clk/SM - tools/fp64_peak.cu), which is the
 // binding roofline of this kernel: ~39 FMA per (row, sample) against 10 bytes.
 #pragma once
+#include <type_traits>
 #include "dmf_gram.cuh"
 
 namespace dmf {
@@ -79,8 +80,9 @@ __device__ __forceinline__ double lds_weight<double>(uint32_t addr) {
     return v;
 }
 
-// sum over the 8 lanes that share (lane & 3): halving butterfly over lane bits 2, 3, 4.  NV is a multiple of 8; on return lane
-// holds the totals of slots base .. base + NV / 8 - 1 in v[0 .. NV / 8).
+// Row sums over the 8 lanes that share (lane & 3): halving butterfly over lane bits 2, 3, 4.  NV is a multiple of 8; on return
+// the lane holds the totals of slots base .. base + NV / 8 - 1 in v[0 .. NV / 8).  (The row <-> MMA column mapping is a property
+// of the whole warp, so the slots cannot be made lane dependent to save the selects.)
 template <int NV>
 __device__ __forceinline__ int reduce_over_groups(double (&v)[NV], int lane) {
     static_assert(NV % 8 == 0, "NV must be a multiple of 8");
@@ -99,6 +101,142 @@ __device__ __forceinline__ int reduce_over_groups(double (&v)[NV], int lane) {
         base += up ? half : 0;
     }
     return base;
+}
+
+// One update_u step of deconvolution.py:82-89 on the row statistics v = [b | H] (gradient at u for the unsupervised variant, :163;
+// same arithmetic as u_inner_kernel): (prev, cur) -> next.
+template <bool AT_CURRENT, int NUB>
+__device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const double (&cu)[NUB], const double (&v)[ng_of(NUB)], double beta,
+                                             double inv_lw, double (&nx)[NUB]) {
+    double ut[NUB];
+#pragma unroll
+    for (int q = 0; q < NUB; ++q) ut[q] = cu[q] + beta * (cu[q] - pv[q]);
+#pragma unroll
+    for (int q = 0; q < NUB; ++q) {
+        double sq = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < NUB; ++q2)
+            sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], AT_CURRENT ? cu[q2] : ut[q2], sq);
+        const double gq = v[q] - sq;
+        // np.clip(., 0, 1) by comparisons (a NaN propagates, as in numpy; the simplex projection of the alpha step then stops the fit)
+        double un = ut[q] + gq * inv_lw;
+        un = un < 0.0 ? 0.0 : un;
+        nx[q] = un > 1.0 ? 1.0 : un;
+    }
+}
+// n2 steps, two at a time so that (u_, u) rotate without register copies; beta_t comes from shared memory
+template <bool AT_CURRENT, int NUB>
+__device__ __forceinline__ void fused_u_iterate(double (&u)[NUB], double (&up)[NUB], const double (&v)[ng_of(NUB)], uint32_t beta32, int n2,
+                                                double inv_lw) {
+    int itn = 0;
+    for (; itn + 2 <= n2; itn += 2) {
+        double b0, b1, n1[NUB], n3[NUB];
+        lds2(beta32 + (uint32_t)itn * 8u, b0, b1);
+        fused_u_step<AT_CURRENT, NUB>(up, u, v, b0, inv_lw, n1);
+        fused_u_step<AT_CURRENT, NUB>(u, n1, v, b1, inv_lw, n3);
+#pragma unroll
+        for (int q = 0; q < NUB; ++q) { up[q] = n1[q]; u[q] = n3[q]; }
+    }
+    if (itn < n2) {
+        double b0, n1[NUB];
+        lds1(beta32 + (uint32_t)itn * 8u, b0);
+        fused_u_step<AT_CURRENT, NUB>(up, u, v, b0, inv_lw, n1);
+#pragma unroll
+        for (int q = 0; q < NUB; ++q) { up[q] = u[q]; u[q] = n1[q]; }
+    }
+}
+
+// A-warps: row statistics of one 8-row block (rb) of a tile for the lane's S samples.  MASK = the tile is short or some of the
+// warp's samples do not exist (d = 0 there).  acc[2 rb NG ...] = [b (NUB) | H upper triangle] of row 8 rb + ti, then of row 8 rb + ti + 4.
+template <bool MASK, typename WT, int KS, int NUB, int S>
+__device__ __forceinline__ void fused_row_block(const FusedArgs& a, uint32_t sb32, int nrows, int rb, int gi, int ti, int K,
+                                                const double (&na)[S][KS > 0 ? KS : 1], const double (&au)[S][NUB],
+                                                const double (&P)[S][ng_of(NUB) - NUB], const int (&jc)[S], const bool (&valid)[S],
+                                                double& cost, double (&acc)[((4 * ng_of(NUB) + 7) / 8) * 8]) {
+    constexpr int NG = ng_of(NUB), NTRI = NG - NUB;
+    const int o0 = 2 * rb * NG;          // rb is a compile-time constant at both call sites
+    const unsigned rpitch = (unsigned)(a.g.ldr * 8);
+    const int ra = 8 * rb + ti, rbw = ra + 4;          // the two rows of this lane's C fragment
+    const bool la = ra < nrows, lb = rbw < nrows;
+    // B operand: R_trunc[row_of_n(gi)][4 kk + ti], MMA column n = 2 t + e  <->  tile row 8 rb + t + 4 e
+    double rfrag[KS > 0 ? KS : 1];
+    const int rown = 8 * rb + (gi >> 1) + 4 * (gi & 1);
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+        const int k = 4 * kk + ti;
+        double t = 0.0;
+        if (k < K) lds1(sb32 + a.offR + (uint32_t)rown * rpitch + (uint32_t)k * 8u, t);
+        rfrag[kk] = t;
+    }
+    const uint32_t xa = sb32 + (uint32_t)ra * a.pitchX, xb = sb32 + (uint32_t)rbw * a.pitchX;
+    const uint32_t da = sb32 + a.offD + (uint32_t)ra * a.pitchD, db = sb32 + a.offD + (uint32_t)rbw * a.pitchD;
+#pragma unroll
+    for (int sb = 0; sb < S; ++sb) {
+        double c0, c1;
+        lds1(xa + (uint32_t)jc[sb] * 8u, c0);
+        lds1(xb + (uint32_t)jc[sb] * 8u, c1);
+        double d0 = lds_weight<WT>(da + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
+        double d1 = lds_weight<WT>(db + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
+        if (MASK) {
+            if (!valid[sb]) { c0 = 0.0; c1 = 0.0; }
+            if (!(valid[sb] && la)) d0 = 0.0;
+            if (!(valid[sb] && lb)) d1 = 0.0;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, na[sb][kk], rfrag[kk]);     // c = x - R_trunc a_k
+        const double z0 = d0 * c0, z1 = d1 * c1;
+        cost = fma(z0, c0, cost);
+        cost = fma(z1, c1, cost);
+#pragma unroll
+        for (int q = 0; q < NUB; ++q) {
+            acc[o0 + q] = fma(z0, au[sb][q], acc[o0 + q]);
+            acc[o0 + NG + q] = fma(z1, au[sb][q], acc[o0 + NG + q]);
+        }
+#pragma unroll
+        for (int e = 0; e < NTRI; ++e) {
+            acc[o0 + NUB + e] = fma(d0, P[sb][e], acc[o0 + NUB + e]);
+            acc[o0 + NG + NUB + e] = fma(d1, P[sb][e], acc[o0 + NG + NUB + e]);
+        }
+    }
+}
+
+// C-warps: one tile of the Gram panel with the new u.  B operand column c = 8 nb + gi of  u (x) [R_trunc | u]  is the product
+// of two entries of the row's [R_trunc | u] in the stage (offsets fa / fb; columns beyond NCOL point both factors at a zero).
+template <bool MASK, typename WT, int NUB, int S, int NBLK>
+__device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb32, int nrows, int ti, const unsigned (&fa_off)[NBLK],
+                                                 const unsigned (&fa_pitch)[NBLK], const unsigned (&fb_off)[NBLK], const unsigned (&fb_pitch)[NBLK], const int (&jc)[S],
+                                                 const bool (&valid)[S], double (&acc)[S][NBLK][2], double (&accx)[S][NUB]) {
+    const unsigned upitch = (unsigned)(a.g.ldu * 8);
+#pragma unroll 2
+    for (int ks = 0; ks < kFusedRows / 4; ++ks) {
+        const int row = 4 * ks + ti;
+        const bool lrow = row < nrows;
+        double bfrag[NBLK], un[NUB];
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) {
+            double fa, fb;
+            lds1(sb32 + fa_off[nb] + (uint32_t)row * fa_pitch[nb], fa);
+            lds1(sb32 + fb_off[nb] + (uint32_t)row * fb_pitch[nb], fb);
+            bfrag[nb] = fa * fb;
+        }
+#pragma unroll
+        for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
+        const uint32_t xr = sb32 + (uint32_t)row * a.pitchX, dr = sb32 + a.offD + (uint32_t)row * a.pitchD;
+#pragma unroll
+        for (int mb = 0; mb < S; ++mb) {
+            double x;
+            lds1(xr + (uint32_t)jc[mb] * 8u, x);
+            double d = lds_weight<WT>(dr + (uint32_t)jc[mb] * (unsigned)sizeof(WT));
+            if (MASK) {
+                if (!(valid[mb] && lrow)) { d = 0.0; x = 0.0; }
+            }
+            const double dx = d * x;
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) accx[mb][q] = fma(dx, un[q], accx[mb][q]);
+#pragma unroll
+            for (int nb = 0; nb < NBLK; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], d, bfrag[nb]);
+        }
+    }
 }
 
 template <typename WT, int KB, int NUB, int S>
@@ -207,21 +345,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const unsigned upitch = (unsigned)(g.ldu * 8);
         // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
         const uint32_t beta32 = smem_u32(&ctl->beta[0]);
-        // one step of deconvolution.py:82-89 (gradient at u for the unsupervised variant, :163): (prev, cur) -> next
-        auto step = [&](const double (&pv)[NUB], const double (&cu)[NUB], const double (&v)[NG], double beta, double (&nx)[NUB]) {
-            double ut[NUB];
-#pragma unroll
-            for (int q = 0; q < NUB; ++q) ut[q] = cu[q] + beta * (cu[q] - pv[q]);
-#pragma unroll
-            for (int q = 0; q < NUB; ++q) {
-                double sq = 0.0;
-#pragma unroll
-                for (int q2 = 0; q2 < NUB; ++q2)
-                    sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], at_current ? cu[q2] : ut[q2], sq);
-                const double gq = v[q] - sq;
-                nx[q] = clip01(ut[q] + gq * inv_lw);
-            }
-        };
         for (int it = uw; it < n_my; it += kFU) {
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
@@ -266,23 +389,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 }
                 cost += ct;
             }
-            // n_iter2 iterations, two at a time so that (u_, u) rotate without register copies
-            int itn = 0;
-            for (; itn + 2 <= n2; itn += 2) {
-                double b0, b1, n1[NUB], n3[NUB];
-                lds2(beta32 + (uint32_t)itn * 8u, b0, b1);
-                step(up, u, v, b0, n1);
-                step(u, n1, v, b1, n3);
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) { up[q] = n1[q]; u[q] = n3[q]; }
-            }
-            if (itn < n2) {
-                double b0, n1[NUB];
-                lds1(beta32 + (uint32_t)itn * 8u, b0);
-                step(up, u, v, b0, n1);
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) { up[q] = u[q]; u[q] = n1[q]; }
-            }
+            if (at_current) fused_u_iterate<true, NUB>(u, up, v, beta32, n2, inv_lw);
+            else fused_u_iterate<false, NUB>(u, up, v, beta32, n2, inv_lw);
             // new iterate: global (other slot pair) and the stage (the C-warps form u (x) [R_trunc | u] and bx_u from it)
             if (live) {
 #pragma unroll
@@ -307,7 +415,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     } else if (warp < kFA) {
         // =========================================================================== A-warps: row statistics
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-        double na[S][KS > 0 ? KS : 1], au[S][NUB], P[S][NTRI];
+        double na[S][KS > 0 ? KS : 1], au[S][NUB], P[S][NTRI > 0 ? NTRI : 1];
         int jc[S];
         bool valid[S];
 #pragma unroll
@@ -328,6 +436,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 for (int q2 = q; q2 < NUB; ++q2) P[sb][tri_index(q, q2, NUB)] = au[sb][q] * au[sb][q2];
         }
         const unsigned rpitch = (unsigned)(g.ldr * 8);
+        const bool cols_full = 8 * (warp * S + S) <= N;       // every sample of this warp exists: no column masks
         for (int it = 0; it < n_my; ++it) {
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
@@ -338,46 +447,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             double acc[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-#pragma unroll
-            for (int rb = 0; rb < 2; ++rb) {
-                const int ra = 8 * rb + ti, rbw = ra + 4;          // the two rows of this lane's C fragment
-                const bool la = ra < nrows, lb = rbw < nrows;
-                // B operand: R_trunc[row_of_n(gi)][4 kk + ti], MMA column n = 2 t + e  <->  tile row 8 rb + t + 4 e
-                double rfrag[KS > 0 ? KS : 1];
-                const int rown = 8 * rb + (gi >> 1) + 4 * (gi & 1);
-#pragma unroll
-                for (int kk = 0; kk < KS; ++kk) {
-                    const int k = 4 * kk + ti;
-                    double t = 0.0;
-                    if (k < K) lds1(sb32 + a.offR + (uint32_t)rown * rpitch + (uint32_t)k * 8u, t);
-                    rfrag[kk] = t;
-                }
-#pragma unroll
-                for (int sb = 0; sb < S; ++sb) {
-                    double c0, c1;
-                    lds1(sb32 + (uint32_t)ra * a.pitchX + (uint32_t)jc[sb] * 8u, c0);
-                    lds1(sb32 + (uint32_t)rbw * a.pitchX + (uint32_t)jc[sb] * 8u, c1);
-                    double d0 = lds_weight<WT>(sb32 + a.offD + (uint32_t)ra * a.pitchD + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
-                    double d1 = lds_weight<WT>(sb32 + a.offD + (uint32_t)rbw * a.pitchD + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
-                    if (!valid[sb]) { c0 = 0.0; c1 = 0.0; }
-                    if (!(valid[sb] && la)) d0 = 0.0;
-                    if (!(valid[sb] && lb)) d1 = 0.0;
-#pragma unroll
-                    for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, na[sb][kk], rfrag[kk]);     // c = x - R_trunc a_k
-                    const double z0 = d0 * c0, z1 = d1 * c1;
-                    cost = fma(z0, c0, cost);
-                    cost = fma(z1, c1, cost);
-#pragma unroll
-                    for (int q = 0; q < NUB; ++q) {
-                        acc[(rb * 2 + 0) * NG + q] = fma(z0, au[sb][q], acc[(rb * 2 + 0) * NG + q]);
-                        acc[(rb * 2 + 1) * NG + q] = fma(z1, au[sb][q], acc[(rb * 2 + 1) * NG + q]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < NTRI; ++e) {
-                        acc[(rb * 2 + 0) * NG + NUB + e] = fma(d0, P[sb][e], acc[(rb * 2 + 0) * NG + NUB + e]);
-                        acc[(rb * 2 + 1) * NG + NUB + e] = fma(d1, P[sb][e], acc[(rb * 2 + 1) * NG + NUB + e]);
-                    }
-                }
+            if (cols_full && nrows == TR) {
+                fused_row_block<false, WT, KS, NUB, S>(a, sb32, nrows, 0, gi, ti, K, na, au, P, jc, valid, cost, acc);
+                fused_row_block<false, WT, KS, NUB, S>(a, sb32, nrows, 1, gi, ti, K, na, au, P, jc, valid, cost, acc);
+            } else {
+                fused_row_block<true, WT, KS, NUB, S>(a, sb32, nrows, 0, gi, ti, K, na, au, P, jc, valid, cost, acc);
+                fused_row_block<true, WT, KS, NUB, S>(a, sb32, nrows, 1, gi, ti, K, na, au, P, jc, valid, cost, acc);
             }
             // sum over the 8 samples of a block row (lanes sharing ti), then one partial per (warp, row, value)
             const int base = reduce_over_groups<NV>(acc, lane);
@@ -410,8 +485,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const unsigned upitch = (unsigned)(g.ldu * 8), rpitch = (unsigned)(g.ldr * 8);
         // B operand of the panel MMA: column c = 8 nb + gi of  u (x) [R_trunc | u]  =  (first factor u_q) x (second factor R_k or u_q2),
         // formed per k-step from the stage (the U-warp left the new u there)
-        unsigned fa_off[NBLK], fb_off[NBLK], fb_pitch[NBLK];
-        bool fzero[NBLK];
+        unsigned fa_off[NBLK], fa_pitch[NBLK], fb_off[NBLK], fb_pitch[NBLK];
+        const unsigned zero_off = a.rowX_bytes;      // the padding behind row 0 of X in every stage: zeroed at kernel start, never copied over
 #pragma unroll
         for (int nb = 0; nb < NBLK; ++nb) {
             const int c = 8 * nb + gi;
@@ -422,11 +497,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 while (e2 >= NUB - q) { e2 -= NUB - q; ++q; }
                 q2 = q + e2;
             }
-            fzero[nb] = c >= NCOL || q >= g.nu || (k >= 0 ? k >= K : q2 >= g.nu);
-            fa_off[nb] = a.offU + (unsigned)q * 8u;
-            fb_off[nb] = (k >= 0 && !fzero[nb]) ? a.offR + (unsigned)k * 8u : a.offU + (unsigned)q2 * 8u;
-            fb_pitch[nb] = (k >= 0 && !fzero[nb]) ? rpitch : upitch;
+            const bool fzero = c >= NCOL || q >= g.nu || (k >= 0 ? k >= K : q2 >= g.nu);
+            // a column that does not exist multiplies a zero by itself (no select in the loop)
+            fa_off[nb] = fzero ? zero_off : a.offU + (unsigned)q * 8u;
+            fa_pitch[nb] = fzero ? 0u : upitch;
+            fb_off[nb] = fzero ? zero_off : ((k >= 0) ? a.offR + (unsigned)k * 8u : a.offU + (unsigned)q2 * 8u);
+            fb_pitch[nb] = fzero ? 0u : ((k >= 0) ? rpitch : upitch);
         }
+        const bool cols_full = 8 * (cw * S + S) <= N;
         for (int it = 0; it < n_my; ++it) {
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
@@ -434,33 +512,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             mbar_wait(smem_u32(&ctl->full[s]), ph);
             const int nrows = tile_rows(it);
             const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
-#pragma unroll 2
-            for (int ks = 0; ks < TR / 4; ++ks) {
-                const int row = 4 * ks + ti;
-                const bool lrow = row < nrows;
-                double bfrag[NBLK], un[NUB];
-#pragma unroll
-                for (int nb = 0; nb < NBLK; ++nb) {
-                    double fa, fb;
-                    lds1(sb32 + fa_off[nb] + (uint32_t)row * upitch, fa);
-                    lds1(sb32 + fb_off[nb] + (uint32_t)row * fb_pitch[nb], fb);
-                    bfrag[nb] = fzero[nb] ? 0.0 : fa * fb;
-                }
-#pragma unroll
-                for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
-#pragma unroll
-                for (int mb = 0; mb < S; ++mb) {
-                    double x;
-                    lds1(sb32 + (uint32_t)row * a.pitchX + (uint32_t)jcC[mb] * 8u, x);
-                    double d = lds_weight<WT>(sb32 + a.offD + (uint32_t)row * a.pitchD + (uint32_t)jcC[mb] * (unsigned)sizeof(WT));
-                    if (!(validC[mb] && lrow)) { d = 0.0; x = 0.0; }
-                    const double dx = d * x;
-#pragma unroll
-                    for (int q = 0; q < NUB; ++q) paccx[mb][q] = fma(dx, un[q], paccx[mb][q]);
-#pragma unroll
-                    for (int nb = 0; nb < NBLK; ++nb) dmma884(pacc[mb][nb][0], pacc[mb][nb][1], d, bfrag[nb]);
-                }
-            }
+            if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, S, NBLK>(a, sb32, nrows, ti, fa_off, fa_pitch, fb_off, fb_pitch, jcC, validC, pacc, paccx);
+            else fused_panel_tile<true, WT, NUB, S, NBLK>(a, sb32, nrows, ti, fa_off, fa_pitch, fb_off, fb_pitch, jcC, validC, pacc, paccx);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[s]));
         }

@@ -13,7 +13,7 @@ from .engine import DeviceProblem, FitBatch
 from .init_func import wls_intercept, wls_all_samples, constrained_nndsvd, nndsvd_initialize
 
 __all__ = ["set_seed", "cost_f_w", "projection_simplex_sort_2d", "init_BSSMF_md", "init_BSSMF_md_p",
-           "mdwbssmf_deconv", "mdwbssmf_deconv_p", "unsupervised_deconv", "last_fit_info"]
+           "mdwbssmf_deconv", "mdwbssmf_deconv_p", "unsupervised_deconv", "last_fit_info", "best_of_restarts"]
 
 _last = {}
 
@@ -35,9 +35,12 @@ def cost_f_w(y, R, alpha, d_x):
     R = np.asarray(R)
     alpha = np.asarray(alpha)
     Kt = R.shape[1]
-    # the kernels take [R_trunc | u]; any split is equivalent for the cost, use the last column as "u"
-    prob = DeviceProblem(y, d_x, R[:, :Kt - 1] if Kt > 1 else None)
-    batch = FitBatch(prob, 1, [R[:, Kt - 1:]], [alpha], mode=_lib.DMF_MODE_PARTIAL if Kt > 1 else _lib.DMF_MODE_UNSUPERVISED)
+    # the kernels take [R_trunc | u]; any split is equivalent for the cost.  The library pads both blocks to even widths and needs
+    # their sum <= 32: the last TWO columns are "u" when Kt is even, the last one when it is odd (works up to Kt = 32)
+    nu = 2 if (Kt % 2 == 0 and Kt >= 2) else 1
+    prob = DeviceProblem(y, d_x, R[:, :Kt - nu] if Kt > nu else None)
+    batch = FitBatch(prob, nu, [R[:, Kt - nu:]], [alpha], mode=_lib.DMF_MODE_PARTIAL if Kt > nu else _lib.DMF_MODE_UNSUPERVISED,
+                     engine="stream")
     batch.pass_init()
     cost = batch.states()[0].cost
     batch.close()
@@ -117,7 +120,8 @@ def init_BSSMF_md_p(init_option, meth_frequency, d_x, R_trunc, n_u, purity, rb_a
 
 
 def _solve(mode, u, alpha, meth_frequency, d_x, R_trunc, n_u, n_iter1, n_iter2, tol, purity=None):
-    prob = DeviceProblem(meth_frequency, d_x, R_trunc)
+    # `meth_frequency` may be a DeviceProblem that is already resident in HBM (the n_u sweep of ic.py fits the same data many times)
+    prob = meth_frequency if isinstance(meth_frequency, DeviceProblem) else DeviceProblem(meth_frequency, d_x, R_trunc)
     batch = FitBatch(prob, n_u, [np.asarray(u).reshape(-1, n_u)], [np.asarray(alpha)], mode=mode, purity=purity)
     states = batch.fit(n_iter1, n_iter2, tol)
     (u_out, a_out, n_outer, cost), = batch.results(states)
@@ -158,3 +162,35 @@ def unsupervised_deconv(meth_frequency, n_u, d_x, init_option, n_iter1=100000, n
     else:
         raise NotImplementedError(f"init option {init_option!r} is not available on the B200 path")
     return _solve(_lib.DMF_MODE_UNSUPERVISED, u, alpha, meth_frequency, d_x, None, n_u, n_iter1, n_iter2, tol)
+
+
+def best_of_restarts(meth_frequency, d_x, R_trunc, n_u, init_option, seed, n_restarts, n_iter1, n_iter2, tol, purity=None,
+                     distinct_seeds=True):
+    """The restart loops of demethify.py:167-203 as ONE batched launch set: n_restarts fits, the one with the lowest final cost
+    wins (first on ties, `cost < best_cost` at :199-203).  The reference re-seeds every restart with the same seed, so its
+    restarts are one and the same fit (SURVEY Q2): distinct_seeds=False reproduces that (a single fit is run);
+    distinct_seeds=True draws restart r from seed + r, the convention ic.py:196 uses.  -> (u, alpha, best restart, costs)."""
+    if not distinct_seeds or n_restarts <= 1:
+        seeds = [seed]
+    else:
+        base = seed[0] if isinstance(seed, (list, tuple)) else seed
+        seeds = [base + r for r in range(n_restarts)]
+    prob = meth_frequency if isinstance(meth_frequency, DeviceProblem) else DeviceProblem(meth_frequency, d_x, R_trunc)
+    src = prob if init_option in ("uniform_", "uniform", "beta") else meth_frequency
+    inits = []
+    for s in seeds:
+        if R_trunc is None:
+            raise NotImplementedError("best_of_restarts: reference-free fits go through unsupervised_deconv one seed at a time")
+        if purity is not None:
+            u0, _, a0 = init_BSSMF_md_p(init_option, src, d_x, R_trunc, n_u, purity, seed=s)
+        else:
+            u0, _, a0 = init_BSSMF_md(init_option, src, d_x, R_trunc, n_u, seed=s)
+        inits.append((np.asarray(u0).reshape(-1, n_u), np.asarray(a0)))
+    mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
+    batch = FitBatch(prob, n_u, [i[0] for i in inits], [i[1] for i in inits], mode=mode, purity=purity)
+    res = batch.results(batch.fit(n_iter1, n_iter2, tol))
+    costs = [r[3] for r in res]
+    best = int(np.argmin(costs))
+    _last.update(n_outer=res[best][2], cost=costs[best], launches=batch.launch_count(), geometry=batch.geometry(), engine=batch.engine)
+    batch.close()
+    return res[best][0], res[best][1], best, costs

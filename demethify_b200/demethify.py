@@ -13,7 +13,8 @@ import pandas as pd
 
 from . import set_engine, set_precision
 from .bootstrap import bt_ci
-from .deconvolution import (cost_f_w, init_BSSMF_md, init_BSSMF_md_p, mdwbssmf_deconv, mdwbssmf_deconv_p, unsupervised_deconv)
+from .deconvolution import (best_of_restarts, cost_f_w, init_BSSMF_md, init_BSSMF_md_p, mdwbssmf_deconv, mdwbssmf_deconv_p,
+                            unsupervised_deconv)
 from .ic import evaluate_best_ic
 from .init_func import wls_all_samples
 
@@ -48,8 +49,15 @@ def build_parser():
     p.add_argument("--noprint", action="store_true", help="Doesnt show the logo.")
     p.add_argument("--bedmethyl", action="store_true", help="Flag to indicate that the input will be bedmethyl files, modkit style")
     p.add_argument("--precision", choices=["fp64", "fp32"], default="fp64", help="(B200 path) arithmetic of the solver kernels")
-    p.add_argument("--engine", choices=["auto", "gram", "stream"], default="auto",
-                   help="(B200 path) device engine: per-iteration streaming passes, or Gram-form statistics (default where supported)")
+    p.add_argument("--engine", choices=["auto", "fused", "gram", "stream"], default="auto",
+                   help="(B200 path) device engine: one fused pass per outer iteration (default where supported), Gram-form statistics, "
+                        "or per-iteration streaming passes")
+    p.add_argument("--distinct-restarts", action="store_true",
+                   help="(B200 path) --restart R draws restart r from seed + r and keeps the lowest cost (the reference re-seeds every "
+                        "restart identically, so its R restarts are one fit); with --confidence every resample is fitted R times")
+    p.add_argument("--shard", choices=["fits", "rows"], default="fits",
+                   help="(B200 path, under torchrun) how --ic / --confidence use several GPUs: independent fits per GPU, or the CpG rows "
+                        "of every fit sharded over the GPUs")
     return p
 
 
@@ -124,10 +132,33 @@ def read_inputs(args):
     return meth_f, counts, ref, header
 
 
+def _init_distributed():
+    """One process per GPU under torchrun (RANK / WORLD_SIZE / LOCAL_RANK in the environment): NCCL process group, device by
+    local rank.  Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), dist.get_world_size()
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    if args.plot:
+        try:
+            from . import plotting  # noqa: F401
+        except ImportError:
+            sys.stderr.write("Error: --plot is not part of the B200 path (presentation only, SURVEY.md 2.1 row 9): run the reference's "
+                             "plotting.py on the CSV files this command writes.\n")
+            sys.exit(1)
     set_precision(args.precision)
     set_engine(args.engine)
+    rank, world = _init_distributed()
     args.restart = 1 if args.restart is None else args.restart[0]
     if not args.iterations:
         args.iterations = [100, 500] if args.purity else [10000, 20]
@@ -155,7 +186,7 @@ def main(argv=None):
     outdir = os.path.join(os.getcwd(), args.outdir)
     if not os.path.exists(outdir):
         print(f"Creating directory {outdir} to store results")
-        os.mkdir(outdir)
+        os.makedirs(outdir, exist_ok=True)
     if args.nbunknown is None:
         args.nbunknown = [0]
     n_u = args.nbunknown[0]
@@ -167,12 +198,12 @@ def main(argv=None):
     bt_results = None
     if args.confidence:
         bt_results = bt_ci(args.confidence[0], args.confidence[1], n_u, meth_f, counts, ref, args.init, it1, it2, tol, header, outdir,
-                           args.methfreq, args.purity, args.seed)
+                           args.methfreq, args.purity, args.seed, restarts=args.restart if args.distinct_restarts else 1)
     list_ic, ic_n_u = None, None
     ref_estimate = None
     if args.ic:
         ref_estimate, proportions, ic_n_u, list_ic = evaluate_best_ic(meth_f, ref, counts, args.init, args.ic, args.seed, iter1=it1,
-                                                                      iter2=it2, tol=tol, n_restarts=nb_r)
+                                                                      iter2=it2, tol=tol, n_restarts=nb_r, shard=args.shard)
         unknown_header = ["unknown_cell_" + str(i + 1) for i in range(ic_n_u)]
         header = header + unknown_header
     elif not args.ref:
@@ -181,7 +212,10 @@ def main(argv=None):
         unknown_header = ["unknown_cell_" + str(i + 1) for i in range(n_u)]
         header = unknown_header
     elif n_u > 0 and meth_f.shape[1] >= 1:
-        if args.purity:
+        if args.distinct_restarts and args.restart > 1:
+            ref_estimate, proportions, _best, _costs = best_of_restarts(meth_f, counts, ref, n_u, args.init, args.seed, args.restart, it1, it2,
+                                                                       tol, purity=purity if args.purity else None)
+        elif args.purity:
             u, R, alpha = init_BSSMF_md_p(args.init, meth_f, counts, ref, n_u, purity, seed=args.seed)
             ref_estimate, proportions = mdwbssmf_deconv_p(u, R, alpha, meth_f, counts, ref, n_u, purity, n_iter1=it1, n_iter2=it2, tol=tol)
         else:
@@ -194,9 +228,11 @@ def main(argv=None):
         unknown_header = []
     else:
         sys.exit(f'Invalid number of unknown value! : "{args.nbunknown}" ')
+    time_tot = time() - t0
+    if rank != 0:                      # under torchrun every rank computed the same result; rank 0 writes the files
+        return
     if ref_estimate is not None:
         pd.DataFrame(ref_estimate).to_csv(outdir + "/methylation_profile_estimate.csv", index=False, header=unknown_header)
-    time_tot = time() - t0
 
     proportions = pd.DataFrame(proportions)
     proportions.index = header

@@ -104,6 +104,11 @@ class DeviceProblem:
             self.Rk = _pad_cols(Rk, _even(self.K))
         self.set_weights(D, narrow_weights)
 
+    @property
+    def shape(self):
+        """(M, N) like the meth_frequency array it holds (lets the reference-shaped entry points take a resident problem)."""
+        return (self.M, self.N)
+
     def set_weights(self, D, narrow=True):
         """Upload d_x.  Integer coverage in [0, 65535] is stored as uint16 (2 B/entry instead of 8)."""
         raw = to_device(D, None, self.device)

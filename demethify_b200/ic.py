@@ -9,11 +9,11 @@ import torch.distributed as dist
 import tqdm
 
 from . import _lib
-from .deconvolution import init_BSSMF_md, mdwbssmf_deconv, unsupervised_deconv, cost_f_w
+from .deconvolution import init_BSSMF_md, mdwbssmf_deconv, unsupervised_deconv, cost_f_w, last_fit_info
 from .engine import DeviceProblem, FitBatch
 
 __all__ = ["compute_bic", "compute_aic", "compute_consensus_matrix", "compute_ccc", "run_deconvolution", "bicross_validation",
-           "evaluate_best_ic", "merge_sweep"]
+           "evaluate_best_ic", "merge_sweep", "sweep_member_supported"]
 
 
 def _world(group=None):
@@ -61,13 +61,18 @@ def compute_aic(cost, n_u, n_cpg, n_ct, n_samples):
 
 
 def compute_consensus_matrix(alpha_runs):
-    """ic.py:24-37."""
-    n_samples = alpha_runs[0].shape[1]
-    consensus = np.zeros((n_samples, n_samples))
-    for alpha in alpha_runs:
-        lab = np.argmax(alpha, axis=0)
-        consensus += (lab[:, None] == lab[None, :])
-    return consensus / len(alpha_runs)
+    """ic.py:24-37: fraction of the runs in which two samples share their dominant cell type (argmax of the alpha column) - one
+    kernel pair of the library (dmf_consensus) on the stacked runs."""
+    import ctypes as C
+    import torch
+    from .engine import _stream_ptr, to_device
+    stack = to_device(np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.float64) for a in alpha_runs])), torch.float64)
+    n_runs, kt, n = stack.shape
+    labels = torch.empty((n_runs, n), dtype=torch.int32, device=stack.device)
+    out = torch.empty((n, n), dtype=torch.float64, device=stack.device)
+    _lib.check(_lib.lib().dmf_consensus(C.c_void_p(stack.data_ptr()), n_runs, kt, n, C.c_void_p(labels.data_ptr()),
+                                        C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out.cpu().numpy()
 
 
 def compute_ccc(alpha_runs):
@@ -99,7 +104,8 @@ def _batched_fits(prob_list, ref, n_u, inits, iter1, iter2, tol):
     return [(u, np.hstack((ref, u.reshape(-1, n_u))), a, c) for (u, a, _n, c) in res]
 
 
-def bicross_validation(meth_f, n_u, counts, iter1, iter2, tol, n_folds=10, seed=None, ref=None, init_option="uniform_", fraction=0.3):
+def bicross_validation(meth_f, n_u, counts, iter1, iter2, tol, n_folds=10, seed=None, ref=None, init_option="uniform_", fraction=0.3,
+                       base=None):
     """ic.py:58-89.  The fold masks come from numpy's GLOBAL stream, which every fold's init re-seeds:
     the same numpy calls are issued in the same order, then all folds are fitted as one batch."""
     np.random.seed(seed)
@@ -120,7 +126,7 @@ def bicross_validation(meth_f, n_u, counts, iter1, iter2, tol, n_folds=10, seed=
                                            tol=tol, seed=seed)
             folds.append((train_mask, test_mask, u, alpha))
     if ref is not None and folds:
-        base = DeviceProblem(meth_f, counts, ref)
+        base = base if base is not None else DeviceProblem(meth_f, counts, ref)
         probs = [base.masked(f[0]) for f in folds]
         fits = _batched_fits(probs, np.asarray(ref), n_u, [(f[2], f[3]) for f in folds], iter1, iter2, tol)
     else:
@@ -134,49 +140,125 @@ def bicross_validation(meth_f, n_u, counts, iter1, iter2, tol, n_folds=10, seed=
     return total_press, best_u, best_alpha       # the reference returns total, not mean (Q15)
 
 
-def evaluate_best_ic(meth_f, ref, counts, init_option, ic, seed, iter1, iter2, tol, n_restarts=5, n_u_values=None):
-    """ic.py:169-218.  n_u_values defaults to the reference's hard-coded range(1, 26) (Q9)."""
+def sweep_member_supported(K, n_u):
+    """The library pads the known and the unknown block to even widths and needs their sum <= 32 (include/demethify_b200.h)."""
+    return n_u >= 0 and (K + (K & 1)) + (n_u + (n_u & 1)) <= 32
+
+
+def _row_sharded_member(prob_local, lo, hi, M, K, N, n_u, init_option, seed, iter1, iter2, tol, group):
+    """One sweep member with the CpG rows sharded over the ranks of `group` (BASELINE config 5): every rank draws the same
+    initial iterate from the same seed, keeps its rows of u and runs the row-sharded solver -> (u_local, alpha, cost)."""
+    from .bootstrap import _shape_only_init
+    from .sharded import mdwbssmf_deconv_sharded
+    if init_option not in ("uniform_", "beta"):
+        raise NotImplementedError("row-sharded sweeps draw the initial iterate from shapes only: --init uniform_ or beta")
+    # RandomState(seed) == the reference's set_seed(seed) + global stream (int -> init_genrand, list -> init_by_array, Q1)
+    u0, a0 = _shape_only_init(seed, init_option if n_u <= N else "uniform_", M, K, N, n_u, with_zero_guard=True)
+    u_loc, alpha, _n, cost = mdwbssmf_deconv_sharded(u0[lo:hi], a0, prob_local, None, None, n_u, n_iter1=iter1, n_iter2=iter2, tol=tol,
+                                                     group=group)
+    return u_loc, alpha, cost
+
+
+def evaluate_best_ic(meth_f, ref, counts, init_option, ic, seed, iter1, iter2, tol, n_restarts=5, n_u_values=None, shard="fits",
+                     group=None):
+    """ic.py:169-218.  n_u_values defaults to the reference's hard-coded range(1, 26) (Q9); 0 may be listed explicitly (AIC / BIC):
+    it is the reference-based fit of demethify.py:209-213 (the reference's own loop breaks at 0).
+
+    X, d_x and R_trunc are uploaded ONCE and stay resident in HBM for the whole sweep; the criterion of a member comes from the
+    cost the solver finished with (the reference recomputes the same number with cost_f_w, ic.py:206).  Members whose shape the
+    library cannot run (known + unknown types, each padded to even, > 32) are reported up front, skipped and recorded as inf.
+
+    Under torch.distributed: shard="fits" (default) gives position p of the sweep to rank p mod world (every member re-seeds and
+    is independent); shard="rows" runs EVERY member with the CpG rows sharded over the ranks (one all-reduce per outer
+    iteration, sharded.py) - the partitioning for matrices that are large per member (AIC / BIC, shape-only inits)."""
     n_u_values = range(1, 25 + 1) if n_u_values is None else n_u_values
-    n_cpg, n_samples = np.asarray(meth_f).shape
+    meth_f = np.asarray(meth_f)
+    n_cpg, n_samples = meth_f.shape
     n_ct = ref.shape[1] if ref is not None else 0
-    best_ic, best_n_u, best_u_overall, best_alpha_overall = float("inf"), None, None, None
-    list_result = []
+    best_n_u, best_u_overall, best_alpha_overall = None, None, None
     if ic == "minka":
         # the reference raises here: run_deconvolution() is called with three arguments missing (ic.py:189, Q7)
         raise TypeError("run_deconvolution() missing 3 required positional arguments: 'iter1', 'iter2', and 'tol'")
     if isinstance(seed, (list, tuple)) and ic == "CCC":
         raise TypeError("can only concatenate list (not \"int\") to list")      # ic.py:196 with `--seed S` (Q1)
     n_u_values = list(n_u_values)
-    rank, world = _world()
+    unsupported = [n for n in n_u_values if not sweep_member_supported(n_ct, n)]
+    if unsupported:
+        import warnings
+        warnings.warn(f"n_u = {unsupported} with {n_ct} known cell types exceed the library limit (known + unknown types, each padded "
+                      "to even, <= 32): these members are skipped and recorded as inf", RuntimeWarning, stacklevel=2)
+    if 0 in n_u_values and (ic not in ("AIC", "BIC") or ref is None):
+        raise ValueError("n_u = 0 (reference-based fit) is available for AIC / BIC with a reference matrix only")
+    rank, world = _world(group)
+    rows_mode = shard == "rows" and world > 1
+    if rows_mode and (ic not in ("AIC", "BIC") or ref is None):
+        raise NotImplementedError("row-sharded sweeps: AIC / BIC with a reference matrix")
+    if rows_mode:
+        from .sharded import row_range
+        lo, hi = row_range(n_cpg, rank, world)
+        prob = DeviceProblem(meth_f[lo:hi], np.asarray(counts)[lo:hi], np.asarray(ref)[lo:hi])
+    else:
+        lo, hi = 0, n_cpg
+        prob = DeviceProblem(meth_f, counts, ref)                       # resident for the whole sweep
+    src = prob if init_option in ("uniform_", "uniform", "beta") else meth_f      # the SVD init reads the host matrix
     local_results, local_payload, local_best = {}, {}, float("inf")
-    positions = list(range(len(n_u_values)))[rank::world]          # under torch.distributed the sweep is sharded over the ranks
+    positions = list(range(len(n_u_values))) if rows_mode else list(range(len(n_u_values)))[rank::world]
     for pos in tqdm.tqdm(positions, disable=rank != 0):
         n_u = n_u_values[pos]
-        if ic == "CCC":
+        if n_u in unsupported:
+            local_results[pos] = float("inf")
+            continue
+        if n_u == 0:
+            from .init_func import wls_all_samples
+            if rows_mode:
+                raise NotImplementedError("n_u = 0 in a row-sharded sweep")
+            alpha = wls_all_samples(prob, None, None, y_is_dx=True)          # demethify.py:209-213
+            u = np.zeros((n_cpg, 0))
+            cost = cost_f_w(meth_f, np.asarray(ref), alpha, counts)
+            ic_result = compute_bic(cost, 0, n_cpg, n_ct, n_samples) if ic == "BIC" else compute_aic(cost, 0, n_cpg, n_ct, n_samples)
+        elif ic == "CCC":
             if ref is not None:
-                prob = DeviceProblem(meth_f, counts, ref)
-                inits = [init_BSSMF_md(init_option, meth_f, counts, ref, n_u, seed=seed + r) for r in range(n_restarts)]
+                inits = [init_BSSMF_md(init_option, src, counts, ref, n_u, seed=seed + r) for r in range(n_restarts)]
                 fits = _batched_fits(prob, np.asarray(ref), n_u, [(i[0], i[2]) for i in inits], iter1, iter2, tol)
                 alpha_runs = [f[2] for f in fits]
                 u, alpha = fits[-1][0], fits[-1][2]
             else:
                 alpha_runs = []
                 for r in range(n_restarts):
-                    u, R, alpha = run_deconvolution(meth_f, counts, ref, n_u, init_option, seed + r, iter1, iter2, tol)
+                    u, alpha = unsupervised_deconv(src, n_u, counts, init_option, n_iter1=iter1, n_iter2=iter2, tol=tol, seed=seed + r)
                     alpha_runs.append(alpha)
             ic_result = -compute_ccc(alpha_runs)
         elif ic == "BCV":
             ic_result, u, alpha = bicross_validation(meth_f, n_u, counts, iter1, iter2, tol, fraction=0.3, n_folds=n_restarts, seed=seed,
-                                                     ref=ref, init_option=init_option)
+                                                     ref=ref, init_option=init_option, base=prob)
         else:
-            u, R, alpha = run_deconvolution(meth_f, counts, ref, n_u, init_option, seed, iter1, iter2, tol)
-            cost = cost_f_w(meth_f, R, alpha, counts)
+            if rows_mode:
+                u, alpha, cost = _row_sharded_member(prob, lo, hi, n_cpg, n_ct, n_samples, n_u, init_option, seed, iter1, iter2, tol, group)
+            elif ref is not None:
+                u0, R0, a0 = init_BSSMF_md(init_option, src, counts, ref, n_u, seed=seed)
+                u, alpha = mdwbssmf_deconv(u0, R0, a0, prob, None, None, n_u, n_iter1=iter1, n_iter2=iter2, tol=tol)
+                cost = last_fit_info()["cost"]
+            else:
+                u, alpha = unsupervised_deconv(src, n_u, counts, init_option, n_iter1=iter1, n_iter2=iter2, tol=tol, seed=seed)
+                cost = last_fit_info()["cost"]
             ic_result = compute_bic(cost, n_u, n_cpg, n_ct, n_samples) if ic == "BIC" else compute_aic(cost, n_u, n_cpg, n_ct, n_samples)
         local_results[pos] = ic_result
         if ic_result < local_best:                 # the overall best (first position of the minimum) is the LAST strict improvement
             local_best = ic_result                 # inside its rank's share: keep only that one
             local_payload = {pos: (u, alpha)}
-    list_result, best_pos, payload = merge_sweep(local_results, local_payload, len(n_u_values))
+    if rows_mode:
+        # every rank evaluated every member on its rows: criteria are replicated, u of the winner is gathered row range by row range
+        values = [local_results[p] for p in range(len(n_u_values))]
+        best_pos = min(local_payload) if local_payload else None
+        payload = None
+        if best_pos is not None:
+            u_loc, alpha = local_payload[best_pos]
+            parts = [None] * world
+            dist.all_gather_object(parts, np.asarray(u_loc), group=group)
+            payload = (np.concatenate(parts, axis=0), alpha)
+        list_result = values
+    else:
+        list_result, best_pos, payload = merge_sweep(local_results, local_payload, len(n_u_values), group)
     if best_pos is not None:
         best_n_u, (best_u_overall, best_alpha_overall) = n_u_values[best_pos], payload
     return best_u_overall, best_alpha_overall, best_n_u, list_result

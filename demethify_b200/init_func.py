@@ -4,7 +4,8 @@
                                             Lawson-Hanson on the GPU (dmf_wls_fit).  `wls_all_samples` is the batched
                                             form every internal caller uses (all sample columns in one launch set).
   nndsvd_initialize    init_func.py:40-82  — NNDSVD; the thin SVD runs in cuSOLVER through torch.linalg.svd (a library
-                                            call made once per fit), the rest is elementwise glue.
+                                            call made once per fit), the sign split / norms / scaling in
+                                            a kernel of the library (dmf_nndsvd_split).
   constrained_nndsvd   init_func.py:17-37
 ICA (init_func.py:99-176) forms an M x M covariance and is out of scope.
 """
@@ -51,43 +52,34 @@ def wls_intercept(x, d_x, R_full):
     return col if x.ndim == 2 else col[:, 0]
 
 
-def _pos_neg(v):
-    return np.maximum(v, 0), np.maximum(-v, 0)
+def _nndsvd_device(Vt, rank):
+    """NNDSVD factors of a non-negative device matrix: thin SVD in cuSOLVER (a library call made once per fit, SURVEY 2.1
+    row 3), then sign split / norms / scaling in one kernel of the library (dmf_nndsvd_split) -> device (W, H)."""
+    Ut, St, Vh = torch.linalg.svd(Vt, full_matrices=False)
+    Ut, Vh = Ut.contiguous(), Vh.contiguous()
+    M, N = Vt.shape
+    W = torch.empty((M, rank), dtype=torch.float64, device=Vt.device)
+    H = torch.empty((rank, N), dtype=torch.float64, device=Vt.device)
+    _lib.check(_lib.lib().dmf_nndsvd_split(C.c_void_p(Ut.data_ptr()), Ut.shape[1], C.c_void_p(St.data_ptr()), C.c_void_p(Vh.data_ptr()),
+                                           Vh.shape[1], M, N, int(rank), C.c_void_p(W.data_ptr()), C.c_void_p(H.data_ptr()), _stream_ptr()))
+    return W, H
 
 
 def nndsvd_initialize(V, rank, flag=0):
-    """init_func.py:40-82 (flag 0/1/2 as in the reference)."""
-    V = np.asarray(V, dtype=np.float64)
-    if np.any(V < 0):
+    """init_func.py:40-82: NNDSVD initialisation of a non-negative matrix; `flag` picks what replaces the zeros of the factors
+    (0: nothing, 1: the mean of V, 2: mean(V) * uniform(0, 1) / 100 drawn from numpy's global stream, W first)."""
+    Vt = to_device(np.asarray(V, dtype=np.float64), torch.float64)
+    if bool((Vt < 0).any()):
         raise ValueError("The input matrix contains negative elements.")
-    Ut, St, Et = torch.linalg.svd(to_device(V, torch.float64), full_matrices=False)     # cuSOLVER gesvd, once per fit
-    U, S, E = Ut.cpu().numpy(), St.cpu().numpy(), Et.cpu().numpy().T
-    W = np.zeros((V.shape[0], rank))
-    H = np.zeros((rank, V.shape[1]))
-    W[:, 0] = np.sqrt(S[0]) * np.abs(U[:, 0])
-    H[0, :] = np.sqrt(S[0]) * np.abs(E[:, 0].T)
-    for i in range(1, rank):
-        uup, uun = _pos_neg(U[:, i])
-        vvp, vvn = _pos_neg(E[:, i])
-        n_uup, n_vvp = np.linalg.norm(uup, 2), np.linalg.norm(vvp, 2)
-        n_uun, n_vvn = np.linalg.norm(uun, 2), np.linalg.norm(vvn, 2)
-        termp, termn = n_uup * n_vvp, n_uun * n_vvn
-        if termp >= termn:
-            W[:, i] = np.sqrt(S[i] * termp) / n_uup * uup
-            H[i, :] = np.sqrt(S[i] * termp) / n_vvp * vvp.T
-        else:
-            W[:, i] = np.sqrt(S[i] * termn) / n_uun * uun
-            H[i, :] = np.sqrt(S[i] * termn) / n_vvn * vvn.T
-    W[W < 1e-11] = 0
-    H[H < 1e-11] = 0
-    if flag == 1:
-        avg = np.mean(V)
-        W[W == 0] = avg
-        H[H == 0] = avg
-    elif flag == 2:
-        avg = np.mean(V)
-        W[W == 0] = avg * np.random.uniform(0, 1, size=W[W == 0].shape) / 100
-        H[H == 0] = avg * np.random.uniform(0, 1, size=H[H == 0].shape) / 100
+    if rank > min(Vt.shape):
+        raise IndexError(f"index {min(Vt.shape)} is out of bounds for axis 1 with size {min(Vt.shape)}")
+    Wd, Hd = _nndsvd_device(Vt, rank)
+    W, H = Wd.cpu().numpy(), Hd.cpu().numpy()
+    if flag in (1, 2):
+        avg = float(Vt.mean())
+        for F in (W, H):
+            zeros = F == 0
+            F[zeros] = avg if flag == 1 else avg * np.random.uniform(0, 1, size=int(zeros.sum())) / 100
     return W, H
 
 
@@ -98,5 +90,4 @@ def constrained_nndsvd(Y, W1, counts, rank, flag=0):
     H1 = wls_all_samples(Y, counts, W1)
     Y_residual = np.maximum(Y - W1 @ H1, 1e-8)
     W2, H2 = nndsvd_initialize(Y_residual, rank=rank, flag=flag)
-    W2 = np.clip(W2, 0, 1)
-    return np.hstack([W1, W2]), np.vstack([H1, H2])
+    return np.hstack([W1, np.clip(W2, 0, 1)]), np.vstack([H1, H2])

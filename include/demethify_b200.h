@@ -243,6 +243,20 @@ int dmf_pack_weights_u16(const void* src, int32_t src_kind /*0 f64, 1 f32, 2 i64
 int dmf_gather_rows(const void* src, const int32_t* rows, int64_t n_rows, int64_t row_elems,
                     int32_t elem_bytes, void* dst, void* stream);
 
+/* the steps right before / after the path ------------------------------------------ */
+/* NNDSVD (init_func.py:40-69) on the factors of a thin SVD (device pointers; U is M x ldu row-major, Vh is r x ldv):
+ * W (M x rank) and H (rank x N) row-major; component 0 = sqrt(S_0) |u_0|, |v_0|; component i >= 1 = the sign pattern with the
+ * larger product of norms, scaled by sqrt(S_i term) / norm; entries < 1e-11 are set to 0 (flag = 0 of the reference). */
+int dmf_nndsvd_split(const double* U, int64_t ldu, const double* S, const double* Vh, int64_t ldv, int64_t M, int32_t N, int32_t rank,
+                     double* W, double* H, void* stream);
+/* np.percentile(stack, [q_lo, q_hi], axis=0), default linear rule (bootstrap.py:53-54, :77-78): stack is B x P row-major (one row
+ * per resample), q in percent.  Selection per entry, no sort; needs floor((B-1) q_lo/100) + 2 and B - floor((B-1) q_hi/100) to be
+ * at most dmf_percentile_max_keep() (DMF_E_SHAPE otherwise). */
+int dmf_percentile_max_keep(void);
+int dmf_percentile_bounds(const double* stack, int32_t B, int64_t P, double q_lo, double q_hi, double* out_lo, double* out_hi, void* stream);
+/* compute_consensus_matrix (ic.py:24-37): alpha_runs is n_runs x Kt x N, labels_ws n_runs x N int32 scratch, consensus N x N. */
+int dmf_consensus(const double* alpha_runs, int32_t n_runs, int32_t Kt, int32_t N, int32_t* labels_ws, double* consensus, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
