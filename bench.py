@@ -22,8 +22,11 @@ metric = update iterations / second (inner iterations of U and alpha); fits/s = 
   cpu_baseline / --impl reference : the numpy port of the reference loop (oracle/) on the host cores, on a
               bounded row sample of the same workload (cost is linear in M; the sample and the scaling are stated)
 
-N > 1 GPUs: fit sharding (restarts / n_u sweep members are independent fits, ic.py:192-207): every rank runs
-its own fit on its own copy of the problem, no data-path collective -> "scaling": "weak".
+N > 1 GPUs: the headline `value` is ONE fit with its CpG rows sharded over the GPUs (BASELINE config 5's partitioning, SURVEY 8 e1
+(ii)): per outer iteration one fused pass over a rank's rows, one all-reduce of the per-sample statistics (in-kernel over NVLink peer
+memory), then the identical test / alpha iterations on every rank -> "scaling": "strong".  The leg first checks, on 5 outer
+iterations, that alpha is bit-identical on all ranks and equals the one-GPU fit of the same data to 1e-9 (`row_sharded.parity`).
+`fit_sharded` = the other partitioning (independent fits, one per GPU, no collective; weak scaling) as an extra key.
 """
 import argparse
 import json
@@ -104,6 +107,8 @@ def cpu_reference_leg(steps, warmup, rows=CPU_SAMPLE_ROWS, data=None):
     """The reference algorithm's numpy port (oracle/bssmf_numpy.py, pinned to the reference by
     tests/test_oracle_golden.py) timed on the host cores.  One step = ONE outer iteration on a row sample.
     `data` = (X, D, Rk, u0, a0) host arrays of the GPU arm (first `rows` rows); else a problem of the same recipe is drawn."""
+    if data is not None:
+        data = (data[0], np.asarray(data[1]).astype(np.int64), data[2], data[3], data[4])
     from oracle import bssmf_numpy as orc
     threads = blas_threads()
     if data is None:
@@ -198,7 +203,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- synthetic inputs, generated on the device (same recipe as synth_host), then mirrored into pinned host memory
     gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    gen.manual_seed(1234)          # the SAME problem on every rank: at N > 1 the headline is ONE fit with its rows sharded
     Kt = K_KNOWN + N_UNK
     conc = torch.rand(Kt, device=dev, generator=gen, dtype=torch.float64) * 0.8 + 0.2
     g1 = torch._standard_gamma(conc.expand(M, Kt).contiguous(), generator=gen)
@@ -217,10 +222,11 @@ def run_b200(args, rank, world, local_rank):
     Rk = Rf[:, :K_KNOWN].contiguous()
     del Rf
     hX = torch.empty(X.shape, dtype=torch.float64, pin_memory=True); hX.copy_(X)
-    hD = torch.empty(D.shape, dtype=torch.int64, pin_memory=True); hD.copy_(D)
+    # coverage as the CLI reader stages it (demethify_b200/demethify.py read_inputs): uint16 in page-locked memory
+    hD = torch.empty(D.shape, dtype=torch.uint16, pin_memory=True); hD.view(torch.int16).copy_(D.to(torch.int16))      # (values < 2^15: the int16 view is exact)
     hR = torch.empty(Rk.shape, dtype=torch.float64, pin_memory=True); hR.copy_(Rk)
     u0, R0_unused, a0 = None, None, None
-    rs = np.random.RandomState(1 + rank)
+    rs = np.random.RandomState(1)
     u0 = rs.uniform(size=(M, N_UNK)); a0 = rs.dirichlet(np.ones(Kt), N_S).T.copy()
     hU = torch.empty(u0.shape, dtype=torch.float64, pin_memory=True); hU.copy_(torch.from_numpy(u0))
     hA = torch.empty(a0.shape, dtype=torch.float64, pin_memory=True); hA.copy_(torch.from_numpy(a0))
@@ -346,51 +352,69 @@ def run_b200(args, rank, world, local_rank):
         sb.close()
         del sb
 
-    # ---- CpG-row sharding of ONE 1M-row fit over the ranks (strong scaling; NCCL all-reduce of the per-sample statistics
-    # and of the cost every outer iteration): rank r contributes M / world of its own rows, alpha is replicated
+    # ---- N > 1: CpG-row sharding of ONE 1M-row fit over the ranks (BASELINE config 5's partitioning; strong scaling).  Rank r holds
+    # rows row_range(M, r, world) of X, d_x, R_trunc, u and a replica of alpha; per outer iteration ONE fused pass over its rows, ONE
+    # all-reduce of [G_j | bx_j | cost, ||u||^2] (in-kernel over NVLink peer memory; NCCL if symmetric memory is unavailable) and the
+    # per-sample kernel that tests / commits / iterates identically on every rank.
     row_sharded = None
     if world > 1 and engine in ("gram", "fused") and not args.profile:
-        from demethify_b200.sharded import GpuShardBackend, RowShardedFit
-        m_loc = M // world
-        sprob = prob.row_slice(0, m_loc)
-        be = GpuShardBackend(sprob, None, None, N_UNK, hU[:m_loc], hA)
-        use_peer = os.environ.get("DMF_BENCH_PEER", "0") == "1" and be.enable_peer_exchange(None)   # in-kernel NVLink all-reduce instead of NCCL
-        rs_fit = RowShardedFit(be)
-        rs_fit.init()
-        be.reserve((args.steps + 1) * OUTER_PER_STEP * N_ITER2 + 4 * N_ITER2)
-        use_graph = os.environ.get("DMF_BENCH_GRAPH", "0") == "1"
-        if use_graph:                                       # one outer iteration incl. both all-reduces as a CUDA graph (1 eager run)
-            graph = rs_fit.capture_outer(N_ITER2, 0.0)
-            step_fn = graph.replay
-        else:
-            rs_fit.outer(N_ITER2, 0.0)
-            step_fn = lambda: rs_fit.outer(N_ITER2, 0.0)
-        if os.environ.get("DMF_BENCH_TRACE"):
-            print(f"[rank {rank}] row-sharded leg: set-up done (graph={use_graph})", file=sys.stderr, flush=True)
-        for _ in range(OUTER_PER_STEP - 1):
-            step_fn()
+        from demethify_b200.sharded import GpuShardBackend, RowShardedFit, row_range
+        lo, hi = row_range(M, rank, world)
+        sprob = prob.row_slice(lo, hi)
+
+        def sharded_fit(n_outer):
+            be = GpuShardBackend(sprob, None, None, N_UNK, hU[lo:hi], hA)
+            peer = os.environ.get("DMF_BENCH_PEER", "1") == "1" and be.enable_peer_exchange(None)
+            fit = RowShardedFit(be)
+            fit.init()
+            be.reserve((n_outer + 2) * N_ITER2 + 4 * N_ITER2)
+            return be, fit, peer
+
+        # parity inside the leg: 5 outer iterations sharded vs the same 5 on one GPU (every rank holds the whole problem here)
+        k_par = 5
+        be, fit, use_peer = sharded_fit(k_par)
+        for _ in range(k_par):
+            fit.outer(N_ITER2, 0.0)
+        fit.finish(0.0)
+        (_, a_sh, n_sh, c_sh), = be.results()
+        be.close()
+        ref_b = FitBatch(prob, N_UNK, [hU], [hA])
+        (_, a_1, n_1, c_1), = ref_b.results(ref_b.fit(k_par, N_ITER2, 0.0))
+        ref_b.close()
+        a_all = [torch.empty_like(torch.from_numpy(a_sh).to(dev)) for _ in range(world)]
+        dist.all_gather(a_all, torch.from_numpy(a_sh).to(dev))
+        replicated = all(bool(torch.equal(a_all[0], t)) for t in a_all)
+        parity = {"outer_iterations": k_par, "alpha_bit_identical_on_all_ranks": bool(replicated),
+                  "max_abs_d_alpha_vs_1gpu": float(np.abs(a_sh - a_1).max()), "n_outer_sharded": int(n_sh), "n_outer_1gpu": int(n_1),
+                  "cost_rel_diff_vs_1gpu": float(abs(c_sh - c_1) / c_1)}
+        assert replicated and parity["max_abs_d_alpha_vs_1gpu"] <= 1e-9 and n_sh == n_1 == k_par, parity
+        # timed: warm-up step, then args.steps steps of OUTER_PER_STEP outer iterations
+        n_total = (args.steps + 1) * OUTER_PER_STEP
+        be, fit, use_peer = sharded_fit(n_total)
+        for _ in range(OUTER_PER_STEP):
+            fit.outer(N_ITER2, 0.0)
         barrier()
-        if os.environ.get("DMF_BENCH_TRACE"):
-            print(f"[rank {rank}] row-sharded leg: warm-up done", file=sys.stderr, flush=True)
+        l0 = be.batch.launch_count()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
         for _ in range(args.steps * OUTER_PER_STEP):
-            step_fn()
+            fit.outer(N_ITER2, 0.0)
         r1.record()
         barrier()
+        rs_launches = be.batch.launch_count() - l0
         rs_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
         dist.all_reduce(rs_ms, op=dist.ReduceOp.MAX)
+        fit.finish(0.0)
         st_rs = be.batch.states()[0]
-        assert st_rs.n_outer == (args.steps + 1) * OUTER_PER_STEP and np.isfinite(st_rs.cost)
+        assert st_rs.n_outer == n_total and np.isfinite(st_rs.cost)
         row_sharded = {"value": 2 * N_ITER2 * OUTER_PER_STEP * args.steps / (float(rs_ms[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
-                       "rows_per_gpu": m_loc, "ms_per_outer_iteration": float(rs_ms[0]) / (args.steps * OUTER_PER_STEP),
-                       "collectives_per_outer_iteration": 2, "launch": "one CUDA graph per outer iteration (kernels + NCCL all-reduces)" if use_graph else "eager (host-driven launches)",
-                       "allreduce": "in-kernel over NVLink peer memory (dmf_gram_exchange)" if use_peer else "NCCL",
-                       "allreduce_doubles_per_outer_iteration": int(Kt * (Kt + 1) * N_S + 16),
-                       "note": "one fit, rows sharded over the ranks; value is the single job's update iterations/s"}
-        step_fn = None
-        if use_graph:
-            del graph                                       # release the captured NCCL work before the process group goes away
+                       "ms_per_step": float(rs_ms[0]) / args.steps, "rows_per_gpu": hi - lo,
+                       "ms_per_outer_iteration": float(rs_ms[0]) / (args.steps * OUTER_PER_STEP),
+                       "engine": "fused" if be.fused else "gram", "collectives_per_outer_iteration": 1 if be.fused else 2,
+                       "launches_per_outer_iteration": rs_launches / (args.steps * OUTER_PER_STEP), "gpu_launches": int(rs_launches),
+                       "allreduce": "one kernel over NVLink peer memory (dmf_gram_exchange: push, flag, rank-ordered sum)" if use_peer else "NCCL",
+                       "allreduce_doubles_per_outer_iteration": int(Kt * (Kt + 1) * N_S + 8),
+                       "parity": parity}
         torch.cuda.synchronize()
         be.close()
         del be, sprob
@@ -418,11 +442,20 @@ def run_b200(args, rank, world, local_rank):
     for i in range(2 + min(args.steps, 3)):
         barrier()
         t0 = time.perf_counter()
-        u_out, a_out = dec.mdwbssmf_deconv(nU, None, nA, nX, nD, nR, N_UNK, n_iter1=OUTER_PER_STEP, n_iter2=N_ITER2, tol=0.0)
+        if world > 1:       # the row-sharded public call: every rank passes ITS rows (host buffers), gets its rows of u and alpha back
+            from demethify_b200.sharded import mdwbssmf_deconv_sharded, row_range
+            lo, hi = row_range(M, rank, world)
+            os.environ.setdefault("DMF_PEER_XCHG", "1")
+            u_out, a_out, _n, _c = mdwbssmf_deconv_sharded(nU[lo:hi], nA, nX[lo:hi], nD[lo:hi], nR[lo:hi], N_UNK, n_iter1=OUTER_PER_STEP,
+                                                           n_iter2=N_ITER2, tol=0.0)
+        else:
+            lo, hi = 0, M
+            u_out, a_out = dec.mdwbssmf_deconv(nU, None, nA, nX, nD, nR, N_UNK, n_iter1=OUTER_PER_STEP, n_iter2=N_ITER2, tol=0.0)
         torch.cuda.synchronize()
         e2e_times.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_times[2:]))
-    h2d = hX.numel() * 8 + hD.numel() * 8 + hR.numel() * 8 + hU.numel() * 8 + hA.numel() * 8
+    rows_here = hi - lo
+    h2d = rows_here * (N_S * 8 + N_S * 2 + K_KNOWN * 8 + N_UNK * 8) + hA.numel() * 8
     d2h = u_out.nbytes + a_out.nbytes
 
     # ---- reduce over ranks: device time = max over ranks, work = sum over ranks
@@ -431,8 +464,16 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_s = float(tmax[0]), float(tmax[1])
-    value = world * its_per_step * args.steps / (elapsed_ms * 1e-3)
-    e2e_value = world * its_per_step / e2e_s
+    fit_sharded_value = world * its_per_step * args.steps / (elapsed_ms * 1e-3)
+    if world > 1 and row_sharded is not None:
+        value, step_ms, scaling = row_sharded["value"], row_sharded["ms_per_step"], "strong"      # ONE fit, rows sharded
+        e2e_value = its_per_step / e2e_s
+        h2d_total = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        dist.all_reduce(h2d_total)
+        h2d, d2h = int(h2d_total[0]), int(h2d_total[1])
+    else:
+        value, step_ms, scaling = fit_sharded_value, elapsed_ms / args.steps, "weak"
+        e2e_value = world * its_per_step / e2e_s
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -485,20 +526,24 @@ def run_b200(args, rank, world, local_rank):
             roof["stream_passes"] = stream
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "config": workload_config(M, {"weights_storage": "u16" if prob_wtype_is_u16(sW, sT) else "float", "engine": engine,
-                                          "parallelism": f"fit-sharded x{world}", "ctas_per_fit": geom["ctas_per_fit"],
+                                          "parallelism": "one GPU" if world == 1 else f"ONE fit, CpG rows sharded over {world} GPUs (fit-sharded "
+                                                         "weak-scaling number under fit_sharded)", "ctas_per_fit": geom["ctas_per_fit"],
                                           "tile_rows": geom["tile_rows"], "smem_bytes": geom["smem_bytes"]}),
             "fits_per_sec_at_100_outer": value / (2 * N_ITER2 * 100),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "s_per_call": e2e_s, "call": "demethify_b200.deconvolution.mdwbssmf_deconv(numpy in, numpy out)"},
-            "gpu_launches": int(launches),
+                    "s_per_call": e2e_s, "call": "demethify_b200.deconvolution.mdwbssmf_deconv(numpy in, numpy out)" if world == 1 else
+                    "demethify_b200.sharded.mdwbssmf_deconv_sharded(this rank's rows: numpy in, numpy out), bytes summed over the ranks"},
+            "gpu_launches": int(launches) if world == 1 else int(row_sharded["gpu_launches"]) if row_sharded else int(launches),
             "roofline": roof,
             "clocks": clocks,
         }
         if row_sharded is not None:
             line["row_sharded"] = row_sharded
+            line["fit_sharded"] = {"value": fit_sharded_value, "unit": UNIT, "scaling": "weak", "ms_per_step": elapsed_ms / args.steps,
+                                   "note": f"{world} independent fits, one per GPU, no data-path collective (restarts / sweep members)"}
         if not args.no_cpu and world == 1:
             ms = parity_gpu[0]
             leg = cpu_reference_leg(2, 1, rows=ms, data=(nX[:ms], nD[:ms], nR[:ms], nU[:ms], nA))

@@ -90,11 +90,11 @@ def percentile_bounds_device(stack, lower_percentile, upper_percentile):
     from .engine import _stream_ptr
     lib = _lib.lib()
     B = stack.shape[0]
-    flat = stack.reshape(B, -1).to(torch.float64).contiguous()
+    flat = stack.reshape(B, -1).to(torch.float64).contiguous()          # (host tensors - the gloo tests - take the torch.quantile branch)
     P = flat.shape[1]
     out = torch.empty((2, P), dtype=torch.float64, device=stack.device)
     klo, khi = int(np.floor((B - 1) * (lower_percentile / 100.0))), int(np.floor((B - 1) * (upper_percentile / 100.0)))
-    if max(min(klo + 2, B), min(B - khi, B)) <= lib.dmf_percentile_max_keep():
+    if stack.is_cuda and max(min(klo + 2, B), min(B - khi, B)) <= lib.dmf_percentile_max_keep():
         _lib.check(lib.dmf_percentile_bounds(C.c_void_p(flat.data_ptr()), B, P, float(lower_percentile), float(upper_percentile),
                                              C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), _stream_ptr()))
     else:

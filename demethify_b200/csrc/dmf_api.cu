@@ -131,7 +131,7 @@ struct Plan {
     size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
     // fused engine
     int fused_ok, kb_f, nub_f, s_f, n_tiles_f, n_parts_f, n_groups_f;
-    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_rowX, f_rowD, smem_f;
+    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_zero_off, smem_f;
 };
 
 constexpr int pow2ceil_h(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -335,10 +335,12 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
         p.s_f = s.N <= 64 ? 1 : (s.N <= 128 ? 2 : 4);
         const int ng = ng_of_h(p.nub_f), ncol = p.nub_f * p.kb_f + (ng - p.nub_f), nblk = (ncol + 7) / 8;
         auto a128f = [](size_t v) { return (unsigned)align_up(v, 128); };
-        p.f_rowX = (unsigned)px; p.f_rowD = (unsigned)pd;
-        p.f_pitchX = (unsigned)px + 32u;
-        p.f_pitchD = (unsigned)pd + (sW == 2 ? 16u : 32u);
-        p.f_offD = a128f((size_t)kFusedRows * p.f_pitchX);
+        // a tile is ONE bulk copy per matrix: it keeps the caller's row pitch in shared memory (dmf_shape_t recommends pitches that
+        // are free of bank conflicts); 16 zero bytes behind the X rows of every stage serve the panel columns that do not exist
+        p.f_pitchX = (unsigned)px;
+        p.f_pitchD = (unsigned)pd;
+        p.f_zero_off = (unsigned)((size_t)kFusedRows * px);
+        p.f_offD = a128f((size_t)kFusedRows * p.f_pitchX + 16);
         p.f_offR = a128f(p.f_offD + (size_t)kFusedRows * p.f_pitchD);
         p.f_offU = a128f(p.f_offR + (size_t)kFusedRows * pr);
         p.f_offUp = a128f(p.f_offU + (size_t)kFusedRows * pu);
@@ -683,7 +685,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         fa.n_tiles = p.n_tiles_f;
         fa.pitchX = p.f_pitchX; fa.pitchD = p.f_pitchD; fa.offD = p.f_offD; fa.offR = p.f_offR; fa.offU = p.f_offU; fa.offUp = p.f_offUp;
         fa.stage_bytes = p.f_stage_bytes; fa.offStats = p.f_offStats;
-        fa.rowX_bytes = p.f_rowX; fa.rowD_bytes = p.f_rowD;
+        fa.zero_off = p.f_zero_off;
         fused_kern_t kf = by_types_f(s, p.kb_f, p.nub_f, p.s_f);
         if (!kf || cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_f) != cudaSuccess) {
             cudaGetLastError();

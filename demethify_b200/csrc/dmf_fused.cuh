@@ -45,10 +45,10 @@ struct FusedArgs {
     const double* mom_a;
     const double* mom_m;
     int n_tiles;
-    unsigned pitchX, pitchD;                          // bytes per row inside a stage (padded)
+    unsigned pitchX, pitchD;                          // bytes per row of X / d_x, in global and in shared memory
     unsigned offD, offR, offU, offUp, stage_bytes;    // stage layout, X at 0
     unsigned offStats;                                // from the start of dynamic shared memory
-    unsigned rowX_bytes, rowD_bytes;                  // bytes copied per row
+    unsigned zero_off;                                // offset (inside a stage) of 8 bytes that always hold 0.0
 };
 typedef void (*fused_kern_t)(const FusedArgs);
 
@@ -103,23 +103,25 @@ __device__ __forceinline__ int reduce_over_groups(double (&v)[NV], int lane) {
     return base;
 }
 
-// One update_u step of deconvolution.py:82-89 on the row statistics v = [b | H] (gradient at u for the unsupervised variant, :163;
-// same arithmetic as u_inner_kernel): (prev, cur) -> next.
+// One update_u step of deconvolution.py:82-89 (gradient at u for the unsupervised variant, :163) on the row's statistics,
+// (prev, cur) -> next.  The U-warps run 16 rows x n_iter2 of these back to back while the other 16 warps of the CTA keep the
+// FP64 pipe busy, so the LENGTH of the dependent chain is what counts.  With  Mh = H / l_w  and  c = b / l_w  (per row, once)
+//     u_t = u + beta (u - u_)                        ->  fma(beta, u - u_, u)
+//     u_t + (b - H u_g) / l_w                        ->  fma(-Mh_q0, u_g0, fma(-Mh_q1, u_g1, u_t + c))   (u_g = u_t, or u at :163)
+// i.e. 5 dependent FP64 operations per iteration instead of 9; the roundings differ from the reference's operation order by
+// <= 1 ulp of u per iteration, the same size as the reference's own rounding of u_t + step.
 template <bool AT_CURRENT, int NUB>
-__device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const double (&cu)[NUB], const double (&v)[ng_of(NUB)], double beta,
-                                             double inv_lw, double (&nx)[NUB]) {
+__device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const double (&cu)[NUB], const double (&mh)[NUB][NUB],
+                                             const double (&c)[NUB], double beta, double (&nx)[NUB]) {
     double ut[NUB];
 #pragma unroll
-    for (int q = 0; q < NUB; ++q) ut[q] = cu[q] + beta * (cu[q] - pv[q]);
+    for (int q = 0; q < NUB; ++q) ut[q] = fma(beta, cu[q] - pv[q], cu[q]);
 #pragma unroll
     for (int q = 0; q < NUB; ++q) {
-        double sq = 0.0;
+        double un = ut[q] + c[q];
 #pragma unroll
-        for (int q2 = 0; q2 < NUB; ++q2)
-            sq = fma(v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))], AT_CURRENT ? cu[q2] : ut[q2], sq);
-        const double gq = v[q] - sq;
+        for (int q2 = 0; q2 < NUB; ++q2) un = fma(-mh[q][q2], AT_CURRENT ? cu[q2] : ut[q2], un);
         // np.clip(., 0, 1) by comparisons (a NaN propagates, as in numpy; the simplex projection of the alpha step then stops the fit)
-        double un = ut[q] + gq * inv_lw;
         un = un < 0.0 ? 0.0 : un;
         nx[q] = un > 1.0 ? 1.0 : un;
     }
@@ -128,19 +130,26 @@ __device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const doub
 template <bool AT_CURRENT, int NUB>
 __device__ __forceinline__ void fused_u_iterate(double (&u)[NUB], double (&up)[NUB], const double (&v)[ng_of(NUB)], uint32_t beta32, int n2,
                                                 double inv_lw) {
+    double mh[NUB][NUB], c[NUB];
+#pragma unroll
+    for (int q = 0; q < NUB; ++q) {
+        c[q] = v[q] * inv_lw;
+#pragma unroll
+        for (int q2 = 0; q2 < NUB; ++q2) mh[q][q2] = v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))] * inv_lw;
+    }
     int itn = 0;
     for (; itn + 2 <= n2; itn += 2) {
         double b0, b1, n1[NUB], n3[NUB];
         lds2(beta32 + (uint32_t)itn * 8u, b0, b1);
-        fused_u_step<AT_CURRENT, NUB>(up, u, v, b0, inv_lw, n1);
-        fused_u_step<AT_CURRENT, NUB>(u, n1, v, b1, inv_lw, n3);
+        fused_u_step<AT_CURRENT, NUB>(up, u, mh, c, b0, n1);
+        fused_u_step<AT_CURRENT, NUB>(u, n1, mh, c, b1, n3);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) { up[q] = n1[q]; u[q] = n3[q]; }
     }
     if (itn < n2) {
         double b0, n1[NUB];
         lds1(beta32 + (uint32_t)itn * 8u, b0);
-        fused_u_step<AT_CURRENT, NUB>(up, u, v, b0, inv_lw, n1);
+        fused_u_step<AT_CURRENT, NUB>(up, u, mh, c, b0, n1);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) { up[q] = u[q]; u[q] = n1[q]; }
     }
@@ -168,15 +177,20 @@ __device__ __forceinline__ void fused_row_block(const FusedArgs& a, uint32_t sb3
         if (k < K) lds1(sb32 + a.offR + (uint32_t)rown * rpitch + (uint32_t)k * 8u, t);
         rfrag[kk] = t;
     }
-    const uint32_t xa = sb32 + (uint32_t)ra * a.pitchX, xb = sb32 + (uint32_t)rbw * a.pitchX;
-    const uint32_t da = sb32 + a.offD + (uint32_t)ra * a.pitchD, db = sb32 + a.offD + (uint32_t)rbw * a.pitchD;
+    // without masks the lane's samples are jc[0] + 8 sb: constant byte offsets from the first one
+    const uint32_t xa = sb32 + (uint32_t)ra * a.pitchX + (MASK ? 0u : (uint32_t)jc[0] * 8u);
+    const uint32_t xb = xa + 4u * a.pitchX;
+    const uint32_t da = sb32 + a.offD + (uint32_t)ra * a.pitchD + (MASK ? 0u : (uint32_t)jc[0] * (unsigned)sizeof(WT));
+    const uint32_t db = da + 4u * a.pitchD;
 #pragma unroll
     for (int sb = 0; sb < S; ++sb) {
+        const uint32_t ox = MASK ? (uint32_t)jc[sb] * 8u : (uint32_t)sb * 64u;
+        const uint32_t od = MASK ? (uint32_t)jc[sb] * (unsigned)sizeof(WT) : (uint32_t)sb * 8u * (unsigned)sizeof(WT);
         double c0, c1;
-        lds1(xa + (uint32_t)jc[sb] * 8u, c0);
-        lds1(xb + (uint32_t)jc[sb] * 8u, c1);
-        double d0 = lds_weight<WT>(da + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
-        double d1 = lds_weight<WT>(db + (uint32_t)jc[sb] * (unsigned)sizeof(WT));
+        lds1(xa + ox, c0);
+        lds1(xb + ox, c1);
+        double d0 = lds_weight<WT>(da + od);
+        double d1 = lds_weight<WT>(db + od);
         if (MASK) {
             if (!valid[sb]) { c0 = 0.0; c1 = 0.0; }
             if (!(valid[sb] && la)) d0 = 0.0;
@@ -221,12 +235,13 @@ __device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb
         }
 #pragma unroll
         for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
-        const uint32_t xr = sb32 + (uint32_t)row * a.pitchX, dr = sb32 + a.offD + (uint32_t)row * a.pitchD;
+        const uint32_t xr = sb32 + (uint32_t)row * a.pitchX + (MASK ? 0u : (uint32_t)jc[0] * 8u);
+        const uint32_t dr = sb32 + a.offD + (uint32_t)row * a.pitchD + (MASK ? 0u : (uint32_t)jc[0] * (unsigned)sizeof(WT));
 #pragma unroll
         for (int mb = 0; mb < S; ++mb) {
             double x;
-            lds1(xr + (uint32_t)jc[mb] * 8u, x);
-            double d = lds_weight<WT>(dr + (uint32_t)jc[mb] * (unsigned)sizeof(WT));
+            lds1(xr + (MASK ? (uint32_t)jc[mb] * 8u : (uint32_t)mb * 64u), x);
+            double d = lds_weight<WT>(dr + (MASK ? (uint32_t)jc[mb] * (unsigned)sizeof(WT) : (uint32_t)mb * 8u * (unsigned)sizeof(WT)));
             if (MASK) {
                 if (!(valid[mb] && lrow)) { d = 0.0; x = 0.0; }
             }
@@ -319,17 +334,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
             if (lane == 0) {
                 fence_proxy_async_smem();      // the U-warps wrote the new u into this stage through the generic proxy
-                mbar_arrive_expect_tx(full, (unsigned)nrows * (a.rowX_bytes + a.rowD_bytes + rbytes + 2u * ubytes));
+                mbar_arrive_expect_tx(full, (unsigned)nrows * (a.pitchX + a.pitchD + rbytes + 2u * ubytes));
             }
             __syncwarp();
-            if (lane < nrows) {
-                bulk_g2s(sb + (uint32_t)lane * a.pitchX, f.X + (r0 + lane) * (long long)a.rowX_bytes, a.rowX_bytes, full);
-            } else if (lane >= 16 && lane - 16 < nrows) {
-                bulk_g2s(sb + a.offD + (uint32_t)(lane - 16) * a.pitchD, f.D + (r0 + lane - 16) * (long long)a.rowD_bytes, a.rowD_bytes, full);
-            }
-            if (lane == 0 && K) bulk_g2s(sb + a.offR, f.Rk + r0 * (long long)rbytes, (unsigned)nrows * rbytes, full);
-            if (lane == 1) bulk_g2s(sb + a.offU, Ucur_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
-            if (lane == 2) bulk_g2s(sb + a.offUp, Uprv_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
+            // one bulk copy per matrix: a tile is contiguous in global memory and keeps its row pitch in shared memory (the caller
+            // pads the rows of X and d_x so that the pitch is bank-conflict free, see dmf_shape_t)
+            if (lane == 0) bulk_g2s(sb, f.X + r0 * (long long)a.pitchX, (unsigned)nrows * a.pitchX, full);
+            if (lane == 1) bulk_g2s(sb + a.offD, f.D + r0 * (long long)a.pitchD, (unsigned)nrows * a.pitchD, full);
+            if (lane == 2 && K) bulk_g2s(sb + a.offR, f.Rk + r0 * (long long)rbytes, (unsigned)nrows * rbytes, full);
+            if (lane == 3) bulk_g2s(sb + a.offU, Ucur_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
+            if (lane == 4) bulk_g2s(sb + a.offUp, Uprv_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
             __syncwarp();
         }
     } else if (warp >= kFA + kFC) {
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         // B operand of the panel MMA: column c = 8 nb + gi of  u (x) [R_trunc | u]  =  (first factor u_q) x (second factor R_k or u_q2),
         // formed per k-step from the stage (the U-warp left the new u there)
         unsigned fa_off[NBLK], fa_pitch[NBLK], fb_off[NBLK], fb_pitch[NBLK];
-        const unsigned zero_off = a.rowX_bytes;      // the padding behind row 0 of X in every stage: zeroed at kernel start, never copied over
+        const unsigned zero_off = a.zero_off;        // 8 bytes of every stage that are zeroed at kernel start and never copied over
 #pragma unroll
         for (int nb = 0; nb < NBLK; ++nb) {
             const int c = 8 * nb + gi;

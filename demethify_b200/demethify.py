@@ -65,7 +65,8 @@ def _pinned_matrix(rows, cols, dtype):
     """(rows, cols) C-ordered numpy matrix backed by page-locked host memory when CUDA is there (the H2D copy of the solver then
     runs at full PCIe rate); plain numpy otherwise."""
     import torch
-    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32,
+           np.dtype(np.uint16): torch.uint16}[np.dtype(dtype)]
     try:
         if torch.cuda.is_available():
             return torch.empty((rows, cols), dtype=tdt, pin_memory=True).numpy()
@@ -110,7 +111,11 @@ def read_inputs(args):
         M = first[0].shape[0]
         int_cov = np.issubdtype(first[1].dtype, np.integer)
         meth_f = _pinned_matrix(M, len(paths), np.float64)
-        counts = _pinned_matrix(M, len(paths), np.int64 if int_cov else np.float64)
+        # integer coverage is staged as uint16 (what the kernels store, a quarter of the int64 bytes on the way to the GPU); a column
+        # that does not fit switches the whole matrix back to int64 below
+        narrow = int_cov and first[1].size > 0 and 0 <= int(first[1].min()) and int(first[1].max()) <= 65535
+        counts = _pinned_matrix(M, len(paths), (np.uint16 if narrow else np.int64) if int_cov else np.float64)
+        wide_cols = {}
 
         float_cols = {}                                   # coverage columns that are not integer typed (NaN without --fillna, ...)
 
@@ -121,10 +126,16 @@ def read_inputs(args):
             meth_f[:, j] = f
             if int_cov and not np.issubdtype(c.dtype, np.integer):
                 float_cols[j] = c
+            elif counts.dtype == np.uint16 and c.size and (int(c.min()) < 0 or int(c.max()) > 65535):
+                wide_cols[j] = c
             else:
                 counts[:, j] = c
         place(0, first)
         list(ex.map(lambda j: place(j, load(paths[j])), range(1, len(paths))))
+    if wide_cols:                                         # coverage beyond 16 bits somewhere: int64 like the reference
+        counts = counts.astype(np.int64)
+        for j, c in wide_cols.items():
+            counts[:, j] = c
     if float_cols:                                        # np.column_stack of mixed int / float columns is float64 in the reference
         counts = counts.astype(np.float64)
         for j, c in float_cols.items():

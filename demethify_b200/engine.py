@@ -92,7 +92,12 @@ class DeviceProblem:
         self.dtype = _tdtype(self.precision)
         X = to_device(X, self.dtype, self.device)
         self.M, self.N = X.shape
-        self.ldx = (self.N + 7) // 8 * 8            # rows of X (and of the u16 weights) start 16-byte aligned: per-row bulk copies
+        # Row pitches (include/demethify_b200.h): a row tile reaches shared memory as ONE bulk copy and keeps its pitch there, so
+        # the pitch decides the shared-memory bank pattern of the kernels that walk several rows per warp instruction (the fused
+        # engine's MMA fragments).  pitch = 32 bytes (X) / 16 bytes (u16 weights) beyond a multiple of 128 bytes is conflict free.
+        es = 8 if self.dtype == torch.float64 else 4
+        self.wide = self.N * es >= 512              # short rows: bank conflicts do not matter, padding would (tile geometry, bytes)
+        self.ldx = ((self.N * es + 127) // 128 * 128 + 32) // es if self.wide else (self.N + 7) // 8 * 8
         self.X = _pad_cols(X, self.ldx)
         self.K = 0
         self.Rk = None
@@ -116,18 +121,27 @@ class DeviceProblem:
             raise ValueError("d_x must have the shape of meth_frequency")
         self.wtype = _lib.DMF_W_FLOAT
         self.D = None
+        es = 8 if self.dtype == torch.float64 else 4
+        self.ldd = self.ldx                                        # float weights: the pitch of X
+        if raw.dtype == torch.uint16:                              # already narrow (the CLI reader stages coverage as uint16): no check needed
+            ldd16 = ((self.N * 2 + 127) // 128 * 128 + 16) // 2 if self.wide else (self.N + 7) // 8 * 8
+            self.D, self.wtype, self.ldd = _pad_cols(raw, ldd16), _lib.DMF_W_U16, ldd16
+            return
         if narrow:
             kind = {torch.float64: 0, torch.float32: 1, torch.int64: 2}.get(raw.dtype)
             if kind is None:
                 raw = raw.to(torch.float64)
                 kind = 0
-            raw = _pad_cols(raw, self.ldx)
-            packed = torch.empty((self.M, self.ldx), dtype=torch.uint16, device=self.device)
+            # u16 weights: 16 bytes beyond a multiple of 128 (wide rows), else 16-byte aligned rows
+            ldd16 = ((self.N * 2 + 127) // 128 * 128 + 16) // 2 if self.wide else (self.N + 7) // 8 * 8
+            raw16 = _pad_cols(raw, ldd16)
+            packed = torch.empty((self.M, ldd16), dtype=torch.uint16, device=self.device)
             bad = torch.zeros(1, dtype=torch.int32, device=self.device)
-            _lib.check(_lib.lib().dmf_pack_weights_u16(C.c_void_p(raw.data_ptr()), kind, raw.numel(), C.c_void_p(packed.data_ptr()),
+            _lib.check(_lib.lib().dmf_pack_weights_u16(C.c_void_p(raw16.data_ptr()), kind, raw16.numel(), C.c_void_p(packed.data_ptr()),
                                                        C.c_void_p(bad.data_ptr()), _stream_ptr()))
             if int(bad.item()) == 0:
-                self.D, self.wtype = packed, _lib.DMF_W_U16
+                self.D, self.wtype, self.ldd = packed, _lib.DMF_W_U16, ldd16
+            del raw16
         if self.D is None:
             self.D = _pad_cols(raw.to(self.dtype), self.ldx)
 
@@ -135,9 +149,9 @@ class DeviceProblem:
         """Problem with weights d_x * mask (BCV training folds, ic.py:75): zero weight == entry left out, so X is shared."""
         m = to_device(np.ascontiguousarray(mask), None, self.device)
         if self.D.dtype == torch.uint16:        # 0/1 multiply through the int16 view (bit-exact for every u16 value)
-            m = _pad_cols(m.to(torch.int16), self.ldx)
+            m = _pad_cols(m.to(torch.int16), self.ldd)
             return self.with_weights((self.D.view(torch.int16) * m).view(torch.uint16), self.wtype)
-        m = _pad_cols(m.to(self.D.dtype), self.ldx)
+        m = _pad_cols(m.to(self.D.dtype), self.ldd)
         return self.with_weights(self.D * m, self.wtype)
 
     def gathered(self, idx):
@@ -237,14 +251,14 @@ class FitBatch:
         self.h = _handle(dev.index if dev.index is not None else torch.cuda.current_device())
         self.shape = _lib.Shape(M=self.M, N=self.N, K=self.K, n_u=self.n_u,
                                 dtype=_lib.DMF_F64 if dt == torch.float64 else _lib.DMF_F32, wtype=p0.wtype, mode=mode,
-                                n_fits=self.n_fits, max_ctas_per_fit=max_ctas_per_fit, ldx=p0.ldx, ldd=p0.ldx, ldr=_even(self.K),
+                                n_fits=self.n_fits, max_ctas_per_fit=max_ctas_per_fit, ldx=p0.ldx, ldd=p0.ldd, ldr=_even(self.K),
                                 ldu=self.ldu, u_slot=self.u_slot, u_slots=self.u_slots)
         nbytes = C.c_size_t()
         _lib.check(lib.dmf_batch_workspace_bytes(self.h, C.byref(self.shape), C.byref(nbytes)))
         self.ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
         descs = (_lib.FitDesc * self.n_fits)()
         for i, p in enumerate(probs):
-            if (p.N, p.K, p.wtype, p.dtype) != (p0.N, p0.K, p0.wtype, p0.dtype):
+            if (p.N, p.K, p.wtype, p.dtype, p.ldd) != (p0.N, p0.K, p0.wtype, p0.dtype, p0.ldd):
                 raise ValueError("all problems of a batch must share shape and storage types")
             d = descs[i]
             d.X, d.D = p.X.data_ptr(), p.D.data_ptr()

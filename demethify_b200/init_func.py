@@ -31,7 +31,7 @@ def wls_all_samples(X, d_x, R_full, extra=None, y_is_dx=False, precision=None):
         R2 = _pad_cols(e, _even(K2))
     out = torch.zeros((prob.K + K2, prob.N), dtype=torch.float64, device=dev)
     desc = _lib.WlsDesc(M=prob.M, N=prob.N, K=prob.K, K2=K2, dtype=_lib.DMF_F64 if dt == torch.float64 else _lib.DMF_F32,
-                        wtype=prob.wtype, y_is_dx=int(bool(y_is_dx)), ldx=prob.ldx, ldd=prob.ldx, ldr=_even(prob.K),
+                        wtype=prob.wtype, y_is_dx=int(bool(y_is_dx)), ldx=prob.ldx, ldd=prob.ldd, ldr=_even(prob.K),
                         ldr2=_even(K2), X=prob.X.data_ptr(), D=prob.D.data_ptr(),
                         R1=prob.Rk.data_ptr() if prob.Rk is not None else None, R2=R2.data_ptr() if R2 is not None else None,
                         out=out.data_ptr())

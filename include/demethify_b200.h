@@ -65,7 +65,10 @@ typedef struct dmf_shape {
     int32_t n_fits; /* fits in the batch                */
     int32_t max_ctas_per_fit; /* 0 = let the library choose (multiple of the SM count overall) */
     /* Row pitches in elements.  ALL PITCHES MUST BE EVEN and the padding entries MUST BE ZERO: the kernels
-     * fetch every matrix as aligned two-element vectors and rely on zero padding instead of bounds tests. */
+     * fetch every matrix as aligned two-element vectors and rely on zero padding instead of bounds tests.
+     * A row tile reaches shared memory as one bulk copy and keeps its pitch there; the FUSED engine walks four rows per warp
+     * instruction, which is free of bank conflicts when the pitch of X is 32 bytes and the pitch of u16 weights 16 bytes
+     * beyond a multiple of 128 bytes (e.g. N = 256 fp64: ldx = 260, ldd = 264 for u16).  Any even pitch is correct. */
     int64_t ldx;    /* row pitch of X  (>= N, even)      */
     int64_t ldd;    /* row pitch of D  (>= N, even)      */
     int64_t ldr;    /* row pitch of Rk (>= K, even)      */

@@ -72,3 +72,22 @@ def test_reader_rejects_ragged_files(tmp_path):
     args = argparse.Namespace(bedmethyl=False, fillna=False, ref=None, methfreq=[str(a), str(b)])
     with pytest.raises(ValueError):
         read_inputs(args)
+
+
+def test_reader_stages_integer_coverage_as_uint16_and_widens_when_needed(tmp_path):
+    """Integer coverage lands in a uint16 matrix (what the kernels store); a file whose coverage does not fit 16 bits turns the
+    whole matrix into int64 - values identical to the reference's column_stack either way."""
+    rs = np.random.RandomState(1)
+    M = 50
+    paths = []
+    for j, big in enumerate([False, False, True]):
+        cov = rs.poisson(30, size=M) + 1
+        if big:
+            cov[7] = 70000
+        p = tmp_path / f"w{j}.csv"
+        pd.DataFrame({"percent_modified": rs.uniform(size=M), "valid_coverage": cov}).to_csv(p, index=False)
+        paths.append(str(p))
+    X, C, _, _ = read_inputs(argparse.Namespace(bedmethyl=False, fillna=False, ref=None, methfreq=paths[:2]))
+    assert C.dtype == np.uint16
+    X3, C3, _, _ = read_inputs(argparse.Namespace(bedmethyl=False, fillna=False, ref=None, methfreq=paths))
+    assert C3.dtype == np.int64 and C3[7, 2] == 70000 and np.array_equal(C3[:, :2], C.astype(np.int64))

@@ -34,7 +34,14 @@ def main():
     u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, n_u, seed=3)
     lo, hi = row_range(M, rank, world)
     ok = True
-    for it1, it2, tol in ((6, 20, 1e-9), (400, 20, 1.0)):
+    # (iterations, tolerance, peer exchange, CUDA graph): NCCL and the in-kernel NVLink exchange, eager and as a replayed graph
+    # (the exchange count lives on the device, so replays advance it)
+    cases = [(6, 20, 1e-9, "0", "0"), (400, 20, 1.0, "0", "0"), (6, 20, 1e-9, "1", "0"), (400, 20, 1.0, "1", "0"), (400, 20, 1.0, "1", "1"),
+             (400, 20, 1.0, "0", "1")]
+    for it1, it2, tol, peer, graph in cases:
+        os.environ["DMF_PEER_XCHG"], os.environ["DMF_SHARDED_GRAPH"] = peer, graph
+        if graph == "1":
+            os.environ.setdefault("NCCL_GRAPH_REGISTER", "0")
         u, al, n_outer, cost = mdwbssmf_deconv_sharded(u0[lo:hi], a0, X[lo:hi], D[lo:hi], Rk[lo:hi], n_u, n_iter1=it1, n_iter2=it2, tol=tol)
         parts = [None] * world
         dist.all_gather_object(parts, (lo, u, al, n_outer))
@@ -46,7 +53,7 @@ def main():
             da, du = np.abs(al - ao).max(), np.abs(ufull - uo).max()
             good = same_alpha and all(p[3] == tr["n_outer"] for p in parts) and da <= 1e-6 and du <= 1e-6
             ok &= good
-            print(f"sharded_check world={world} peer_xchg={os.environ.get('DMF_PEER_XCHG', '0')} it1={it1}: n_outer={n_outer} oracle={tr['n_outer']} max|d alpha|={da:.2e} max|d u|={du:.2e} "
+            print(f"sharded_check world={world} peer_xchg={peer} graph={graph} it1={it1}: n_outer={n_outer} oracle={tr['n_outer']} max|d alpha|={da:.2e} max|d u|={du:.2e} "
                   f"alpha replicated={same_alpha} peer={sharded.last_info} -> {'OK' if good else 'FAIL'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
