@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--profile", action="store_true", help="resident arm only (for runs under ncu): no e2e, no CPU leg")
     ap.add_argument("--outer", type=int, default=OUTER_PER_STEP, help="outer iterations per step (default: one 100-iteration fit)")
     ap.add_argument("--engine", default="auto", choices=["auto", "fused", "gram", "stream"], help="device engine of the timed region")
+    ap.add_argument("--boot-resamples", type=int, default=1000, help="resamples of the BASELINE config-4 bootstrap leg (0 = skip the leg)")
+    ap.add_argument("--boot-rows", type=int, default=500_000, help="CpG rows of the bootstrap leg (debug)")
     return ap.parse_args()
 
 
@@ -176,6 +178,74 @@ def run_reference(args, rank, world):
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def bootstrap_leg(args, dev, rank, world):
+    """BASELINE config 4: bootstrap confidence intervals, 500k CpG x 64 samples, K = 6, n_u = 1, CLI defaults (10000 x 20, tol 1e-2,
+    init uniform_, seed 1 -> the reference's seed sequence 1, 2, 4, 7, ...), boot_resamples resamples, percentiles included
+    (bootstrap.py:26-54, :77-78).  Fit-sharded over the ranks (resample b on rank b mod world, no data-path collective; the alpha
+    and u stacks are all-gathered for the percentiles).  Wall clock of the public pieces bt_ci is made of, host work included."""
+    import torch
+    import torch.distributed as dist
+    from demethify_b200.bootstrap import bootstrap_fits, bootstrap_seeds, merge_resample_stacks, percentile_bounds_device, shard_of
+    from demethify_b200.engine import DeviceProblem
+    Mb, Nb, Kb, nub, B = args.boot_rows, 64, K_KNOWN, 1, args.boot_resamples
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321)
+    conc = torch.rand(Kb + 1, device=dev, generator=gen, dtype=torch.float64) * 0.8 + 0.2
+    g1 = torch._standard_gamma(conc.expand(Mb, Kb + 1).contiguous(), generator=gen)
+    g2 = torch._standard_gamma(conc.expand(Mb, Kb + 1).contiguous(), generator=gen)
+    Rf = g1 / (g1 + g2)
+    unk = torch.rand(Nb, device=dev, generator=gen, dtype=torch.float64) * 0.9
+    ek = -torch.log1p(-torch.rand(Kb, Nb, device=dev, generator=gen, dtype=torch.float64))
+    A_true = torch.cat([ek / ek.sum(0) * (1 - unk), unk[None]], 0)
+    D = torch.poisson(torch.full((Mb, Nb), 50.0, device=dev), generator=gen).to(torch.int64) + 1
+    X = torch.binomial(D.to(torch.float64), (Rf @ A_true).clamp_(0, 1), generator=gen) / D.to(torch.float64)
+    Rk = Rf[:, :Kb].contiguous()
+    prob = DeviceProblem(X, D, Rk)
+    Xh, Rh = X.cpu().numpy(), Rk.cpu().numpy()               # bootstrap_fits takes the reference's host arrays (shapes / data-dependent inits)
+    del g1, g2, Rf, X, D
+    seeds = shard_of(bootstrap_seeds(1, B), rank, world)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    alphas, us, n_outer = bootstrap_fits(len(seeds), nub, Xh, None, Rh, "uniform_", 10000, 20, 1e-2, None, 1, prob=prob, on_device=True,
+                                         seeds=seeds)
+    torch.cuda.synchronize()
+    t_fit = time.perf_counter() - t0
+    if world > 1:
+        alphas = merge_resample_stacks(alphas, B)
+        us = merge_resample_stacks(us, B)
+    lo, hi = percentile_bounds_device(alphas, 2.5, 97.5)
+    ulo, uhi = percentile_bounds_device(us, 2.5, 97.5)
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    tt = torch.tensor([t_fit, t_all, float(sum(n_outer))], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        t_fit, t_all, total_outer = float(tmax[0]), float(tmax[1]), float(tt[2])
+    else:
+        total_outer = float(tt[2])
+    ok = bool(np.isfinite(lo).all() and np.isfinite(uhi).all() and (hi >= lo).all() and (uhi >= ulo).all())
+    # algorithmic FP64 work of one outer iteration of one resample (n_u = 1): the fused-pass count of SURVEY 8 d4 with n_u = 1
+    flops_outer = 2.0 * Mb * Nb * (Kb + 2 + 1 + 1 + 1 + 1 + Kb + 1)
+    fp64_peak = 37.1
+    fpath = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(fpath):
+        fp64_peak = json.load(open(fpath))["fp64_tflops"]
+    tf = flops_outer * total_outer / t_fit / 1e12 / world
+    return {"workload": "BASELINE configs[3]: bootstrap CIs, 500k CpG x 64 samples, K=6, n_u=1, 10000 x 20 iterations, tol 1e-2, uniform_ init",
+            "M_cpg": Mb, "N_samples": Nb, "resamples": B, "n_gpus": world, "parallelism": f"fit-sharded x{world} (resample b on rank b mod {world})",
+            "seconds_total": t_all, "seconds_fits": t_fit, "seconds_percentiles_and_gather": t_all - t_fit,
+            "resample_fits_per_sec": B / t_all, "seconds_per_1000_resamples": t_all * 1000.0 / max(B, 1),
+            "mean_outer_iterations": total_outer / max(B, 1), "bounds_finite_and_ordered": ok,
+            "form": "multiplicity form (shared X, d_x, R_trunc served from L2; per-position u through a CSR), Gram-form engine",
+            "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                         "algorithmic_fp64_flops_per_fit_outer_iteration": flops_outer,
+                         "note": "per GPU; the shared matrices come from L2 (profiles/r1g_bootstrap_summary.md), so HBM is not the bound here"}}
 
 
 def run_b200(args, rank, world, local_rank):
@@ -475,6 +545,9 @@ def run_b200(args, rank, world, local_rank):
         value, step_ms, scaling = fit_sharded_value, elapsed_ms / args.steps, "weak"
         e2e_value = world * its_per_step / e2e_s
 
+    boot = None
+    if args.boot_resamples > 0 and not args.profile and engine in ("gram", "fused") and args.precision == "fp64":
+        boot = bootstrap_leg(args, dev, rank, world)
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -540,6 +613,8 @@ def run_b200(args, rank, world, local_rank):
             "roofline": roof,
             "clocks": clocks,
         }
+        if boot is not None:
+            line["bootstrap_config4"] = boot
         if row_sharded is not None:
             line["row_sharded"] = row_sharded
             line["fit_sharded"] = {"value": fit_sharded_value, "unit": UNIT, "scaling": "weak", "ms_per_step": elapsed_ms / args.steps,

@@ -1090,7 +1090,9 @@ __device__ __forceinline__ bool project_simplex_reg(double (&v)[KTB], int p) {
                 const int l = i ^ j;
                 if (l > i) {
                     const bool desc = (i & kk) == 0;
-                    const double hi = fmax(u[i], u[l]), lo = fmin(u[i], u[l]);
+                    // NaNs were excluded above: one comparison and selects instead of the NaN-aware fmax / fmin pair
+                    const bool gt = u[i] > u[l];
+                    const double hi = gt ? u[i] : u[l], lo = gt ? u[l] : u[i];
                     u[i] = desc ? hi : lo;
                     u[l] = desc ? lo : hi;
                 }
@@ -1108,7 +1110,7 @@ __device__ __forceinline__ bool project_simplex_reg(double (&v)[KTB], int p) {
     }
     if (!found) return false;
 #pragma unroll
-    for (int k = 0; k < KTB; ++k) v[k] = fmax(v[k] - theta, 0.0);
+    for (int k = 0; k < KTB; ++k) { const double w = v[k] - theta; v[k] = w > 0.0 ? w : 0.0; }      // np.maximum(v - theta, 0), no NaN here
     return true;
 }
 
