@@ -179,6 +179,19 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
     mode = _lib.DMF_MODE_PURITY if purity is not None else _lib.DMF_MODE_PARTIAL
     use_mult = prob.K <= 6 and n_u <= 4 and prob.K + (prob.K & 1) + n_u + (n_u & 1) <= 8
     dev = prob.device
+    # MATERIALISED form: where the fused one-pass engine applies (FP64, n_u <= 2, K <= 8, N <= 256, n_iter2 <= 64) every resample of
+    # a wave gets its own gathered copy of X, d_x, R_trunc (one row-gather kernel per matrix) and runs the same single streaming pass
+    # per outer iteration as a plain fit: half the FP64 work per outer iteration of the two-pass multiplicity form, positions stay in
+    # the reference's order (no sort / CSR), at the price of HBM traffic instead of L2 hits and of gigabytes of scratch per wave.
+    from . import get_engine
+    use_fused = (get_engine() in ("auto", "fused") and prob.precision == "fp64" and n_u <= 2 and prob.K <= 8 and N <= 256 and 1 <= n_iter2 <= 64
+                 and M >= 4096)
+    if use_fused:
+        row_bytes = prob.X.shape[1] * prob.X.element_size() + prob.D.shape[1] * prob.D.element_size() + \
+            (prob.Rk.shape[1] * prob.Rk.element_size() if prob.Rk is not None else 0)
+        per_fit = M * (row_bytes + 4 * (n_u + (n_u & 1)) * 8 + 8 + 8 * n_u * 3) + 64 * (prob.K + n_u) * N * 8 + (1 << 20)
+        wave = int(max(1, min(n_bootstrap * restarts, (device_free_bytes(prob.device) * 2 // 3) // max(per_fit, 1), 1024)))
+        wave = max(restarts, wave // restarts * restarts)
     for w0 in range(0, len(jobs), wave):
         chunk = jobs[w0:w0 + wave]
 
@@ -213,6 +226,32 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         # permuted along; multiplicities and CSR offsets per source row
         idx_d = torch.from_numpy(idx_np).to(dev)                                                    # (Bw, M) int64
         u0_d = torch.from_numpy(u0_np).to(dev)                                                      # (Bw, M, n_u)
+        if use_fused:
+            probs = [prob.gathered(idx_d[k]) for k in range(Bw)]                                    # this wave's resampled matrices
+            del idx_d
+            batch = FitBatch(probs, n_u, u0_d, A0, mode=mode, purity=purity)
+            del u0_d
+            states = batch.fit(n_iter1, n_iter2, tol)
+            U_d, A_d = batch.stacked_current(states)
+            if restarts > 1:
+                cost = torch.tensor([st.cost for st in states], dtype=torch.float64, device=dev).view(-1, restarts)
+                best = torch.argmin(cost, dim=1) + torch.arange(cost.shape[0], device=dev) * restarts
+                U_d, A_d = U_d[best], A_d[best]
+                n_outer.extend(states[int(i)].n_outer for i in best.cpu())
+            else:
+                n_outer.extend(st.n_outer for st in states)
+            b0, nb = w0 // restarts, Bw // restarts
+            if on_device:
+                alphas[b0:b0 + nb] = A_d.to(torch.float64)
+                if keep_u:
+                    us[b0:b0 + nb] = U_d.to(torch.float64)
+            else:
+                alphas[b0:b0 + nb] = A_d.to(torch.float64).cpu().numpy()
+                if keep_u:
+                    us[b0:b0 + nb] = U_d.to(torch.float64).cpu().numpy()
+            batch.close()
+            del batch, probs, U_d, A_d
+            continue
         order_d, rows_d, cnt, offs_d = resample_layout(idx_d, M, with_csr=use_mult)
         U0 = torch.gather(u0_d, 1, order_d.unsqueeze(-1).expand(-1, -1, n_u))
         del u0_d

@@ -156,7 +156,7 @@ class DeviceProblem:
 
     def gathered(self, idx):
         """New problem holding rows idx of X, d_x, R_trunc (row gather kernel of the library; bootstrap.py:28)."""
-        rows = to_device(np.asarray(idx, dtype=np.int32), torch.int32, self.device)
+        rows = idx.to(self.device, torch.int32) if isinstance(idx, torch.Tensor) else to_device(np.asarray(idx, dtype=np.int32), torch.int32, self.device)
         other = object.__new__(DeviceProblem)
         other.__dict__.update(self.__dict__)
         n = rows.numel()
