@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdemethify_sm100.so")
+LIB_PATH = os.environ.get("DMF_LIB") or os.path.join(HERE, "libdemethify_sm100.so")      # DMF_LIB: an alternative build of the same sources (kernel experiments)
 
 DMF_F64, DMF_F32 = 0, 1
 DMF_W_FLOAT, DMF_W_U16 = 0, 1

@@ -131,7 +131,7 @@ struct Plan {
     size_t stats_gbx, stats_scal;      // offsets (in doubles) of gbx and scal inside a per-fit stats block [gram | gbx | scal(8)]
     // fused engine
     int fused_ok, kb_f, nub_f, s_f, n_tiles_f, n_parts_f, n_groups_f;
-    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_zero_off, smem_f;
+    unsigned f_pitchX, f_pitchD, f_offD, f_offR, f_offU, f_offUp, f_stage_bytes, f_offStats, f_offTab, f_zero_off, smem_f;
 };
 
 constexpr int pow2ceil_h(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -346,7 +346,9 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
         p.f_offUp = a128f(p.f_offU + (size_t)kFusedRows * pu);
         p.f_stage_bytes = a128f(p.f_offUp + (size_t)kFusedRows * pu);
         p.f_offStats = kFusedCtlBytes + kFusedStages * p.f_stage_bytes;
-        p.smem_f = p.f_offStats + 2u * kFA * kFusedRows * ng * 8u;
+        // double-buffered row statistics (4 sample-group partials per row), then the per-sample table of the A-warps
+        p.f_offTab = a128f(p.f_offStats + 2u * kFusedSGroups * kFusedRows * ng * 8u);
+        p.smem_f = p.f_offTab + 32u * p.s_f * 2u * ng * 8u;
         (void)nblk;
         const size_t n_rec = 2 + (size_t)(ncol + p.nub_f) * s.N;
         if (p.smem_f <= smem_cap && kFusedCtlBytes + n_rec * 8 <= p.f_offStats) {
@@ -684,7 +686,7 @@ int dmf_batch_create(dmf_handle_t h, const dmf_shape_t* shape, const dmf_fit_des
         fa.g.n_parts = p.n_parts_f; fa.g.n_groups = p.n_groups_f; fa.g.fit_major = 0; fa.g.multmode = 0;
         fa.n_tiles = p.n_tiles_f;
         fa.pitchX = p.f_pitchX; fa.pitchD = p.f_pitchD; fa.offD = p.f_offD; fa.offR = p.f_offR; fa.offU = p.f_offU; fa.offUp = p.f_offUp;
-        fa.stage_bytes = p.f_stage_bytes; fa.offStats = p.f_offStats;
+        fa.stage_bytes = p.f_stage_bytes; fa.offStats = p.f_offStats; fa.offTab = p.f_offTab;
         fa.zero_off = p.f_zero_off;
         fused_kern_t kf = by_types_f(s, p.kb_f, p.nub_f, p.s_f);
         if (!kf || cudaFuncSetAttribute((const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_f) != cudaSuccess) {

@@ -31,11 +31,20 @@
 namespace dmf {
 
 constexpr int kFA = 8, kFC = 8, kFU = 3, kFP = 1;
+// Registers per thread after the role split (setmaxnreg; the kernel is launched with 96): 256 (RA + RC) + 128 x 64 <= 640 x 96
+#ifndef DMF_RA
+#define DMF_RA 96
+#endif
+#ifndef DMF_RC
+#define DMF_RC 112
+#endif
+static_assert(DMF_RA % 8 == 0 && DMF_RC % 8 == 0 && DMF_RA + DMF_RC <= 208, "register split of the fused pass");
 constexpr int kFusedThreads = (kFA + kFC + kFU + kFP) * 32;
 constexpr int kFusedRows = 16;           // rows per tile (two 8-row MMA blocks, four 4-row k-steps)
 constexpr int kFusedStages = 5;
 constexpr int kFusedMaxInner = 64;       // beyond this the U-warps (16 rows at a time) would bound the pass: Gram engine instead
 constexpr unsigned kFusedCtlBytes = 2048;
+constexpr int kFusedSGroups = 4;         // A-warps: 2 row blocks x 4 sample groups; a row has 4 partial statistics records
 
 struct FusedArgs {
     Geom g;                  // problem sizes, pitches, n_parts / n_groups / part_stride of this launch
@@ -47,7 +56,7 @@ struct FusedArgs {
     int n_tiles;
     unsigned pitchX, pitchD;                          // bytes per row of X / d_x, in global and in shared memory
     unsigned offD, offR, offU, offUp, stage_bytes;    // stage layout, X at 0
-    unsigned offStats;                                // from the start of dynamic shared memory
+    unsigned offStats, offTab;                        // from the start of dynamic shared memory
     unsigned zero_off;                                // offset (inside a stage) of 8 bytes that always hold 0.0
 };
 typedef void (*fused_kern_t)(const FusedArgs);
@@ -60,170 +69,156 @@ struct FusedCtl {
 };
 static_assert(sizeof(FusedCtl) <= kFusedCtlBytes, "fused control block too large");
 
+// D (8 x 8) += A (8 x 4, lane holds A[lane / 4][lane % 4]) x B (4 x 8, lane holds B[lane % 4][lane / 4]); the lane's two
+// accumulators are D[lane / 4][2 (lane % 4)] and D[lane / 4][2 (lane % 4) + 1]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// two adjacent weights (same row, samples j and j + 1; j even) as doubles
 template <typename WT>
-__device__ __forceinline__ double lds_weight(uint32_t addr);
+__device__ __forceinline__ void lds_weight2(uint32_t addr, double& d0, double& d1);
 template <>
-__device__ __forceinline__ double lds_weight<uint16_t>(uint32_t addr) {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-    return (double)(unsigned)v;
+__device__ __forceinline__ void lds_weight2<uint16_t>(uint32_t addr, double& d0, double& d1) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    d0 = (double)(v & 0xffffu);
+    d1 = (double)(v >> 16);
 }
 template <>
-__device__ __forceinline__ double lds_weight<double>(uint32_t addr) {
-    double v;
-    lds1(addr, v);
-    return v;
-}
+__device__ __forceinline__ void lds_weight2<double>(uint32_t addr, double& d0, double& d1) { lds2(addr, d0, d1); }
 
-// Row sums over the 8 lanes that share (lane & 3): halving butterfly over lane bits 2, 3, 4.  NV is a multiple of 8; on return
-// the lane holds the totals of slots base .. base + NV / 8 - 1 in v[0 .. NV / 8).  (The row <-> MMA column mapping is a property
-// of the whole warp, so the slots cannot be made lane dependent to save the selects.)
-template <int NV>
-__device__ __forceinline__ int reduce_over_groups(double (&v)[NV], int lane) {
-    static_assert(NV % 8 == 0, "NV must be a multiple of 8");
-    int base = 0;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-        const int o = 4 << s;
-        const int half = NV >> (s + 1);
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const double send = up ? v[i] : v[i + half];
-            const double keep = up ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-        base += up ? half : 0;
-    }
-    return base;
+// np.clip(., 0, 1) by two comparisons of the SAME value (they issue together; a NaN fails both and propagates, as in numpy;
+// the simplex projection of the alpha step then stops the fit)
+__device__ __forceinline__ double clip01_keepnan(double v) {
+    double r = v > 1.0 ? 1.0 : v;
+    return v < 0.0 ? 0.0 : r;
 }
 
 // One update_u step of deconvolution.py:82-89 (gradient at u for the unsupervised variant, :163) on the row's statistics,
 // (prev, cur) -> next.  The U-warps run 16 rows x n_iter2 of these back to back while the other 16 warps of the CTA keep the
-// FP64 pipe busy, so the LENGTH of the dependent chain is what counts.  With  Mh = H / l_w  and  c = b / l_w  (per row, once)
-//     u_t = u + beta (u - u_)                        ->  fma(beta, u - u_, u)
-//     u_t + (b - H u_g) / l_w                        ->  fma(-Mh_q0, u_g0, fma(-Mh_q1, u_g1, u_t + c))   (u_g = u_t, or u at :163)
-// i.e. 5 dependent FP64 operations per iteration instead of 9; the roundings differ from the reference's operation order by
-// <= 1 ulp of u per iteration, the same size as the reference's own rounding of u_t + step.
+// FP64 pipe busy - every dependent FP64 operation queues behind their DMMAs - so the DEPTH of the chain from cur to next is
+// what counts.  With  Mh = H / l_w,  c = b / l_w  and  Am = I - Mh  (per row, once):
+//     u_t = u + beta (u - u_)                        ->  fma(1 + beta, u, -beta u_)        (-beta u_ does not depend on u)
+//     u_t + (b - H u_t) / l_w  =  Am u_t + c         ->  fma(Am_qq, u_t[q], fma(Am_qq', u_t[q'], c_q))
+// i.e. 3 dependent FP64 operations + the comparison per iteration instead of 9; the roundings differ from the reference's
+// operation order by ~1 ulp of u per iteration, the same size as the reference's own rounding of u_t + step.
 template <bool AT_CURRENT, int NUB>
-__device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const double (&cu)[NUB], const double (&mh)[NUB][NUB],
+__device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const double (&cu)[NUB], const double (&am)[NUB][NUB],
                                              const double (&c)[NUB], double beta, double (&nx)[NUB]) {
+    const double opb = 1.0 + beta;
     double ut[NUB];
 #pragma unroll
-    for (int q = 0; q < NUB; ++q) ut[q] = fma(beta, cu[q] - pv[q], cu[q]);
+    for (int q = 0; q < NUB; ++q) ut[q] = fma(opb, cu[q], -beta * pv[q]);
 #pragma unroll
     for (int q = 0; q < NUB; ++q) {
-        double un = ut[q] + c[q];
+        double un;
+        if (AT_CURRENT) {        // gradient at u (deconvolution.py:163): am = -Mh
+            double gq = c[q];
 #pragma unroll
-        for (int q2 = 0; q2 < NUB; ++q2) un = fma(-mh[q][q2], AT_CURRENT ? cu[q2] : ut[q2], un);
-        // np.clip(., 0, 1) by comparisons (a NaN propagates, as in numpy; the simplex projection of the alpha step then stops the fit)
-        un = un < 0.0 ? 0.0 : un;
-        nx[q] = un > 1.0 ? 1.0 : un;
+            for (int q2 = 0; q2 < NUB; ++q2) gq = fma(am[q][q2], cu[q2], gq);
+            un = ut[q] + gq;
+        } else {                 // am = I - Mh
+            un = c[q];
+#pragma unroll
+            for (int q2 = 0; q2 < NUB; ++q2)
+                if (q2 != q) un = fma(am[q][q2], ut[q2], un);
+            un = fma(am[q][q], ut[q], un);
+        }
+        nx[q] = clip01_keepnan(un);
     }
 }
 // n2 steps, two at a time so that (u_, u) rotate without register copies; beta_t comes from shared memory
 template <bool AT_CURRENT, int NUB>
 __device__ __forceinline__ void fused_u_iterate(double (&u)[NUB], double (&up)[NUB], const double (&v)[ng_of(NUB)], uint32_t beta32, int n2,
                                                 double inv_lw) {
-    double mh[NUB][NUB], c[NUB];
+    double am[NUB][NUB], c[NUB];
 #pragma unroll
     for (int q = 0; q < NUB; ++q) {
         c[q] = v[q] * inv_lw;
 #pragma unroll
-        for (int q2 = 0; q2 < NUB; ++q2) mh[q][q2] = v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))] * inv_lw;
+        for (int q2 = 0; q2 < NUB; ++q2) {
+            const double mh = v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))] * inv_lw;
+            am[q][q2] = (!AT_CURRENT && q == q2) ? 1.0 - mh : -mh;
+        }
     }
     int itn = 0;
     for (; itn + 2 <= n2; itn += 2) {
         double b0, b1, n1[NUB], n3[NUB];
         lds2(beta32 + (uint32_t)itn * 8u, b0, b1);
-        fused_u_step<AT_CURRENT, NUB>(up, u, mh, c, b0, n1);
-        fused_u_step<AT_CURRENT, NUB>(u, n1, mh, c, b1, n3);
+        fused_u_step<AT_CURRENT, NUB>(up, u, am, c, b0, n1);
+        fused_u_step<AT_CURRENT, NUB>(u, n1, am, c, b1, n3);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) { up[q] = n1[q]; u[q] = n3[q]; }
     }
     if (itn < n2) {
         double b0, n1[NUB];
         lds1(beta32 + (uint32_t)itn * 8u, b0);
-        fused_u_step<AT_CURRENT, NUB>(up, u, mh, c, b0, n1);
+        fused_u_step<AT_CURRENT, NUB>(up, u, am, c, b0, n1);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) { up[q] = u[q]; u[q] = n1[q]; }
     }
 }
 
-// A-warps: row statistics of one 8-row block (rb) of a tile for the lane's S samples.  MASK = the tile is short or some of the
-// warp's samples do not exist (d = 0 there).  acc[2 rb NG ...] = [b (NUB) | H upper triangle] of row 8 rb + ti, then of row 8 rb + ti + 4.
-template <bool MASK, typename WT, int KS, int NUB, int S>
-__device__ __forceinline__ void fused_row_block(const FusedArgs& a, uint32_t sb32, int nrows, int rb, int gi, int ti, int K,
-                                                const double (&na)[S][KS > 0 ? KS : 1], const double (&au)[S][NUB],
-                                                const double (&P)[S][ng_of(NUB) - NUB], const int (&jc)[S], const bool (&valid)[S],
-                                                double& cost, double (&acc)[((4 * ng_of(NUB) + 7) / 8) * 8]) {
+// A-warps: row statistics of ONE row (the lane's, rows on the M side of the MMA) over the warp's NSB blocks of 8 samples; the lane
+// owns samples 2 ti, 2 ti + 1 of every block.  xa / da: the lane's row at the warp's first block, sample 2 ti; ta: the lane's pair
+// record of the per-sample table [a_u(j) | a_u(j + 1) | P(j) | P(j + 1)] (P = upper triangle of a_u a_u^T).  MASK: the tile is short
+// or some of the warp's samples do not exist (nblk = existing blocks, jlane = first block's sample 2 ti).
+// acc = [b (NUB) | H upper triangle] of the row.
+template <bool MASK, typename WT, int KS, int NUB, int NSB>
+__device__ __forceinline__ void fused_row_stats(uint32_t xa, uint32_t da, uint32_t ta, const double (&rfrag)[KS > 0 ? KS : 1],
+                                                const double (&nab)[NSB][KS > 0 ? KS : 1], int nblk, int jlane, int N, bool live,
+                                                double& cost, double (&acc)[ng_of(NUB)]) {
     constexpr int NG = ng_of(NUB), NTRI = NG - NUB;
-    const int o0 = 2 * rb * NG;          // rb is a compile-time constant at both call sites
-    const unsigned rpitch = (unsigned)(a.g.ldr * 8);
-    const int ra = 8 * rb + ti, rbw = ra + 4;          // the two rows of this lane's C fragment
-    const bool la = ra < nrows, lb = rbw < nrows;
-    // B operand: R_trunc[row_of_n(gi)][4 kk + ti], MMA column n = 2 t + e  <->  tile row 8 rb + t + 4 e
-    double rfrag[KS > 0 ? KS : 1];
-    const int rown = 8 * rb + (gi >> 1) + 4 * (gi & 1);
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-        const int k = 4 * kk + ti;
-        double t = 0.0;
-        if (k < K) lds1(sb32 + a.offR + (uint32_t)rown * rpitch + (uint32_t)k * 8u, t);
-        rfrag[kk] = t;
-    }
-    // without masks the lane's samples are jc[0] + 8 sb: constant byte offsets from the first one
-    const uint32_t xa = sb32 + (uint32_t)ra * a.pitchX + (MASK ? 0u : (uint32_t)jc[0] * 8u);
-    const uint32_t xb = xa + 4u * a.pitchX;
-    const uint32_t da = sb32 + a.offD + (uint32_t)ra * a.pitchD + (MASK ? 0u : (uint32_t)jc[0] * (unsigned)sizeof(WT));
-    const uint32_t db = da + 4u * a.pitchD;
+    for (int sb = 0; sb < NSB; ++sb) {
+        if (MASK && sb >= nblk) break;
+        double c0, c1, d0, d1, tb[2 * NG];
+        lds2(xa + (uint32_t)sb * 64u, c0, c1);
+        lds_weight2<WT>(da + (uint32_t)sb * 8u * (unsigned)sizeof(WT), d0, d1);
 #pragma unroll
-    for (int sb = 0; sb < S; ++sb) {
-        const uint32_t ox = MASK ? (uint32_t)jc[sb] * 8u : (uint32_t)sb * 64u;
-        const uint32_t od = MASK ? (uint32_t)jc[sb] * (unsigned)sizeof(WT) : (uint32_t)sb * 8u * (unsigned)sizeof(WT);
-        double c0, c1;
-        lds1(xa + ox, c0);
-        lds1(xb + ox, c1);
-        double d0 = lds_weight<WT>(da + od);
-        double d1 = lds_weight<WT>(db + od);
+        for (int i = 0; i < NG; ++i) lds2(ta + (uint32_t)sb * (4u * 2u * NG * 8u) + (uint32_t)i * 16u, tb[2 * i], tb[2 * i + 1]);
         if (MASK) {
-            if (!valid[sb]) { c0 = 0.0; c1 = 0.0; }
-            if (!(valid[sb] && la)) d0 = 0.0;
-            if (!(valid[sb] && lb)) d1 = 0.0;
+            const bool v0 = jlane + 8 * sb < N, v1 = jlane + 8 * sb + 1 < N;
+            if (!v0) c0 = 0.0;
+            if (!v1) c1 = 0.0;
+            if (!(v0 && live)) d0 = 0.0;
+            if (!(v1 && live)) d1 = 0.0;
         }
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, na[sb][kk], rfrag[kk]);     // c = x - R_trunc a_k
+        for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, rfrag[kk], nab[sb][kk]);     // c = x - R_trunc a_k
         const double z0 = d0 * c0, z1 = d1 * c1;
         cost = fma(z0, c0, cost);
         cost = fma(z1, c1, cost);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) {
-            acc[o0 + q] = fma(z0, au[sb][q], acc[o0 + q]);
-            acc[o0 + NG + q] = fma(z1, au[sb][q], acc[o0 + NG + q]);
+            acc[q] = fma(z0, tb[q], acc[q]);
+            acc[q] = fma(z1, tb[NUB + q], acc[q]);
         }
 #pragma unroll
         for (int e = 0; e < NTRI; ++e) {
-            acc[o0 + NUB + e] = fma(d0, P[sb][e], acc[o0 + NUB + e]);
-            acc[o0 + NG + NUB + e] = fma(d1, P[sb][e], acc[o0 + NG + NUB + e]);
+            acc[NUB + e] = fma(d0, tb[2 * NUB + e], acc[NUB + e]);
+            acc[NUB + e] = fma(d1, tb[2 * NUB + NTRI + e], acc[NUB + e]);
         }
     }
 }
 
-// C-warps: one tile of the Gram panel with the new u.  B operand column c = 8 nb + gi of  u (x) [R_trunc | u]  is the product
-// of two entries of the row's [R_trunc | u] in the stage (offsets fa / fb; columns beyond NCOL point both factors at a zero).
-template <bool MASK, typename WT, int NUB, int S, int NBLK>
-__device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb32, int nrows, int ti, const unsigned (&fa_off)[NBLK],
-                                                 const unsigned (&fa_pitch)[NBLK], const unsigned (&fb_off)[NBLK], const unsigned (&fb_pitch)[NBLK], const int (&jc)[S],
-                                                 const bool (&valid)[S], double (&acc)[S][NBLK][2], double (&accx)[S][NUB]) {
+// C-warps: KSW k-steps (4 rows each) of one tile of the Gram panel with the new u, for the warp's 32 samples.  The lane's samples
+// are jb + 16 h + 2 gi + e (mb = 2 h + e is the MMA block, gi the row of the A fragment), so x and d come as pairs; k-step ks
+// covers tile rows 8 (ks / 2) + (ks % 2) + 2 ti (bank-conflict free with the recommended pitches).  B operand column
+// c = 8 nb + gi of  u (x) [R_trunc | u]  is the product of two entries of the row's [R_trunc | u] in the stage (offsets fa / fb;
+// columns beyond NCOL point both factors at a zero).
+template <bool MASK, typename WT, int NUB, int KSW, int NBLK>
+__device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb32, int nrows, int ti, int ks0, uint32_t xoff, uint32_t doff,
+                                                 const unsigned (&fa_off)[NBLK], const unsigned (&fa_pitch)[NBLK], const unsigned (&fb_off)[NBLK],
+                                                 const unsigned (&fb_pitch)[NBLK], const bool (&valid)[4], double (&acc)[4][NBLK][2],
+                                                 double (&accx)[4][NUB]) {
     const unsigned upitch = (unsigned)(a.g.ldu * 8);
-#pragma unroll 2
-    for (int ks = 0; ks < kFusedRows / 4; ++ks) {
-        const int row = 4 * ks + ti;
+#pragma unroll
+    for (int i = 0; i < KSW; ++i) {
+        const int ks = ks0 + i;
+        const int row = 8 * (ks >> 1) + (ks & 1) + 2 * ti;
         const bool lrow = row < nrows;
         double bfrag[NBLK], un[NUB];
 #pragma unroll
@@ -233,23 +228,33 @@ __device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb
             lds1(sb32 + fb_off[nb] + (uint32_t)row * fb_pitch[nb], fb);
             bfrag[nb] = fa * fb;
         }
+        if (NUB == 2) lds2(sb32 + a.offU + (uint32_t)row * upitch, un[0], un[NUB - 1]);
+        else {
 #pragma unroll
-        for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
-        const uint32_t xr = sb32 + (uint32_t)row * a.pitchX + (MASK ? 0u : (uint32_t)jc[0] * 8u);
-        const uint32_t dr = sb32 + a.offD + (uint32_t)row * a.pitchD + (MASK ? 0u : (uint32_t)jc[0] * (unsigned)sizeof(WT));
+            for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
+        }
+        const uint32_t xr = sb32 + (uint32_t)row * a.pitchX + xoff;
+        const uint32_t dr = sb32 + a.offD + (uint32_t)row * a.pitchD + doff;
 #pragma unroll
-        for (int mb = 0; mb < S; ++mb) {
-            double x;
-            lds1(xr + (MASK ? (uint32_t)jc[mb] * 8u : (uint32_t)mb * 64u), x);
-            double d = lds_weight<WT>(dr + (MASK ? (uint32_t)jc[mb] * (unsigned)sizeof(WT) : (uint32_t)mb * 8u * (unsigned)sizeof(WT)));
+        for (int h = 0; h < 2; ++h) {
+            double x0, x1, d0, d1;
+            lds2(xr + (uint32_t)h * 128u, x0, x1);
+            lds_weight2<WT>(dr + (uint32_t)h * 16u * (unsigned)sizeof(WT), d0, d1);
             if (MASK) {
-                if (!(valid[mb] && lrow)) { d = 0.0; x = 0.0; }
+                if (!(valid[2 * h] && lrow)) { d0 = 0.0; x0 = 0.0; }
+                if (!(valid[2 * h + 1] && lrow)) { d1 = 0.0; x1 = 0.0; }
             }
-            const double dx = d * x;
+            const double dx0 = d0 * x0, dx1 = d1 * x1;
 #pragma unroll
-            for (int q = 0; q < NUB; ++q) accx[mb][q] = fma(dx, un[q], accx[mb][q]);
+            for (int q = 0; q < NUB; ++q) {
+                accx[2 * h][q] = fma(dx0, un[q], accx[2 * h][q]);
+                accx[2 * h + 1][q] = fma(dx1, un[q], accx[2 * h + 1][q]);
+            }
 #pragma unroll
-            for (int nb = 0; nb < NBLK; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], d, bfrag[nb]);
+            for (int nb = 0; nb < NBLK; ++nb) {
+                dmma884(acc[2 * h][nb][0], acc[2 * h][nb][1], d0, bfrag[nb]);
+                dmma884(acc[2 * h + 1][nb][0], acc[2 * h + 1][nb][1], d1, bfrag[nb]);
+            }
         }
     }
 }
@@ -263,7 +268,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     constexpr int NCOL = NUB * KB + NTRI;             // panel columns: u_q R_k (q major), then the upper triangle of u u^T
     constexpr int NBLK = (NCOL + 7) / 8;
     constexpr int NS = kFusedStages, TR = kFusedRows;
-    constexpr int NV = ((2 * 2 * NG + 7) / 8) * 8;    // per-lane row partials of one tile: 2 row blocks x 2 rows x NG, padded
+    constexpr int NSB = 2 * S;                        // A-warp: 8 rows x NSB blocks of 8 samples (4 sample groups x 2 row blocks)
+    constexpr int RSP = 4 / S;                        // C-warp: 32 samples x S k-steps (2 S sample groups x RSP row splits)
+    constexpr unsigned PAIRB = 2u * NG * 8u;          // bytes of one pair record of the per-sample table
     const Geom& g = a.g;
     const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
@@ -298,6 +305,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         for (unsigned i = tid; i < n16; i += kFusedThreads)
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(stages32 + i * 16u), "r"(0u) : "memory");
     }
+    // per-sample table of the A-warps, one record per pair of samples: [a_u(j) | a_u(j + 1) | P(j) | P(j + 1)], zero beyond N
+    for (int p = tid; p < 32 * S; p += kFusedThreads) {
+        double* rec = reinterpret_cast<double*>(smem + a.offTab + (size_t)p * PAIRB);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = 2 * p + e;
+            double au[NUB];
+#pragma unroll
+            for (int q = 0; q < NUB; ++q) {
+                au[q] = (j < N && q < g.nu) ? Acur[(size_t)(K + q) * N + j] : 0.0;
+                rec[e * NUB + q] = au[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NUB; ++q)
+#pragma unroll
+                for (int q2 = q; q2 < NUB; ++q2) rec[2 * NUB + e * NTRI + tri_index(q, q2, NUB)] = au[q] * au[q2];
+        }
+    }
     if (tid < a.n_iter2) {
         // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
         const double l_w = st->l_w;
@@ -315,9 +340,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
 
     double cost = 0.0, ssq = 0.0;       // per-thread partials (A-warps: sum d c^2; U-warps: cross terms, ||u_new||^2)
     // C-warp state (declared here because it is stored after the CTA-wide barrier that follows the role loops)
-    double pacc[S][NBLK][2], paccx[S][NUB];
-    int jcC[S];
-    bool validC[S];
+    double pacc[4][NBLK][2], paccx[4][NUB];
+    bool validC[4];
+    const int cwC = warp - kFA, grpC = cwC / RSP, rqC = cwC - grpC * RSP;
+    const int jbC = 32 * grpC;          // lane's samples: jbC + 16 h + 2 gi + e  <->  MMA block mb = 2 h + e, fragment row gi
 
     if (warp >= kFA + kFC + kFU) {
         // =========================================================================== producer warp: the TMA ring
@@ -357,7 +383,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const double inv_lw = 1.0 / l_w;       // as u_inner_kernel: reciprocal multiply (<= 1 ulp of a ~1e-4-sized step vs the division of :88)
         const bool at_current = (g.mode == 2);
         const unsigned upitch = (unsigned)(g.ldu * 8);
-        // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
         const uint32_t beta32 = smem_u32(&ctl->beta[0]);
         for (int it = uw; it < n_my; it += kFU) {
             const int s = it % NS;
@@ -369,14 +394,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
             const bool live = lane < nrows;
             const int row = lane < TR ? lane : 0;
-            // row statistics: the 8 A-warp partials in warp order; the buffer is free for tile it + 2 as soon as they are in registers
+            // row statistics: the 4 sample-group partials in group order; the buffer is free for tile it + 2 as soon as they are in registers
             double v[NG];
 #pragma unroll
             for (int i = 0; i < NG; ++i) v[i] = 0.0;
             {
-                const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFA * TR * NG * 8u) + (uint32_t)row * (NG * 8u);
+                const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u) + (uint32_t)row * (NG * 8u);
 #pragma unroll
-                for (int w = 0; w < kFA; ++w)
+                for (int w = 0; w < kFusedSGroups; ++w)
 #pragma unroll
                     for (int i = 0; i < NG; ++i) {
                         double t;
@@ -428,69 +453,72 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         }
     } else if (warp < kFA) {
         // =========================================================================== A-warps: row statistics
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-        double na[S][KS > 0 ? KS : 1], au[S][NUB], P[S][NTRI > 0 ? NTRI : 1];
-        int jc[S];
-        bool valid[S];
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DMF_RA));
+        const int arb = warp & 1, asg = warp >> 1;                  // row block of the tile, sample group
+        const int rowA = 8 * arb + (gi >> 1) + 4 * (gi & 1);        // fragment row gi <-> tile row: lanes of a quarter warp read rows 4 apart
+        const int blk0 = asg * NSB;                                 // the warp's first block of 8 samples
+        const int nblk = min(NSB, max(0, (N + 7) / 8 - blk0));      // blocks that exist
+        const bool cols_full = 8 * (blk0 + NSB) <= N;               // every sample of this warp exists: no column masks
+        const int jlane = 8 * blk0 + 2 * ti;
+        double nab[NSB][KS > 0 ? KS : 1];                           // B operand: -alpha_k[4 kk + ti][sample gi of block sb]
 #pragma unroll
-        for (int sb = 0; sb < S; ++sb) {
-            const int j = 8 * (warp * S + sb) + gi;
-            valid[sb] = j < N;
-            jc[sb] = valid[sb] ? j : 0;
+        for (int sb = 0; sb < NSB; ++sb) {
+            const int j = 8 * (blk0 + sb) + gi;
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
+            for (int kk = 0; kk < (KS > 0 ? KS : 1); ++kk) {
                 const int k = 4 * kk + ti;
-                na[sb][kk] = (valid[sb] && k < K) ? -Acur[(size_t)k * N + j] : 0.0;
+                nab[sb][kk] = (KS > 0 && j < N && k < K) ? -Acur[(size_t)k * N + j] : 0.0;
             }
-#pragma unroll
-            for (int q = 0; q < NUB; ++q) au[sb][q] = (valid[sb] && q < g.nu) ? Acur[(size_t)(K + q) * N + j] : 0.0;
-#pragma unroll
-            for (int q = 0; q < NUB; ++q)
-#pragma unroll
-                for (int q2 = q; q2 < NUB; ++q2) P[sb][tri_index(q, q2, NUB)] = au[sb][q] * au[sb][q2];
         }
         const unsigned rpitch = (unsigned)(g.ldr * 8);
-        const bool cols_full = 8 * (warp * S + S) <= N;       // every sample of this warp exists: no column masks
+        const uint32_t xrel = (uint32_t)rowA * a.pitchX + (uint32_t)jlane * 8u;
+        const uint32_t drel = a.offD + (uint32_t)rowA * a.pitchD + (uint32_t)jlane * (unsigned)sizeof(WT);
+        const uint32_t ta = smem32 + a.offTab + (uint32_t)(4 * blk0 + ti) * PAIRB;
+        const uint32_t srel = a.offStats + (uint32_t)asg * (TR * NG * 8u) + (uint32_t)rowA * (NG * 8u);
         for (int it = 0; it < n_my; ++it) {
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
             mbar_wait(smem_u32(&ctl->full[s]), ph);
-            if (it >= 2) mbar_wait(smem_u32(&ctl->sfree[it & 1]), ((unsigned)((it >> 1) - 1)) & 1u);     // tile it - 2's partials were read
             const int nrows = tile_rows(it);
             const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
-            double acc[NV];
+            double rfrag[KS > 0 ? KS : 1];                          // A operand: R_trunc[row][4 kk + ti]
 #pragma unroll
-            for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-            if (cols_full && nrows == TR) {
-                fused_row_block<false, WT, KS, NUB, S>(a, sb32, nrows, 0, gi, ti, K, na, au, P, jc, valid, cost, acc);
-                fused_row_block<false, WT, KS, NUB, S>(a, sb32, nrows, 1, gi, ti, K, na, au, P, jc, valid, cost, acc);
-            } else {
-                fused_row_block<true, WT, KS, NUB, S>(a, sb32, nrows, 0, gi, ti, K, na, au, P, jc, valid, cost, acc);
-                fused_row_block<true, WT, KS, NUB, S>(a, sb32, nrows, 1, gi, ti, K, na, au, P, jc, valid, cost, acc);
+            for (int kk = 0; kk < KS; ++kk) {
+                const int k = 4 * kk + ti;
+                double t = 0.0;
+                if (k < K) lds1(sb32 + a.offR + (uint32_t)rowA * rpitch + (uint32_t)k * 8u, t);
+                rfrag[kk] = t;
             }
-            // sum over the 8 samples of a block row (lanes sharing ti), then one partial per (warp, row, value)
-            const int base = reduce_over_groups<NV>(acc, lane);
-            const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFA * TR * NG * 8u) + (uint32_t)warp * (TR * NG * 8u);
+            double acc[NG];
 #pragma unroll
-            for (int i = 0; i < NV / 8; ++i) {
-                const int slot = base + i;
-                if (slot < 4 * NG) {
-                    const int re = slot / NG, vi = slot - re * NG;       // re = rb * 2 + e
-                    const int row = 8 * (re >> 1) + ti + 4 * (re & 1);
-                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbase + (uint32_t)(row * NG + vi) * 8u), "d"(acc[i]) : "memory");
-                }
+            for (int i = 0; i < NG; ++i) acc[i] = 0.0;
+            if (cols_full && nrows == TR) fused_row_stats<false, WT, KS, NUB, NSB>(sb32 + xrel, sb32 + drel, ta, rfrag, nab, nblk, jlane, N, true, cost, acc);
+            else fused_row_stats<true, WT, KS, NUB, NSB>(sb32 + xrel, sb32 + drel, ta, rfrag, nab, nblk, jlane, N, rowA < nrows, cost, acc);
+            // sum over the 4 lanes of the row (ti), then one partial per (sample group, row, value)
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+            }
+            if (it >= 2) mbar_wait(smem_u32(&ctl->sfree[it & 1]), ((unsigned)((it >> 1) - 1)) & 1u);     // tile it - 2's partials were read
+            if (ti == 0) {
+                const uint32_t sbase = smem32 + srel + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u);
+#pragma unroll
+                for (int i = 0; i < NG; ++i) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbase + (uint32_t)i * 8u), "d"(acc[i]) : "memory");
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->stats[s]));
         }
     } else {
         // =========================================================================== C-warps: Gram panel with the new u
-        const int cw = warp - kFA;
+#if DMF_RC > 96
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DMF_RC));
+#elif DMF_RC < 96
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DMF_RC));
+#endif
 #pragma unroll
-        for (int mb = 0; mb < S; ++mb) {
-            const int j = 8 * (cw * S + mb) + gi;
-            validC[mb] = j < N;
-            jcC[mb] = validC[mb] ? j : 0;
+        for (int mb = 0; mb < 4; ++mb) {
+            validC[mb] = jbC + 16 * (mb >> 1) + 2 * gi + (mb & 1) < N;
 #pragma unroll
             for (int nb = 0; nb < NBLK; ++nb) { pacc[mb][nb][0] = 0.0; pacc[mb][nb][1] = 0.0; }
 #pragma unroll
@@ -518,7 +546,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             fb_off[nb] = fzero ? zero_off : ((k >= 0) ? a.offR + (unsigned)k * 8u : a.offU + (unsigned)q2 * 8u);
             fb_pitch[nb] = fzero ? 0u : ((k >= 0) ? rpitch : upitch);
         }
-        const bool cols_full = 8 * (cw * S + S) <= N;
+        const bool work = jbC < N;                     // (N <= 32 S - 32: this sample group is empty, the warp only keeps the ring moving)
+        const bool cols_full = jbC + 32 <= N;
+        const uint32_t xoff = (uint32_t)(jbC + 2 * gi) * 8u, doff = (uint32_t)(jbC + 2 * gi) * (unsigned)sizeof(WT);
+        const int ks0 = rqC * S;
         for (int it = 0; it < n_my; ++it) {
             const int s = it % NS;
             const unsigned ph = ((unsigned)(it / NS)) & 1u;
@@ -526,34 +557,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             mbar_wait(smem_u32(&ctl->full[s]), ph);
             const int nrows = tile_rows(it);
             const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
-            if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, S, NBLK>(a, sb32, nrows, ti, fa_off, fa_pitch, fb_off, fb_pitch, jcC, validC, pacc, paccx);
-            else fused_panel_tile<true, WT, NUB, S, NBLK>(a, sb32, nrows, ti, fa_off, fa_pitch, fb_off, fb_pitch, jcC, validC, pacc, paccx);
+            if (work) {
+                if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, S, NBLK>(a, sb32, nrows, ti, ks0, xoff, doff, fa_off, fa_pitch, fb_off, fb_pitch, validC, pacc, paccx);
+                else fused_panel_tile<true, WT, NUB, S, NBLK>(a, sb32, nrows, ti, ks0, xoff, doff, fa_off, fa_pitch, fb_off, fb_pitch, validC, pacc, paccx);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[s]));
         }
     }
     __syncthreads();
-    if (warp >= kFA && warp < kFA + kFC) {
-        const int cw = warp - kFA;
-        // CTA record: [cost, ||u||^2, panel NCOL x N, bx NUB x N] - the stage ring is free once every role left its loop
+    // CTA record: [cost, ||u||^2, panel NCOL x N, bx NUB x N] - the stage ring is free once every role left its loop.  The RSP
+    // C-warps that share a sample group (row splits of the tile) add their sums in split order.
+    {
         double* rec = reinterpret_cast<double*>(smem + kFusedCtlBytes);
 #pragma unroll
-        for (int mb = 0; mb < S; ++mb) {
-            const int j = 8 * (cw * S + mb) + gi;
+        for (int r = 0; r < RSP; ++r) {
+            if (warp >= kFA && warp < kFA + kFC && rqC == r) {
 #pragma unroll
-            for (int nb = 0; nb < NBLK; ++nb)
+                for (int mb = 0; mb < 4; ++mb) {
+                    const int j = jbC + 16 * (mb >> 1) + 2 * gi + (mb & 1);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = 8 * nb + 2 * ti + e;
-                    if (validC[mb] && c < NCOL) rec[2 + (size_t)c * N + j] = pacc[mb][nb][e];
+                    for (int nb = 0; nb < NBLK; ++nb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = 8 * nb + 2 * ti + e;
+                            if (validC[mb] && c < NCOL) {
+                                double* p = &rec[2 + (size_t)c * N + j];
+                                *p = (r == 0) ? pacc[mb][nb][e] : *p + pacc[mb][nb][e];
+                            }
+                        }
+#pragma unroll
+                    for (int q = 0; q < NUB; ++q) {
+                        double t = paccx[mb][q];
+                        t += __shfl_xor_sync(0xffffffffu, t, 1);
+                        t += __shfl_xor_sync(0xffffffffu, t, 2);
+                        if (validC[mb] && ti == 0) {
+                            double* p = &rec[2 + (size_t)(NCOL + q) * N + j];
+                            *p = (r == 0) ? t : *p + t;
+                        }
+                    }
                 }
-#pragma unroll
-            for (int q = 0; q < NUB; ++q) {
-                double t = paccx[mb][q];
-                t += __shfl_xor_sync(0xffffffffu, t, 1);
-                t += __shfl_xor_sync(0xffffffffu, t, 2);
-                if (validC[mb] && ti == 0) rec[2 + (size_t)(NCOL + q) * N + j] = t;
             }
+            if (r + 1 < RSP) __syncthreads();
         }
     }
     // scalar partials: warp sums, then the warps in order

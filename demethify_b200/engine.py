@@ -94,10 +94,10 @@ class DeviceProblem:
         self.M, self.N = X.shape
         # Row pitches (include/demethify_b200.h): a row tile reaches shared memory as ONE bulk copy and keeps its pitch there, so
         # the pitch decides the shared-memory bank pattern of the kernels that walk several rows per warp instruction (the fused
-        # engine's MMA fragments).  pitch = 32 bytes (X) / 16 bytes (u16 weights) beyond a multiple of 128 bytes is conflict free.
+        # engine's MMA fragments).  pitch = 16 bytes beyond a multiple of 128 bytes (X and u16 weights) is conflict free.
         es = 8 if self.dtype == torch.float64 else 4
         self.wide = self.N * es >= 512              # short rows: bank conflicts do not matter, padding would (tile geometry, bytes)
-        self.ldx = ((self.N * es + 127) // 128 * 128 + 32) // es if self.wide else (self.N + 7) // 8 * 8
+        self.ldx = ((self.N * es + 127) // 128 * 128 + 16) // es if self.wide else (self.N + 7) // 8 * 8
         self.X = _pad_cols(X, self.ldx)
         self.K = 0
         self.Rk = None
