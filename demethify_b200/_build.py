@@ -37,6 +37,28 @@ def _compile(nvcc, src, verbose):
     return obj, res.stderr
 
 
+def build_variant(tag, flags):
+    """Kernel experiments: the same sources with extra -D flags into demethify_b200/variants/lib_<tag>.so (load with DMF_LIB=...)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    obj = os.path.join(HERE, "build_" + tag)
+    os.makedirs(obj, exist_ok=True)
+    os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+    out = os.path.join(HERE, "variants", f"lib_{tag}.so")
+
+    def one(src):
+        o = os.path.join(obj, src[:-3] + ".o")
+        res = subprocess.run([nvcc] + NVCC_FLAGS + list(flags) + ["-c", os.path.join(CSRC, src), "-o", o], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(res.stdout + res.stderr)
+        return o
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, _sources()))
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", out], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(res.stdout + res.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)

@@ -348,7 +348,7 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
         p.f_offStats = kFusedCtlBytes + kFusedStages * p.f_stage_bytes;
         // double-buffered row statistics (4 sample-group partials per row), then the per-sample table of the A-warps
         p.f_offTab = a128f(p.f_offStats + 2u * kFusedSGroups * kFusedRows * ng * 8u);
-        p.smem_f = p.f_offTab + 32u * p.s_f * 2u * ng * 8u;
+        p.smem_f = p.f_offTab + 32u * p.s_f * 2u * p.nub_f * 8u;
         (void)nblk;
         const size_t n_rec = 2 + (size_t)(ncol + p.nub_f) * s.N;
         if (p.smem_f <= smem_cap && kFusedCtlBytes + n_rec * 8 <= p.f_offStats) {

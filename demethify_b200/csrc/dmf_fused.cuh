@@ -30,7 +30,10 @@
 
 namespace dmf {
 
-constexpr int kFA = 8, kFC = 8, kFU = 3, kFP = 1;
+#ifndef DMF_FU
+#define DMF_FU 3
+#endif
+constexpr int kFA = 8, kFC = 8, kFU = DMF_FU, kFP = 1;
 // Registers per thread after the role split (setmaxnreg; the kernel is launched with 96): 256 (RA + RC) + 128 x 64 <= 640 x 96
 #ifndef DMF_RA
 #define DMF_RA 96
@@ -38,10 +41,13 @@ constexpr int kFA = 8, kFC = 8, kFU = 3, kFP = 1;
 #ifndef DMF_RC
 #define DMF_RC 112
 #endif
-static_assert(DMF_RA % 8 == 0 && DMF_RC % 8 == 0 && DMF_RA + DMF_RC <= 208, "register split of the fused pass");
+static_assert(DMF_RA % 8 == 0 && DMF_RC % 8 == 0 && 256 * (DMF_RA + DMF_RC) + 32 * (DMF_FU + 1) * 64 <= 32 * (17 + DMF_FU) * 96, "register split of the fused pass");
 constexpr int kFusedThreads = (kFA + kFC + kFU + kFP) * 32;
 constexpr int kFusedRows = 16;           // rows per tile (two 8-row MMA blocks, four 4-row k-steps)
-constexpr int kFusedStages = 5;
+#ifndef DMF_STAGES
+#define DMF_STAGES 5
+#endif
+constexpr int kFusedStages = DMF_STAGES;
 constexpr int kFusedMaxInner = 64;       // beyond this the U-warps (16 rows at a time) would bound the pass: Gram engine instead
 constexpr unsigned kFusedCtlBytes = 2048;
 constexpr int kFusedSGroups = 4;         // A-warps: 2 row blocks x 4 sample groups; a row has 4 partial statistics records
@@ -64,7 +70,7 @@ typedef void (*fused_kern_t)(const FusedArgs);
 struct FusedCtl {
     unsigned long long full[8], empty[8], stats[8], udone[8], sfree[2];
     double wsum[2][kFA + kFC + kFU + kFP];
-    double beta[kFusedMaxInner];          // extrapolation weights of this launch's update_u iterations (the same for every row)
+    double beta[2 * kFusedMaxInner];      // (1 + beta_t, -beta_t) of this launch's update_u iterations (the same for every row)
     int flag, commit;
 };
 static_assert(sizeof(FusedCtl) <= kFusedCtlBytes, "fused control block too large");
@@ -95,22 +101,32 @@ __device__ __forceinline__ double clip01_keepnan(double v) {
     double r = v > 1.0 ? 1.0 : v;
     return v < 0.0 ? 0.0 : r;
 }
+// The same clip on the integer pipe, for FINITE v (the U-warps check once per tile that every iterate stays finite): every
+// FP64 instruction of a U-warp queues behind the DMMAs of the other 16 warps, integer compares do not.
+//   v < 0  <=>  sign bit set (-0.0 -> 0.0, equal);   v > 1  <=>  sign clear and bits > bits(1.0)
+__device__ __forceinline__ double clip01_finite(double v) {
+    const long long b = __double_as_longlong(v);
+    const bool big = (unsigned long long)b > 0x3FF0000000000000ull;
+    const bool neg = b < 0;
+    const long long r = neg ? 0ll : (big ? 0x3FF0000000000000ll : b);
+    return __longlong_as_double(r);
+}
 
 // One update_u step of deconvolution.py:82-89 (gradient at u for the unsupervised variant, :163) on the row's statistics,
 // (prev, cur) -> next.  The U-warps run 16 rows x n_iter2 of these back to back while the other 16 warps of the CTA keep the
-// FP64 pipe busy - every dependent FP64 operation queues behind their DMMAs - so the DEPTH of the chain from cur to next is
-// what counts.  With  Mh = H / l_w,  c = b / l_w  and  Am = I - Mh  (per row, once):
-//     u_t = u + beta (u - u_)                        ->  fma(1 + beta, u, -beta u_)        (-beta u_ does not depend on u)
+// FP64 pipe busy - every FP64 instruction queues behind their DMMAs - so both the DEPTH of the chain from cur to next and the
+// NUMBER of FP64 instructions count.  With  Mh = H / l_w,  c = b / l_w  and  Am = I - Mh  (per row, once):
+//     u_t = u + beta (u - u_)                        ->  fma(1 + beta, u, (-beta) u_)      ((-beta) u_ does not depend on u)
 //     u_t + (b - H u_t) / l_w  =  Am u_t + c         ->  fma(Am_qq, u_t[q], fma(Am_qq', u_t[q'], c_q))
-// i.e. 3 dependent FP64 operations + the comparison per iteration instead of 9; the roundings differ from the reference's
-// operation order by ~1 ulp of u per iteration, the same size as the reference's own rounding of u_t + step.
-template <bool AT_CURRENT, int NUB>
+// i.e. 3 dependent FP64 operations per iteration instead of 9 and the clip on the integer pipe; the roundings differ from the
+// reference's operation order by ~1 ulp of u per iteration, the same size as the reference's own rounding of u_t + step.
+// bt = (1 + beta_t, -beta_t) from shared memory.
+template <bool AT_CURRENT, bool FINITE, int NUB>
 __device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const double (&cu)[NUB], const double (&am)[NUB][NUB],
-                                             const double (&c)[NUB], double beta, double (&nx)[NUB]) {
-    const double opb = 1.0 + beta;
+                                             const double (&c)[NUB], double opb, double nbeta, double (&nx)[NUB]) {
     double ut[NUB];
 #pragma unroll
-    for (int q = 0; q < NUB; ++q) ut[q] = fma(opb, cu[q], -beta * pv[q]);
+    for (int q = 0; q < NUB; ++q) ut[q] = fma(opb, cu[q], nbeta * pv[q]);
 #pragma unroll
     for (int q = 0; q < NUB; ++q) {
         double un;
@@ -126,59 +142,99 @@ __device__ __forceinline__ void fused_u_step(const double (&pv)[NUB], const doub
                 if (q2 != q) un = fma(am[q][q2], ut[q2], un);
             un = fma(am[q][q], ut[q], un);
         }
-        nx[q] = clip01_keepnan(un);
+        nx[q] = FINITE ? clip01_finite(un) : clip01_keepnan(un);
     }
 }
-// n2 steps, two at a time so that (u_, u) rotate without register copies; beta_t comes from shared memory
-template <bool AT_CURRENT, int NUB>
-__device__ __forceinline__ void fused_u_iterate(double (&u)[NUB], double (&up)[NUB], const double (&v)[ng_of(NUB)], uint32_t beta32, int n2,
-                                                double inv_lw) {
-    double am[NUB][NUB], c[NUB];
-#pragma unroll
-    for (int q = 0; q < NUB; ++q) {
-        c[q] = v[q] * inv_lw;
-#pragma unroll
-        for (int q2 = 0; q2 < NUB; ++q2) {
-            const double mh = v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))] * inv_lw;
-            am[q][q2] = (!AT_CURRENT && q == q2) ? 1.0 - mh : -mh;
-        }
-    }
+// n2 steps, two at a time so that (u_, u) rotate without register copies; (1 + beta_t, -beta_t) come from shared memory
+template <bool AT_CURRENT, bool FINITE, int NUB>
+__device__ __forceinline__ void fused_u_loop(double (&u)[NUB], double (&up)[NUB], const double (&am)[NUB][NUB], const double (&c)[NUB],
+                                             uint32_t beta32, int n2) {
     int itn = 0;
     for (; itn + 2 <= n2; itn += 2) {
-        double b0, b1, n1[NUB], n3[NUB];
-        lds2(beta32 + (uint32_t)itn * 8u, b0, b1);
-        fused_u_step<AT_CURRENT, NUB>(up, u, am, c, b0, n1);
-        fused_u_step<AT_CURRENT, NUB>(u, n1, am, c, b1, n3);
+        double o0, b0, o1, b1, n1[NUB], n3[NUB];
+        lds2(beta32 + (uint32_t)itn * 16u, o0, b0);
+        lds2(beta32 + (uint32_t)itn * 16u + 16u, o1, b1);
+        fused_u_step<AT_CURRENT, FINITE, NUB>(up, u, am, c, o0, b0, n1);
+        fused_u_step<AT_CURRENT, FINITE, NUB>(u, n1, am, c, o1, b1, n3);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) { up[q] = n1[q]; u[q] = n3[q]; }
     }
     if (itn < n2) {
-        double b0, n1[NUB];
-        lds1(beta32 + (uint32_t)itn * 8u, b0);
-        fused_u_step<AT_CURRENT, NUB>(up, u, am, c, b0, n1);
+        double o0, b0, n1[NUB];
+        lds2(beta32 + (uint32_t)itn * 16u, o0, b0);
+        fused_u_step<AT_CURRENT, FINITE, NUB>(up, u, am, c, o0, b0, n1);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) { up[q] = u[q]; u[q] = n1[q]; }
+    }
+}
+template <bool AT_CURRENT, int NUB>
+__device__ __forceinline__ void fused_u_iterate(double (&u)[NUB], double (&up)[NUB], const double (&v)[ng_of(NUB)], uint32_t beta32, int n2,
+                                                double inv_lw) {
+    double am[NUB][NUB], c[NUB];
+    // every iterate stays finite (|u_next| <= |Am| |u_t| + |c| with |u_t| <= 3) when the row's constants and the incoming pair are
+    // moderate: then the clip runs on the integer pipe; otherwise (l_w = 0, NaN / Inf in the data) the comparisons keep numpy's NaN rules
+    bool tame = true;
+#pragma unroll
+    for (int q = 0; q < NUB; ++q) {
+        c[q] = v[q] * inv_lw;
+        tame = tame && fabs(c[q]) < 1e150 && fabs(u[q]) <= 1.0 && fabs(up[q]) <= 1.0;
+#pragma unroll
+        for (int q2 = 0; q2 < NUB; ++q2) {
+            const double mh = v[NUB + (q <= q2 ? tri_index(q, q2, NUB) : tri_index(q2, q, NUB))] * inv_lw;
+            am[q][q2] = (!AT_CURRENT && q == q2) ? 1.0 - mh : -mh;
+            tame = tame && fabs(mh) < 1e150;
+        }
+    }
+    if (__all_sync(0xffffffffu, tame)) fused_u_loop<AT_CURRENT, true, NUB>(u, up, am, c, beta32, n2);
+    else fused_u_loop<AT_CURRENT, false, NUB>(u, up, am, c, beta32, n2);
+}
+
+// Two unknown types: the two components of a row live in lanes (row, row + 16), so a U-warp issues half as many FP64 instructions
+// per iteration (each of them queues behind the DMMAs of the other warps) and uses all 32 lanes; the other component's u_t
+// (u at :163) comes through one shuffle.  cu / pv: own component of (u, u_); on return (u_new, previous u_new).
+template <bool AT_CURRENT, bool FINITE>
+__device__ __forceinline__ void fused_u_loop_split(double& cu, double& pv, double am_own, double am_oth, double c, uint32_t beta32, int n2) {
+    for (int itn = 0; itn < n2; ++itn) {
+        double opb, nbeta, un;
+        lds2(beta32 + (uint32_t)itn * 16u, opb, nbeta);
+        const double ut = fma(opb, cu, nbeta * pv);
+        if (AT_CURRENT) {
+            const double cuo = __shfl_xor_sync(0xffffffffu, cu, 16);
+            un = ut + fma(am_oth, cuo, fma(am_own, cu, c));
+        } else {
+            const double t = fma(am_own, ut, c);
+            const double uto = __shfl_xor_sync(0xffffffffu, ut, 16);
+            un = fma(am_oth, uto, t);
+        }
+        pv = cu;
+        cu = FINITE ? clip01_finite(un) : clip01_keepnan(un);
     }
 }
 
 // A-warps: row statistics of ONE row (the lane's, rows on the M side of the MMA) over the warp's NSB blocks of 8 samples; the lane
 // owns samples 2 ti, 2 ti + 1 of every block.  xa / da: the lane's row at the warp's first block, sample 2 ti; ta: the lane's pair
-// record of the per-sample table [a_u(j) | a_u(j + 1) | P(j) | P(j + 1)] (P = upper triangle of a_u a_u^T).  MASK: the tile is short
-// or some of the warp's samples do not exist (nblk = existing blocks, jlane = first block's sample 2 ti).
+// record [a_u(j) | a_u(j + 1)] of the per-sample table.  The shared-memory data pipe is the busiest unit of this kernel after the
+// FP64 pipe, so the table holds a_u only and the H terms go through w_q = d a_u[q]:  b_q += w_q c,  H_qq' += w_q a_u[q'].
+// MASK: the tile is short or some of the warp's samples do not exist (nblk = existing blocks, jlane = first block's sample 2 ti).
 // acc = [b (NUB) | H upper triangle] of the row.
 template <bool MASK, typename WT, int KS, int NUB, int NSB>
 __device__ __forceinline__ void fused_row_stats(uint32_t xa, uint32_t da, uint32_t ta, const double (&rfrag)[KS > 0 ? KS : 1],
                                                 const double (&nab)[NSB][KS > 0 ? KS : 1], int nblk, int jlane, int N, bool live,
                                                 double& cost, double (&acc)[ng_of(NUB)]) {
-    constexpr int NG = ng_of(NUB), NTRI = NG - NUB;
 #pragma unroll
     for (int sb = 0; sb < NSB; ++sb) {
         if (MASK && sb >= nblk) break;
-        double c0, c1, d0, d1, tb[2 * NG];
+        double c0, c1, d0, d1, au0[NUB], au1[NUB];
         lds2(xa + (uint32_t)sb * 64u, c0, c1);
         lds_weight2<WT>(da + (uint32_t)sb * 8u * (unsigned)sizeof(WT), d0, d1);
+        if (NUB == 1) lds2(ta + (uint32_t)sb * 64u, au0[0], au1[0]);
+        else {
 #pragma unroll
-        for (int i = 0; i < NG; ++i) lds2(ta + (uint32_t)sb * (4u * 2u * NG * 8u) + (uint32_t)i * 16u, tb[2 * i], tb[2 * i + 1]);
+            for (int i = 0; i < NUB / 2; ++i) {
+                lds2(ta + (uint32_t)sb * (4u * 2u * NUB * 8u) + (uint32_t)i * 16u, au0[2 * i], au0[2 * i + 1]);
+                lds2(ta + (uint32_t)sb * (4u * 2u * NUB * 8u) + (uint32_t)(NUB / 2 + i) * 16u, au1[2 * i], au1[2 * i + 1]);
+            }
+        }
         if (MASK) {
             const bool v0 = jlane + 8 * sb < N, v1 = jlane + 8 * sb + 1 < N;
             if (!v0) c0 = 0.0;
@@ -193,46 +249,45 @@ __device__ __forceinline__ void fused_row_stats(uint32_t xa, uint32_t da, uint32
         cost = fma(z1, c1, cost);
 #pragma unroll
         for (int q = 0; q < NUB; ++q) {
-            acc[q] = fma(z0, tb[q], acc[q]);
-            acc[q] = fma(z1, tb[NUB + q], acc[q]);
-        }
+            const double w0 = d0 * au0[q], w1 = d1 * au1[q];
+            acc[q] = fma(w0, c0, acc[q]);
+            acc[q] = fma(w1, c1, acc[q]);
 #pragma unroll
-        for (int e = 0; e < NTRI; ++e) {
-            acc[NUB + e] = fma(d0, tb[2 * NUB + e], acc[NUB + e]);
-            acc[NUB + e] = fma(d1, tb[2 * NUB + NTRI + e], acc[NUB + e]);
+            for (int q2 = q; q2 < NUB; ++q2) {
+                acc[NUB + tri_index(q, q2, NUB)] = fma(w0, au0[q2], acc[NUB + tri_index(q, q2, NUB)]);
+                acc[NUB + tri_index(q, q2, NUB)] = fma(w1, au1[q2], acc[NUB + tri_index(q, q2, NUB)]);
+            }
         }
     }
 }
 
 // C-warps: KSW k-steps (4 rows each) of one tile of the Gram panel with the new u, for the warp's 32 samples.  The lane's samples
 // are jb + 16 h + 2 gi + e (mb = 2 h + e is the MMA block, gi the row of the A fragment), so x and d come as pairs; k-step ks
-// covers tile rows 8 (ks / 2) + (ks % 2) + 2 ti (bank-conflict free with the recommended pitches).  B operand column
-// c = 8 nb + gi of  u (x) [R_trunc | u]  is the product of two entries of the row's [R_trunc | u] in the stage (offsets fa / fb;
-// columns beyond NCOL point both factors at a zero).
-template <bool MASK, typename WT, int NUB, int KSW, int NBLK>
+// covers tile rows 8 (ks / 2) + (ks % 2) + 2 ti (bank-conflict free with the recommended pitches).  The B operand is
+// u_q (x) W with W = [R_trunc | u] (KB + NUB columns, WB blocks of 8): block nb = q WB + wb, column gi = u_q W[8 wb + gi]; the lane
+// reads its W entry from the stage (w_off / w_pitch; columns that do not exist point at a zero with pitch 0).
+template <bool MASK, typename WT, int NUB, int KSW, int WB>
 __device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb32, int nrows, int ti, int ks0, uint32_t xoff, uint32_t doff,
-                                                 const unsigned (&fa_off)[NBLK], const unsigned (&fa_pitch)[NBLK], const unsigned (&fb_off)[NBLK],
-                                                 const unsigned (&fb_pitch)[NBLK], const bool (&valid)[4], double (&acc)[4][NBLK][2],
-                                                 double (&accx)[4][NUB]) {
+                                                 const unsigned (&w_off)[WB], const unsigned (&w_pitch)[WB], const bool (&valid)[4],
+                                                 double (&acc)[4][NUB * WB][2], double (&accx)[4][NUB]) {
     const unsigned upitch = (unsigned)(a.g.ldu * 8);
 #pragma unroll
     for (int i = 0; i < KSW; ++i) {
         const int ks = ks0 + i;
         const int row = 8 * (ks >> 1) + (ks & 1) + 2 * ti;
         const bool lrow = row < nrows;
-        double bfrag[NBLK], un[NUB];
-#pragma unroll
-        for (int nb = 0; nb < NBLK; ++nb) {
-            double fa, fb;
-            lds1(sb32 + fa_off[nb] + (uint32_t)row * fa_pitch[nb], fa);
-            lds1(sb32 + fb_off[nb] + (uint32_t)row * fb_pitch[nb], fb);
-            bfrag[nb] = fa * fb;
-        }
+        double bfrag[NUB * WB], un[NUB], w[WB];
         if (NUB == 2) lds2(sb32 + a.offU + (uint32_t)row * upitch, un[0], un[NUB - 1]);
         else {
 #pragma unroll
             for (int q = 0; q < NUB; ++q) lds1(sb32 + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, un[q]);
         }
+#pragma unroll
+        for (int wb = 0; wb < WB; ++wb) lds1(sb32 + w_off[wb] + (uint32_t)row * w_pitch[wb], w[wb]);
+#pragma unroll
+        for (int q = 0; q < NUB; ++q)
+#pragma unroll
+            for (int wb = 0; wb < WB; ++wb) bfrag[q * WB + wb] = un[q] * w[wb];
         const uint32_t xr = sb32 + (uint32_t)row * a.pitchX + xoff;
         const uint32_t dr = sb32 + a.offD + (uint32_t)row * a.pitchD + doff;
 #pragma unroll
@@ -251,7 +306,7 @@ __device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb
                 accx[2 * h + 1][q] = fma(dx1, un[q], accx[2 * h + 1][q]);
             }
 #pragma unroll
-            for (int nb = 0; nb < NBLK; ++nb) {
+            for (int nb = 0; nb < NUB * WB; ++nb) {
                 dmma884(acc[2 * h][nb][0], acc[2 * h][nb][1], d0, bfrag[nb]);
                 dmma884(acc[2 * h + 1][nb][0], acc[2 * h + 1][nb][1], d1, bfrag[nb]);
             }
@@ -266,17 +321,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     constexpr int NG = ng_of(NUB);
     constexpr int NTRI = NG - NUB;
     constexpr int NCOL = NUB * KB + NTRI;             // panel columns: u_q R_k (q major), then the upper triangle of u u^T
-    constexpr int NBLK = (NCOL + 7) / 8;
+    constexpr int WB = (KB + NUB + 7) / 8;            // blocks of 8 columns of W = [R_trunc | u]; the panel MMA runs u_q (x) W per q
+    constexpr int NBLK = NUB * WB;
     constexpr int NS = kFusedStages, TR = kFusedRows;
     constexpr int NSB = 2 * S;                        // A-warp: 8 rows x NSB blocks of 8 samples (4 sample groups x 2 row blocks)
     constexpr int RSP = 4 / S;                        // C-warp: 32 samples x S k-steps (2 S sample groups x RSP row splits)
-    constexpr unsigned PAIRB = 2u * NG * 8u;          // bytes of one pair record of the per-sample table
+    constexpr unsigned PAIRB = 2u * NUB * 8u;         // bytes of one pair record of the per-sample table
     const Geom& g = a.g;
     const FitDev f = a.fits[fit_id(g)];
     FitState* st = f.st;
     if (st->done) return;
     FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+#ifdef DMF_ROLE_SPLIT
+    // experiment: A-warps on SM sub-partitions 0 and 1, C-warps on 2 and 3 (hardware warp w runs on sub-partition w % 4)
+    const int hw = tid >> 5;
+    const int warp = hw >= kFA + kFC ? hw : ((hw & 3) < 2 ? 2 * (hw >> 2) + (hw & 1) : kFA + 2 * (hw >> 2) + (hw & 1));
+#else
+    const int warp = tid >> 5;
+#endif
     const int gi = lane >> 2, ti = lane & 3;
     const uint32_t smem32 = smem_u32(smem);
     const uint32_t stages32 = smem32 + kFusedCtlBytes;
@@ -291,7 +354,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         for (int s = 0; s < NS; ++s) {
             mbar_init(smem_u32(&ctl->full[s]), 1);
             mbar_init(smem_u32(&ctl->empty[s]), kFC);
-            mbar_init(smem_u32(&ctl->stats[s]), kFA);
+            mbar_init(smem_u32(&ctl->stats[s]), kFA * 8);      // the 8 writer lanes of every A-warp
             mbar_init(smem_u32(&ctl->udone[s]), 1);
         }
         mbar_init(smem_u32(&ctl->sfree[0]), 1);
@@ -305,38 +368,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         for (unsigned i = tid; i < n16; i += kFusedThreads)
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(stages32 + i * 16u), "r"(0u) : "memory");
     }
-    // per-sample table of the A-warps, one record per pair of samples: [a_u(j) | a_u(j + 1) | P(j) | P(j + 1)], zero beyond N
+    // per-sample table of the A-warps, one record per pair of samples: [a_u(j) | a_u(j + 1)], zero beyond N
     for (int p = tid; p < 32 * S; p += kFusedThreads) {
         double* rec = reinterpret_cast<double*>(smem + a.offTab + (size_t)p * PAIRB);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int j = 2 * p + e;
-            double au[NUB];
 #pragma unroll
-            for (int q = 0; q < NUB; ++q) {
-                au[q] = (j < N && q < g.nu) ? Acur[(size_t)(K + q) * N + j] : 0.0;
-                rec[e * NUB + q] = au[q];
-            }
-#pragma unroll
-            for (int q = 0; q < NUB; ++q)
-#pragma unroll
-                for (int q2 = q; q2 < NUB; ++q2) rec[2 * NUB + e * NTRI + tri_index(q, q2, NUB)] = au[q] * au[q2];
+            for (int q = 0; q < NUB; ++q) rec[e * NUB + q] = (j < N && q < g.nu) ? Acur[(size_t)(K + q) * N + j] : 0.0;
         }
     }
     if (tid < a.n_iter2) {
         // beta_t = min((a_t - 1) / a_{t+1}, 0.9999 sqrt(l_w_ / l_w)); l_w_ == l_w from the second inner iteration on (:89)
         const double l_w = st->l_w;
         const double cap = 0.9999 * sqrt((tid == 0 ? st->l_w_old : l_w) / l_w);
-        ctl->beta[tid] = fmin(a.mom_m[st->t_u + tid], cap);
+        const double bt = fmin(a.mom_m[st->t_u + tid], cap);
+        ctl->beta[2 * tid] = 1.0 + bt;
+        ctl->beta[2 * tid + 1] = -bt;
     }
     fence_proxy_async_smem();
     __syncthreads();
 
-    auto tile_rows = [&](int it) {
-        const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
-        const long long left = g.M - r0;
-        return (int)(left < TR ? left : TR);
-    };
+    // only the last tile of the matrix can be short; it is local tile it_short of the CTA that owns it
+    const int rows_last = (int)(g.M - (long long)(a.n_tiles - 1) * TR);
+    const int it_short = (rows_last < TR && (a.n_tiles - 1) % g.n_parts == part) ? (a.n_tiles - 1) / g.n_parts : -1;
+    auto tile_rows = [&](int it) { return it == it_short ? rows_last : TR; };
 
     double cost = 0.0, ssq = 0.0;       // per-thread partials (A-warps: sum d c^2; U-warps: cross terms, ||u_new||^2)
     // C-warp state (declared here because it is stored after the CTA-wide barrier that follows the role loops)
@@ -351,9 +407,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const char* Ucur_g = f.U + (size_t)ucur * g.uslot_bytes;
         const char* Uprv_g = f.U + (size_t)(ucur ^ 1) * g.uslot_bytes;
         const unsigned rbytes = (unsigned)(g.ldr * 8), ubytes = (unsigned)(g.ldu * 8);
+        int s = 0;
+        unsigned ph = 0;
         for (int it = 0; it < n_my; ++it) {
-            const int s = it % NS;
-            mbar_wait(smem_u32(&ctl->empty[s]), (((unsigned)(it / NS)) & 1u) ^ 1u);      // the C-warps released tile it - NS
+            mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);      // the C-warps released tile it - NS
             const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
             const int nrows = tile_rows(it);
             const uint32_t full = smem_u32(&ctl->full[s]);
@@ -371,6 +428,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             if (lane == 3) bulk_g2s(sb + a.offU, Ucur_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
             if (lane == 4) bulk_g2s(sb + a.offUp, Uprv_g + r0 * (long long)ubytes, (unsigned)nrows * ubytes, full);
             __syncwarp();
+            if (++s == NS) { s = 0; ph ^= 1u; }
         }
     } else if (warp >= kFA + kFC) {
         // =========================================================================== U-warps: update_u on the row statistics
@@ -384,14 +442,67 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const bool at_current = (g.mode == 2);
         const unsigned upitch = (unsigned)(g.ldu * 8);
         const uint32_t beta32 = smem_u32(&ctl->beta[0]);
+        int s = uw % NS;
+        unsigned ph = (unsigned)(uw / NS) & 1u;
         for (int it = uw; it < n_my; it += kFU) {
-            const int s = it % NS;
-            const unsigned ph = ((unsigned)(it / NS)) & 1u;
             mbar_wait(smem_u32(&ctl->stats[s]), ph);
             mbar_wait(smem_u32(&ctl->full[s]), ph);        // complete long ago; orders this warp after the bulk copies
             const int nrows = tile_rows(it);
             const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
             const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
+            if constexpr (NUB == 2) {
+                // lane = (row, component): rows 0..15 in both half warps, component q = lane / 16
+                const int row = lane & 15, q = lane >> 4;
+                const bool live = row < nrows;
+                double v[NG];
+#pragma unroll
+                for (int i = 0; i < NG; ++i) v[i] = 0.0;
+                {
+                    const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u) + (uint32_t)row * (NG * 8u);
+#pragma unroll
+                    for (int w = 0; w < kFusedSGroups; ++w)
+#pragma unroll
+                        for (int i = 0; i < NG; ++i) {
+                            double t;
+                            lds1(sbase + (uint32_t)w * (TR * NG * 8u) + (uint32_t)i * 8u, t);
+                            v[i] += t;
+                        }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->sfree[it & 1]));
+                }
+                double cu, pv, cuo;
+                lds1(sb + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, cu);
+                lds1(sb + a.offUp + (uint32_t)row * upitch + (uint32_t)q * 8u, pv);
+                lds1(sb + a.offU + (uint32_t)row * upitch + (uint32_t)(q ^ 1) * 8u, cuo);
+                if (live && q == 0) {      // cost of the incoming iterate: -2 u^T b + u^T H u of this row
+                    double ct = cu * (fma(v[3], cuo, v[2] * cu) - 2.0 * v[0]);
+                    ct = fma(cuo, fma(v[4], cuo, v[3] * cu) - 2.0 * v[1], ct);
+                    cost += ct;
+                }
+#ifndef DMF_SKIP_U
+                {
+                    const double c = (q ? v[1] : v[0]) * inv_lw, mh_own = (q ? v[4] : v[2]) * inv_lw, mh_oth = v[3] * inv_lw;
+                    const double am_own = at_current ? -mh_own : 1.0 - mh_own, am_oth = -mh_oth;
+                    const bool tame = fabs(c) < 1e150 && fabs(mh_own) < 1e150 && fabs(mh_oth) < 1e150 && fabs(cu) <= 1.0 && fabs(pv) <= 1.0;
+                    if (__all_sync(0xffffffffu, tame)) {
+                        if (at_current) fused_u_loop_split<true, true>(cu, pv, am_own, am_oth, c, beta32, n2);
+                        else fused_u_loop_split<false, true>(cu, pv, am_own, am_oth, c, beta32, n2);
+                    } else {
+                        if (at_current) fused_u_loop_split<true, false>(cu, pv, am_own, am_oth, c, beta32, n2);
+                        else fused_u_loop_split<false, false>(cu, pv, am_own, am_oth, c, beta32, n2);
+                    }
+                }
+#endif
+                if (live) {
+                    Unew_g[(size_t)(r0 + row) * g.ldu + q] = cu;
+                    Unpv_g[(size_t)(r0 + row) * g.ldu + q] = pv;
+                    ssq = fma(cu, cu, ssq);
+                }
+                {
+                    const double un = live ? cu : 0.0;
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u), "d"(un) : "memory");
+                }
+            } else {
             const bool live = lane < nrows;
             const int row = lane < TR ? lane : 0;
             // row statistics: the 4 sample-group partials in group order; the buffer is free for tile it + 2 as soon as they are in registers
@@ -428,8 +539,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 }
                 cost += ct;
             }
+#ifndef DMF_SKIP_U
             if (at_current) fused_u_iterate<true, NUB>(u, up, v, beta32, n2, inv_lw);
             else fused_u_iterate<false, NUB>(u, up, v, beta32, n2, inv_lw);
+#endif
             // new iterate: global (other slot pair) and the stage (the C-warps form u (x) [R_trunc | u] and bx_u from it)
             if (live) {
 #pragma unroll
@@ -448,12 +561,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + a.offU + (uint32_t)lane * upitch + (uint32_t)q * 8u), "d"(un) : "memory");
                 }
             }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->udone[s]));
+            s += kFU % NS;
+            if (kFU >= NS) ph ^= (unsigned)(kFU / NS) & 1u;
+            if (s >= NS) { s -= NS; ph ^= 1u; }
         }
     } else if (warp < kFA) {
         // =========================================================================== A-warps: row statistics
+#if DMF_RA > 96
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DMF_RA));
+#elif DMF_RA < 96
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DMF_RA));
+#endif
         const int arb = warp & 1, asg = warp >> 1;                  // row block of the tile, sample group
         const int rowA = 8 * arb + (gi >> 1) + 4 * (gi & 1);        // fragment row gi <-> tile row: lanes of a quarter warp read rows 4 apart
         const int blk0 = asg * NSB;                                 // the warp's first block of 8 samples
@@ -475,12 +596,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const uint32_t drel = a.offD + (uint32_t)rowA * a.pitchD + (uint32_t)jlane * (unsigned)sizeof(WT);
         const uint32_t ta = smem32 + a.offTab + (uint32_t)(4 * blk0 + ti) * PAIRB;
         const uint32_t srel = a.offStats + (uint32_t)asg * (TR * NG * 8u) + (uint32_t)rowA * (NG * 8u);
+        int s = 0;
+        unsigned ph = 0;
+        uint32_t sb32 = stages32;
+        const bool writer = (ti == 0);
         for (int it = 0; it < n_my; ++it) {
-            const int s = it % NS;
-            const unsigned ph = ((unsigned)(it / NS)) & 1u;
             mbar_wait(smem_u32(&ctl->full[s]), ph);
             const int nrows = tile_rows(it);
-            const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
             double rfrag[KS > 0 ? KS : 1];                          // A operand: R_trunc[row][4 kk + ti]
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
@@ -492,8 +614,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             double acc[NG];
 #pragma unroll
             for (int i = 0; i < NG; ++i) acc[i] = 0.0;
+#ifndef DMF_SKIP_A
             if (cols_full && nrows == TR) fused_row_stats<false, WT, KS, NUB, NSB>(sb32 + xrel, sb32 + drel, ta, rfrag, nab, nblk, jlane, N, true, cost, acc);
             else fused_row_stats<true, WT, KS, NUB, NSB>(sb32 + xrel, sb32 + drel, ta, rfrag, nab, nblk, jlane, N, rowA < nrows, cost, acc);
+#endif
             // sum over the 4 lanes of the row (ti), then one partial per (sample group, row, value)
 #pragma unroll
             for (int i = 0; i < NG; ++i) {
@@ -501,13 +625,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
             }
             if (it >= 2) mbar_wait(smem_u32(&ctl->sfree[it & 1]), ((unsigned)((it >> 1) - 1)) & 1u);     // tile it - 2's partials were read
-            if (ti == 0) {
+            {   // the 8 lanes with ti == 0 store their row's record and arrive themselves (no warp-wide reconvergence)
                 const uint32_t sbase = smem32 + srel + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u);
 #pragma unroll
-                for (int i = 0; i < NG; ++i) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sbase + (uint32_t)i * 8u), "d"(acc[i]) : "memory");
+                for (int i = 0; i < NG; ++i)
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f64 [%0], %1;\n}" ::"r"(sbase + (uint32_t)i * 8u), "d"(acc[i]), "r"((unsigned)writer) : "memory");
+                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(smem_u32(&ctl->stats[s])), "r"((unsigned)writer) : "memory");
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&ctl->stats[s]));
+            sb32 += a.stage_bytes;
+            if (++s == NS) { s = 0; ph ^= 1u; sb32 = stages32; }
         }
     } else {
         // =========================================================================== C-warps: Gram panel with the new u
@@ -525,44 +651,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             for (int q = 0; q < NUB; ++q) paccx[mb][q] = 0.0;
         }
         const unsigned upitch = (unsigned)(g.ldu * 8), rpitch = (unsigned)(g.ldr * 8);
-        // B operand of the panel MMA: column c = 8 nb + gi of  u (x) [R_trunc | u]  =  (first factor u_q) x (second factor R_k or u_q2),
-        // formed per k-step from the stage (the U-warp left the new u there)
-        unsigned fa_off[NBLK], fa_pitch[NBLK], fb_off[NBLK], fb_pitch[NBLK];
-        const unsigned zero_off = a.zero_off;        // 8 bytes of every stage that are zeroed at kernel start and never copied over
+        // B operand of the panel MMA: u_q times the lane's entry of W = [R_trunc | u] (column 8 wb + gi), read from the stage
+        // (the U-warp left the new u there); a column that does not exist reads a zero (pitch 0: no select in the loop)
+        unsigned w_off[WB], w_pitch[WB];
 #pragma unroll
-        for (int nb = 0; nb < NBLK; ++nb) {
-            const int c = 8 * nb + gi;
-            int q = 0, q2 = 0, k = -1;
-            if (c < NUB * KB) { q = c / (KB > 0 ? KB : 1); k = c - q * KB; }
-            else if (c < NCOL) {
-                int e2 = c - NUB * KB;
-                while (e2 >= NUB - q) { e2 -= NUB - q; ++q; }
-                q2 = q + e2;
-            }
-            const bool fzero = c >= NCOL || q >= g.nu || (k >= 0 ? k >= K : q2 >= g.nu);
-            // a column that does not exist multiplies a zero by itself (no select in the loop)
-            fa_off[nb] = fzero ? zero_off : a.offU + (unsigned)q * 8u;
-            fa_pitch[nb] = fzero ? 0u : upitch;
-            fb_off[nb] = fzero ? zero_off : ((k >= 0) ? a.offR + (unsigned)k * 8u : a.offU + (unsigned)q2 * 8u);
-            fb_pitch[nb] = fzero ? 0u : ((k >= 0) ? rpitch : upitch);
+        for (int wb = 0; wb < WB; ++wb) {
+            const int w = 8 * wb + gi;
+            const bool isr = w < KB, exists = isr ? w < K : (w - KB) < g.nu && (w - KB) < NUB;
+            w_off[wb] = !exists ? a.zero_off : (isr ? a.offR + (unsigned)w * 8u : a.offU + (unsigned)(w - KB) * 8u);
+            w_pitch[wb] = !exists ? 0u : (isr ? rpitch : upitch);
         }
         const bool work = jbC < N;                     // (N <= 32 S - 32: this sample group is empty, the warp only keeps the ring moving)
         const bool cols_full = jbC + 32 <= N;
         const uint32_t xoff = (uint32_t)(jbC + 2 * gi) * 8u, doff = (uint32_t)(jbC + 2 * gi) * (unsigned)sizeof(WT);
         const int ks0 = rqC * S;
+        int s = 0;
+        unsigned ph = 0;
+        uint32_t sb32 = stages32;
         for (int it = 0; it < n_my; ++it) {
-            const int s = it % NS;
-            const unsigned ph = ((unsigned)(it / NS)) & 1u;
             mbar_wait(smem_u32(&ctl->udone[s]), ph);
             mbar_wait(smem_u32(&ctl->full[s]), ph);
             const int nrows = tile_rows(it);
-            const uint32_t sb32 = stages32 + (uint32_t)s * a.stage_bytes;
+#ifndef DMF_SKIP_C
             if (work) {
-                if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, S, NBLK>(a, sb32, nrows, ti, ks0, xoff, doff, fa_off, fa_pitch, fb_off, fb_pitch, validC, pacc, paccx);
-                else fused_panel_tile<true, WT, NUB, S, NBLK>(a, sb32, nrows, ti, ks0, xoff, doff, fa_off, fa_pitch, fb_off, fb_pitch, validC, pacc, paccx);
+                if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, S, WB>(a, sb32, nrows, ti, ks0, xoff, doff, w_off, w_pitch, validC, pacc, paccx);
+                else fused_panel_tile<true, WT, NUB, S, WB>(a, sb32, nrows, ti, ks0, xoff, doff, w_off, w_pitch, validC, pacc, paccx);
             }
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[s]));
+            sb32 += a.stage_bytes;
+            if (++s == NS) { s = 0; ph ^= 1u; sb32 = stages32; }
         }
     }
     __syncthreads();
@@ -580,8 +699,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                     for (int nb = 0; nb < NBLK; ++nb)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int c = 8 * nb + 2 * ti + e;
-                            if (validC[mb] && c < NCOL) {
+                            // block nb = q WB + wb holds u_q W[8 wb + 2 ti + e]: W columns < KB are R_trunc, then u_q2 (upper triangle kept)
+                            const int q = nb / WB, w = 8 * (nb - q * WB) + 2 * ti + e, q2 = w - KB;
+                            int c = -1;
+                            if (w < KB) c = q * KB + w;
+                            else if (q2 >= q && q2 < NUB) c = NUB * KB + tri_index(q < NUB ? q : 0, q2 >= q ? q2 : q, NUB);
+                            if (validC[mb] && c >= 0) {
                                 double* p = &rec[2 + (size_t)c * N + j];
                                 *p = (r == 0) ? pacc[mb][nb][e] : *p + pacc[mb][nb][e];
                             }
