@@ -9,6 +9,8 @@ streaming passes read the shared matrices contiguously and, with a fit-major gri
 the percentile arithmetic follow the reference exactly: seed_i = seed_{i-1} + i,
 sklearn.utils.resample == RandomState(seed).randint.
 """
+import os
+
 import numpy as np
 import pandas as pd
 import torch
@@ -79,6 +81,40 @@ def _shape_only_init(seed, init_option, M, K, N, n_u, with_zero_guard):
         alpha[-n_u:][0] = 1e-10
         alpha[:-n_u] = (1 - 1e-10) * alpha[:-n_u]
     return u, alpha
+
+
+def device_draws(chunk, M, n_u, K, N, dev, with_zero_guard):
+    """The draws of one wave of (resample seed, init seed) jobs with the `uniform_` init, on the device (dmf_rng_legacy_streams):
+    idx (B, M) int32 = RandomState(resample seed).randint(0, M, M) (bootstrap.py:28), u0 (B, M, n_u) = the first M n_u uniforms of
+    RandomState(init seed) (deconvolution.py:54-55); alpha_0 (B, Kt, N) numpy: the dirichlet draw that follows in the same stream,
+    taken by numpy itself from the generator state the kernel hands back (Kt N values; its -log(1 - U) must round like glibc's)."""
+    import ctypes as C
+    from .engine import _stream_ptr
+    lib = _lib.lib()
+    B = len(chunk)
+    row_seeds = sorted({j[0] for j in chunk})
+    pos = {sd: i for i, sd in enumerate(row_seeds)}
+    sr = torch.from_numpy(np.array(row_seeds, dtype=np.uint32).view(np.int32)).to(dev)        # (uint32 bits in an int32 tensor)
+    idx_u = torch.empty((len(row_seeds), M), dtype=torch.int32, device=dev)
+    _lib.check(lib.dmf_rng_legacy_streams(C.c_void_p(sr.data_ptr()), len(row_seeds), M, C.c_void_p(idx_u.data_ptr()), M, 0, None, 0, None,
+                                          _stream_ptr()))
+    idx_d = idx_u if len(row_seeds) == B else idx_u[torch.tensor([pos[j[0]] for j in chunk], device=dev)]
+    si = torch.from_numpy(np.array([j[1] for j in chunk], dtype=np.uint32).view(np.int32)).to(dev)
+    u0_d = torch.empty((B, M, n_u), dtype=torch.float64, device=dev)
+    state = torch.empty((B, 625), dtype=torch.int32, device=dev)
+    _lib.check(lib.dmf_rng_legacy_streams(C.c_void_p(si.data_ptr()), B, 0, None, 0, M * n_u, C.c_void_p(u0_d.data_ptr()), M * n_u,
+                                          C.c_void_p(state.data_ptr()), _stream_ptr()))
+    st = state.cpu().numpy().view(np.uint32)
+    A0 = np.empty((B, K + n_u, N))
+    rs = np.random.RandomState(0)
+    for k in range(B):
+        rs.set_state(("MT19937", st[k, :624], int(st[k, 624]), 0, 0.0))
+        alpha = rs.dirichlet(np.ones(K + n_u), N).T
+        if with_zero_guard and alpha[-n_u:][0].all() == 0.0:      # deconvolution.py:74-76 (init_BSSMF_md only)
+            alpha[-n_u:][0] = 1e-10
+            alpha[:-n_u] = (1 - 1e-10) * alpha[:-n_u]
+        A0[k] = alpha
+    return idx_d, u0_d, A0
 
 
 def percentile_bounds_device(stack, lower_percentile, upper_percentile):
@@ -192,40 +228,47 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
         per_fit = M * (row_bytes + 4 * (n_u + (n_u & 1)) * 8 + 8 + 8 * n_u * 3) + 64 * (prob.K + n_u) * N * 8 + (1 << 20)
         wave = int(max(1, min(n_bootstrap * restarts, (device_free_bytes(prob.device) * 2 // 3) // max(per_fit, 1), 1024)))
         wave = max(restarts, wave // restarts * restarts)
+    device_rng = (init_option == "uniform_" and prob.X.is_cuda and all(isinstance(t, (int, np.integer)) and 0 <= t < 2 ** 32 for j in jobs for t in j)
+                  and os.environ.get("DMF_HOST_RNG") != "1")
     for w0 in range(0, len(jobs), wave):
         chunk = jobs[w0:w0 + wave]
 
-        # host staging for the wave: the worker threads draw straight into it, one H2D copy per array (pageable on purpose:
-        # page-locking gigabytes per wave costs more than the copy saves)
         Bw = len(chunk)
-        idx_np = np.empty((Bw, M), dtype=np.int64)
-        u0_np = np.empty((Bw, M, n_u), dtype=np.float64)
-        A0 = np.empty((Bw, prob.K + n_u, N))
+        if device_rng:
+            # the two large draws of every resample come from the library's MT19937 kernel (bit-identical to numpy's
+            # legacy streams); the host only continues each stream for the Kt x N dirichlet draw of alpha_0
+            idx_d, u0_d, A0 = device_draws(chunk, M, n_u, prob.K, N, dev, with_zero_guard=purity is None)
+        else:
+            # host staging for the wave: the worker threads draw straight into it, one H2D copy per array (pageable on purpose:
+            # page-locking gigabytes per wave costs more than the copy saves)
+            idx_np = np.empty((Bw, M), dtype=np.int64)
+            u0_np = np.empty((Bw, M, n_u), dtype=np.float64)
+            A0 = np.empty((Bw, prob.K + n_u, N))
 
-        def prepare(k):
-            s_rows, s = chunk[k]
-            idx = resample_indices(s_rows, M)
-            if data_dependent_init:      # `uniform` / SVD look at the resampled data and use the global stream: sequential
-                Xb, Db, Rb = meth_f[idx], np.asarray(counts)[idx], np.asarray(ref)[idx]
-                if purity is not None:
-                    u0, _, a0 = init_BSSMF_md_p(init_option, Xb, Db, Rb, n_u, purity, seed=s)
-                else:
-                    u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
-            else:                        # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
-                u0, a0 = _shape_only_init(s, init_option, M, prob.K, N, n_u, with_zero_guard=purity is None)
-            idx_np[k], u0_np[k], A0[k] = idx, np.asarray(u0).reshape(M, n_u), a0
-        if data_dependent_init:
-            for k in range(Bw):
-                prepare(k)
-        else:                            # numpy's legacy generators release the GIL: draw the resamples of the wave in parallel
-            from concurrent.futures import ThreadPoolExecutor
-            import os
-            with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-                list(ex.map(prepare, range(Bw)))
-        # batched device ops: order the resampled positions of every fit by source row (stable sort); u is position-indexed, so it is
-        # permuted along; multiplicities and CSR offsets per source row
-        idx_d = torch.from_numpy(idx_np).to(dev)                                                    # (Bw, M) int64
-        u0_d = torch.from_numpy(u0_np).to(dev)                                                      # (Bw, M, n_u)
+            def prepare(k):
+                s_rows, s = chunk[k]
+                idx = resample_indices(s_rows, M)
+                if data_dependent_init:      # `uniform` / SVD look at the resampled data and use the global stream: sequential
+                    Xb, Db, Rb = meth_f[idx], np.asarray(counts)[idx], np.asarray(ref)[idx]
+                    if purity is not None:
+                        u0, _, a0 = init_BSSMF_md_p(init_option, Xb, Db, Rb, n_u, purity, seed=s)
+                    else:
+                        u0, _, a0 = init_BSSMF_md(init_option, Xb, Db, Rb, n_u, seed=s)
+                else:                        # uniform_ / beta draws depend on shapes only (deconvolution.py:54-61)
+                    u0, a0 = _shape_only_init(s, init_option, M, prob.K, N, n_u, with_zero_guard=purity is None)
+                idx_np[k], u0_np[k], A0[k] = idx, np.asarray(u0).reshape(M, n_u), a0
+            if data_dependent_init:
+                for k in range(Bw):
+                    prepare(k)
+            else:                            # numpy's legacy generators release the GIL: draw the resamples of the wave in parallel
+                from concurrent.futures import ThreadPoolExecutor
+                import os
+                with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+                    list(ex.map(prepare, range(Bw)))
+            # batched device ops: order the resampled positions of every fit by source row (stable sort); u is position-indexed, so it is
+            # permuted along; multiplicities and CSR offsets per source row
+            idx_d = torch.from_numpy(idx_np).to(dev)                                                    # (Bw, M) int64
+            u0_d = torch.from_numpy(u0_np).to(dev)                                                      # (Bw, M, n_u)
         if use_fused:
             probs = [prob.gathered(idx_d[k]) for k in range(Bw)]                                    # this wave's resampled matrices
             del idx_d
@@ -252,7 +295,7 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
             batch.close()
             del batch, probs, U_d, A_d
             continue
-        order_d, rows_d, cnt, offs_d = resample_layout(idx_d, M, with_csr=use_mult)
+        order_d, rows_d, cnt, offs_d = resample_layout(idx_d.long(), M, with_csr=use_mult)
         U0 = torch.gather(u0_d, 1, order_d.unsqueeze(-1).expand(-1, -1, n_u))
         del u0_d
         batch = None

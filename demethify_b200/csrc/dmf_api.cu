@@ -11,6 +11,7 @@
 #include "dmf_inst.h"
 #include "dmf_gram.cuh"
 #include "dmf_fused.cuh"
+#include "dmf_rng.cuh"
 
 using namespace dmf;
 
@@ -1308,6 +1309,18 @@ int dmf_percentile_bounds(const double* stack, int32_t B, int64_t P, double q_lo
     if (keep <= 32) percentile_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(stack, B, P, q_lo, q_hi, out_lo, out_hi);
     else if (keep <= 128) percentile_kernel<128><<<blocks, 128, 0, (cudaStream_t)stream>>>(stack, B, P, q_lo, q_hi, out_lo, out_hi);
     else return fail(DMF_E_SHAPE, "percentile: more than 128 order statistics per tail would have to be kept (dmf_percentile_max_keep)");
+    CUDA_TRY(cudaGetLastError());
+    return DMF_OK;
+}
+
+int dmf_rng_legacy_streams(const uint32_t* seeds, int32_t n_streams, int64_t M, int32_t* idx, int64_t ld_idx, int64_t n_dbl, double* u,
+                           int64_t ld_u, uint32_t* state, void* stream) {
+    if (!seeds || n_streams < 0 || M < 0 || n_dbl < 0) return fail(DMF_E_ARG, "rng: bad argument");
+    if (M > 0x7fffffffll) return fail(DMF_E_ARG, "rng: row indices are int32 (M < 2^31)");
+    if ((idx && ld_idx < M) || (u && ld_u < n_dbl)) return fail(DMF_E_ARG, "rng: output pitch smaller than the row");
+    if (n_streams == 0 || (!idx && !u && !state)) return DMF_OK;
+    legacy_streams_kernel<<<dim3((n_streams + kRngWarps - 1) / kRngWarps, 2, 1), kRngWarps * 32, 0, (cudaStream_t)stream>>>(
+        seeds, n_streams, (long long)M, idx, (long long)ld_idx, (long long)n_dbl, u, (long long)ld_u, state);
     CUDA_TRY(cudaGetLastError());
     return DMF_OK;
 }

@@ -257,6 +257,15 @@ int dmf_nndsvd_split(const double* U, int64_t ldu, const double* S, const double
  * at most dmf_percentile_max_keep() (DMF_E_SHAPE otherwise). */
 int dmf_percentile_max_keep(void);
 int dmf_percentile_bounds(const double* stack, int32_t B, int64_t P, double q_lo, double q_hi, double* out_lo, double* out_hi, void* stream);
+/* The legacy numpy streams a bootstrap resample draws, bit for bit, one warp per stream.  For stream b, with
+ * seed = seeds[b] (DEVICE array of n_streams uint32):
+ *   idx   != NULL:  idx[b * ld_idx + i]  = RandomState(seed).randint(0, M, size=M)[i]      (sklearn.utils.resample, bootstrap.py:28)
+ *   u     != NULL:  u[b * ld_u + i]      = RandomState(seed).uniform(size=n_dbl)[i]        (set_seed + rd.uniform, deconvolution.py:9-11, :54-55)
+ *   state != NULL:  state[b * 625 ..]    = the 624 key words and pos of that generator AFTER the n_dbl doubles, so that the host can
+ *                                          continue the stream (RandomState.set_state) with the small draws that follow (dirichlet).
+ * MT19937 as numpy seeds and steps it; randint = masked rejection on 32-bit outputs; uniform = ((a >> 5) 2^26 + (b >> 6)) / 2^53. */
+int dmf_rng_legacy_streams(const uint32_t* seeds, int32_t n_streams, int64_t M, int32_t* idx, int64_t ld_idx, int64_t n_dbl, double* u,
+                           int64_t ld_u, uint32_t* state, void* stream);
 /* compute_consensus_matrix (ic.py:24-37): alpha_runs is n_runs x Kt x N, labels_ws n_runs x N int32 scratch, consensus N x N. */
 int dmf_consensus(const double* alpha_runs, int32_t n_runs, int32_t Kt, int32_t N, int32_t* labels_ws, double* consensus, void* stream);
 
