@@ -262,7 +262,6 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
                     prepare(k)
             else:                            # numpy's legacy generators release the GIL: draw the resamples of the wave in parallel
                 from concurrent.futures import ThreadPoolExecutor
-                import os
                 with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
                     list(ex.map(prepare, range(Bw)))
             # batched device ops: order the resampled positions of every fit by source row (stable sort); u is position-indexed, so it is

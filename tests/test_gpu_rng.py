@@ -58,7 +58,9 @@ def test_sklearn_resample_indices():
 
 
 def test_bootstrap_device_draws_equal_host_draws(monkeypatch):
-    """bootstrap_fits with the device streams returns exactly what it returns with numpy's host streams."""
+    """bootstrap_fits with the device streams returns what it returns with numpy's host streams (the draws themselves are compared bit
+    for bit above; two runs of the same batch differ by a few ulp because the resampled matrices of a wave land at different
+    addresses, so the fits are compared at 1e-12 with identical outer-iteration counts)."""
     from demethify_b200 import bootstrap as bt
     rs = np.random.RandomState(5)
     M, N, K, n_u = 6000, 12, 5, 1
@@ -73,4 +75,4 @@ def test_bootstrap_device_draws_equal_host_draws(monkeypatch):
         a, u, n = bt.bootstrap_fits(5, n_u, X, D, Rk, "uniform_", 8, 20, 1e-2, None, 3)
         out[mode] = (np.asarray(a), np.asarray(u), n)
     assert out["0"][2] == out["1"][2]
-    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    assert np.abs(out["0"][0] - out["1"][0]).max() <= 1e-12 and np.abs(out["0"][1] - out["1"][1]).max() <= 1e-12
