@@ -1061,6 +1061,10 @@ __global__ void __launch_bounds__(kThreads, (PA * (PB + 1) * C <= 40) ? 2 : 1) g
         } else {
             const int ib = alpha_row_of(g, 2 * a.cb0 + q);
             if (ib < 0) continue;
+            // a diagonal launch holds (ia, ib) twice, as (p, q) and as (q', p'), computed as (d z_a) z_b and (d z_b) z_a: the two
+            // roundings differ and both would be stored to the same two entries by different threads - keep the (ia <= ib) one
+            const int ra = 2 * a.ca0 + p, rb = 2 * a.cb0 + q;
+            if (ra > rb && rb >= 2 * a.ca0 && rb < 2 * a.ca0 + PA && ra >= 2 * a.cb0 && ra < 2 * a.cb0 + PB) continue;
             f.gram[((size_t)ia * g.Kt + ib) * g.N + j] = v;
             f.gram[((size_t)ib * g.Kt + ia) * g.N + j] = v;
         }
