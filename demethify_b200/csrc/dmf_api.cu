@@ -337,23 +337,25 @@ int make_plan(const dmf_handle_s* h, const dmf_shape_t& s, Plan& p) {
         const int ng = ng_of_h(p.nub_f), ncol = p.nub_f * p.kb_f + (ng - p.nub_f), nblk = (ncol + 7) / 8;
         auto a128f = [](size_t v) { return (unsigned)align_up(v, 128); };
         // a tile is ONE bulk copy per matrix: it keeps the caller's row pitch in shared memory (dmf_shape_t recommends pitches that
-        // are free of bank conflicts); 16 zero bytes behind the X rows of every stage serve the panel columns that do not exist
+        // are free of bank conflicts); 16 zero bytes behind the X rows of every stage serve the panel columns that do not exist.
+        // Rows per tile, ring depth and statistics buffers depend on the width class (FusedCfg in dmf_fused.cuh).
+        const int f_rows = fused_cfg_rows(p.s_f), f_stages = fused_cfg_stages(p.s_f);
         p.f_pitchX = (unsigned)px;
         p.f_pitchD = (unsigned)pd;
-        p.f_zero_off = (unsigned)((size_t)kFusedRows * px);
-        p.f_offD = a128f((size_t)kFusedRows * p.f_pitchX + 16);
-        p.f_offR = a128f(p.f_offD + (size_t)kFusedRows * p.f_pitchD);
-        p.f_offU = a128f(p.f_offR + (size_t)kFusedRows * pr);
-        p.f_offUp = a128f(p.f_offU + (size_t)kFusedRows * pu);
-        p.f_stage_bytes = a128f(p.f_offUp + (size_t)kFusedRows * pu);
-        p.f_offStats = kFusedCtlBytes + kFusedStages * p.f_stage_bytes;
-        // double-buffered row statistics (4 sample-group partials per row), then the per-sample table of the A-warps
-        p.f_offTab = a128f(p.f_offStats + 2u * kFusedSGroups * kFusedRows * ng * 8u);
+        p.f_zero_off = (unsigned)((size_t)f_rows * px);
+        p.f_offD = a128f((size_t)f_rows * p.f_pitchX + 16);
+        p.f_offR = a128f(p.f_offD + (size_t)f_rows * p.f_pitchD);
+        p.f_offU = a128f(p.f_offR + (size_t)f_rows * pr);
+        p.f_offUp = a128f(p.f_offU + (size_t)f_rows * pu);
+        p.f_stage_bytes = a128f(p.f_offUp + (size_t)f_rows * pu);
+        p.f_offStats = kFusedCtlBytes + f_stages * p.f_stage_bytes;
+        // row statistics (one partial per A-warp sample group and row; fused_cfg_nstat buffers), then the per-sample table of the A-warps
+        p.f_offTab = a128f(p.f_offStats + (unsigned)fused_cfg_nstat(p.s_f) * fused_cfg_sgroups(p.s_f) * f_rows * ng * 8u);
         p.smem_f = p.f_offTab + 32u * p.s_f * 2u * p.nub_f * 8u;
         (void)nblk;
         const size_t n_rec = 2 + (size_t)(ncol + p.nub_f) * s.N;
         if (p.smem_f <= smem_cap && kFusedCtlBytes + n_rec * 8 <= p.f_offStats) {
-            p.n_tiles_f = (int)((s.M + kFusedRows - 1) / kFusedRows);
+            p.n_tiles_f = (int)((s.M + f_rows - 1) / f_rows);
             long long per_fit_f = std::max<long long>(kMinParts, (long long)h->sm_count / s.n_fits);
             if (s.max_ctas_per_fit > 0) per_fit_f = std::min<long long>(per_fit_f, s.max_ctas_per_fit);
             p.n_parts_f = (int)std::min<long long>(per_fit_f, p.n_tiles_f);
@@ -774,7 +776,7 @@ int dmf_batch_geometry(dmf_batch_t b, int32_t* ctas_per_fit, int32_t* tile_rows,
     if (!b) return fail(DMF_E_ARG, "NULL batch");
     if (b->engine == DMF_ENGINE_FUSED) {
         if (ctas_per_fit) *ctas_per_fit = b->fa.g.n_parts;
-        if (tile_rows) *tile_rows = kFusedRows;
+        if (tile_rows) *tile_rows = fused_cfg_rows(b->s_f);
         if (smem_bytes) *smem_bytes = (int32_t)b->smem_f;
         return DMF_OK;
     }
@@ -1003,7 +1005,7 @@ int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
     a.flags = b->sharded ? kFlagPartial : 0;      // row-sharded: publish this GPU's sums, dmf_fused_alpha_commit decides on the reduced ones
     a.tol = tol;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
-    k<<<dim3(a.g.n_parts, b->n_active, 1), kFusedThreads, b->smem_f, (cudaStream_t)stream>>>(a);
+    k<<<dim3(a.g.n_parts, b->n_active, 1), fused_cfg_threads(b->s_f), b->smem_f, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     b->launches++;
     b->fused_pending = 1;

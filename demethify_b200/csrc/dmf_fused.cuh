@@ -33,24 +33,60 @@ namespace dmf {
 #ifndef DMF_FU
 #define DMF_FU 3
 #endif
-constexpr int kFA = 8, kFC = 8, kFU = DMF_FU, kFP = 1;
-// Registers per thread after the role split (setmaxnreg; the kernel is launched with 96): 256 (RA + RC) + 128 x 64 <= 640 x 96
+#ifndef DMF_FU_NARROW
+#define DMF_FU_NARROW 3
+#endif
+#ifndef DMF_STAGES
+#define DMF_STAGES 5
+#endif
+constexpr int kFA = 8, kFC = 8, kFP = 1;
+// Registers per thread after the role split (setmaxnreg).  The pool is what the CTA got at launch (threads x the register count ptxas
+// derives from __launch_bounds__): 20 warps -> 96 per thread, 24 warps -> 80 per thread.  With 3 U-warps: A 96, C 112, U / producer 64
+// (256 (96 + 112) + 128 x 64 = 640 x 96); with 7 U-warps: A 88, C 96, U / producer 56 (256 (88 + 96) + 256 x 56 = 768 x 80).
+// setmaxnreg is a warpgroup instruction: the warp count must stay a multiple of 4 (FU = 3 or 7) so that every group is one role set.
 #ifndef DMF_RA
 #define DMF_RA 96
 #endif
 #ifndef DMF_RC
 #define DMF_RC 112
 #endif
-static_assert(DMF_RA % 8 == 0 && DMF_RC % 8 == 0 && 256 * (DMF_RA + DMF_RC) + 32 * (DMF_FU + 1) * 64 <= 32 * (17 + DMF_FU) * 96, "register split of the fused pass");
-constexpr int kFusedThreads = (kFA + kFC + kFU + kFP) * 32;
-constexpr int kFusedRows = 16;           // rows per tile (two 8-row MMA blocks, four 4-row k-steps)
-#ifndef DMF_STAGES
-#define DMF_STAGES 5
-#endif
-constexpr int kFusedStages = DMF_STAGES;
-constexpr int kFusedMaxInner = 64;       // beyond this the U-warps (16 rows at a time) would bound the pass: Gram engine instead
+constexpr int kFusedMaxU = DMF_FU > DMF_FU_NARROW ? DMF_FU : DMF_FU_NARROW;
+constexpr int fused_launch_regs(int threads) { return (65536 / ((threads + 127) / 128 * 128)) / 8 * 8; }
+template <int FROM, int TO>
+__device__ __forceinline__ void fused_set_regs() {
+    if constexpr (TO > FROM) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TO));
+    else if constexpr (TO < FROM) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TO));
+}
+// Tile geometry by the width class S (N <= 64 S samples).  The 20 dependent update_u iterations of a tile take the same time
+// whatever N is, while the A / C work of a row shrinks with N: narrow problems get 32-row tiles (a U-warp pass uses all 32 lanes
+// when there is one unknown type, two U-warps share a tile when there are two), one more U-warp and - their stages being small -
+// a deeper ring, so that enough tiles are in flight to cover the U latency.
+//   S = 4: 16-row tiles, A-warps = 2 row blocks x 4 sample groups (8 blocks of 8 samples each), C-warps = 8 sample groups x 4 k-steps
+//   S = 2: 32-row tiles, A-warps = 4 row blocks x 2 sample groups (8 blocks),                   C-warps = 4 sample groups x 2 row splits x 4 k-steps
+//   S = 1: 32-row tiles, A-warps = 4 row blocks x 2 sample groups (4 blocks),                   C-warps = 2 sample groups x 4 row splits x 2 k-steps
+template <int S>
+struct FusedCfg {
+    static constexpr int TR = S == 4 ? 16 : 32;                        // rows per tile
+    static constexpr int FU = S == 4 ? DMF_FU : DMF_FU_NARROW;         // U-warps
+    static constexpr int NS = S == 4 ? DMF_STAGES : (S == 2 ? 4 : 8);  // ring stages
+    static constexpr int RB = TR / 8, SG = 8 / RB, NSB = 8 * S / SG;   // A-warps: row blocks x sample groups, 8-sample blocks per warp
+    static constexpr int CSG = 2 * S, RSP = 8 / CSG, KSW = (TR / 4) / RSP;   // C-warps: 32-sample groups x row splits, k-steps (4 rows) per warp
+    static constexpr int WARPS = kFA + kFC + FU + kFP, THREADS = WARPS * 32;
+    static constexpr int LR = fused_launch_regs(THREADS);              // registers per thread at launch
+    static constexpr int RA = FU >= 5 ? 88 : DMF_RA, RC = FU >= 5 ? 96 : DMF_RC, RU = FU >= 5 ? 56 : 64;
+    static_assert(WARPS % 4 == 0 && RA % 8 == 0 && RC % 8 == 0 && 256 * (RA + RC) + 32 * (FU + 1) * RU <= THREADS * LR, "register split of the fused pass");
+    // row-statistics buffers: S = 4 double-buffers them (released through `sfree` as soon as the U-warp holds the partials in
+    // registers: shared memory is full there); the narrow classes keep one per stage (released with the stage)
+    static constexpr int NSTAT = S == 4 ? 2 : NS;
+    __host__ __device__ static constexpr int u_passes(int nub) { return nub == 2 ? TR / 16 : 1; }   // U work units per tile (16 rows x 2 components, or all rows)
+};
+constexpr int fused_cfg_rows(int s) { return s == 4 ? FusedCfg<4>::TR : FusedCfg<1>::TR; }
+constexpr int fused_cfg_stages(int s) { return s == 4 ? FusedCfg<4>::NS : (s == 2 ? FusedCfg<2>::NS : FusedCfg<1>::NS); }
+constexpr int fused_cfg_threads(int s) { return s == 4 ? FusedCfg<4>::THREADS : FusedCfg<1>::THREADS; }
+constexpr int fused_cfg_sgroups(int s) { return s == 4 ? FusedCfg<4>::SG : FusedCfg<1>::SG; }
+constexpr int fused_cfg_nstat(int s) { return s == 4 ? FusedCfg<4>::NSTAT : (s == 2 ? FusedCfg<2>::NSTAT : FusedCfg<1>::NSTAT); }
+constexpr int kFusedMaxInner = 64;       // beyond this the U-warps would bound the pass: Gram engine instead
 constexpr unsigned kFusedCtlBytes = 2048;
-constexpr int kFusedSGroups = 4;         // A-warps: 2 row blocks x 4 sample groups; a row has 4 partial statistics records
 
 struct FusedArgs {
     Geom g;                  // problem sizes, pitches, n_parts / n_groups / part_stride of this launch
@@ -69,7 +105,7 @@ typedef void (*fused_kern_t)(const FusedArgs);
 
 struct FusedCtl {
     unsigned long long full[8], empty[8], stats[8], udone[8], sfree[2];
-    double wsum[2][kFA + kFC + kFU + kFP];
+    double wsum[2][kFA + kFC + kFusedMaxU + kFP];
     double beta[2 * kFusedMaxInner];      // (1 + beta_t, -beta_t) of this launch's update_u iterations (the same for every row)
     int flag, commit;
 };
@@ -315,17 +351,21 @@ __device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb
 }
 
 template <typename WT, int KB, int NUB, int S>
-__global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(FusedCfg<S>::THREADS, 1) fused_outer_kernel(const FusedArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    using Cfg = FusedCfg<S>;
     constexpr int KS = (KB + 3) / 4;                  // k-steps of the c = x - R_trunc a_k MMA
     constexpr int NG = ng_of(NUB);
     constexpr int NTRI = NG - NUB;
     constexpr int NCOL = NUB * KB + NTRI;             // panel columns: u_q R_k (q major), then the upper triangle of u u^T
     constexpr int WB = (KB + NUB + 7) / 8;            // blocks of 8 columns of W = [R_trunc | u]; the panel MMA runs u_q (x) W per q
     constexpr int NBLK = NUB * WB;
-    constexpr int NS = kFusedStages, TR = kFusedRows;
-    constexpr int NSB = 2 * S;                        // A-warp: 8 rows x NSB blocks of 8 samples (4 sample groups x 2 row blocks)
-    constexpr int RSP = 4 / S;                        // C-warp: 32 samples x S k-steps (2 S sample groups x RSP row splits)
+    constexpr int NS = Cfg::NS, TR = Cfg::TR, FU = Cfg::FU, THREADS = Cfg::THREADS;
+    constexpr int NSB = Cfg::NSB;                     // A-warp: 8 rows x NSB blocks of 8 samples
+    constexpr int SG = Cfg::SG;                       // partial statistics records per row (one per A-warp sample group)
+    constexpr int RSP = Cfg::RSP, KSW = Cfg::KSW;     // C-warp: 32 samples x KSW k-steps (CSG sample groups x RSP row splits)
+    constexpr int UP = Cfg::u_passes(NUB);            // U work units per tile
+    constexpr unsigned STATB = (unsigned)(SG * TR * NG) * 8u;   // bytes of one row-statistics buffer
     constexpr unsigned PAIRB = 2u * NUB * 8u;         // bytes of one pair record of the per-sample table
     const Geom& g = a.g;
     const FitDev f = a.fits[fit_id(g)];
@@ -333,13 +373,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     if (st->done) return;
     FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem);
     const int tid = threadIdx.x, lane = tid & 31;
-#ifdef DMF_ROLE_SPLIT
-    // experiment: A-warps on SM sub-partitions 0 and 1, C-warps on 2 and 3 (hardware warp w runs on sub-partition w % 4)
-    const int hw = tid >> 5;
-    const int warp = hw >= kFA + kFC ? hw : ((hw & 3) < 2 ? 2 * (hw >> 2) + (hw & 1) : kFA + 2 * (hw >> 2) + (hw & 1));
-#else
     const int warp = tid >> 5;
-#endif
     const int gi = lane >> 2, ti = lane & 3;
     const uint32_t smem32 = smem_u32(smem);
     const uint32_t stages32 = smem32 + kFusedCtlBytes;
@@ -355,7 +389,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             mbar_init(smem_u32(&ctl->full[s]), 1);
             mbar_init(smem_u32(&ctl->empty[s]), kFC);
             mbar_init(smem_u32(&ctl->stats[s]), kFA * 8);      // the 8 writer lanes of every A-warp
-            mbar_init(smem_u32(&ctl->udone[s]), 1);
+            mbar_init(smem_u32(&ctl->udone[s]), UP);
         }
         mbar_init(smem_u32(&ctl->sfree[0]), 1);
         mbar_init(smem_u32(&ctl->sfree[1]), 1);
@@ -365,11 +399,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     // which only works on finite values
     {
         const unsigned n16 = (a.offStats - kFusedCtlBytes) / 16;
-        for (unsigned i = tid; i < n16; i += kFusedThreads)
+        for (unsigned i = tid; i < n16; i += THREADS)
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(stages32 + i * 16u), "r"(0u) : "memory");
     }
     // per-sample table of the A-warps, one record per pair of samples: [a_u(j) | a_u(j + 1)], zero beyond N
-    for (int p = tid; p < 32 * S; p += kFusedThreads) {
+    for (int p = tid; p < 32 * S; p += THREADS) {
         double* rec = reinterpret_cast<double*>(smem + a.offTab + (size_t)p * PAIRB);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -398,12 +432,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     // C-warp state (declared here because it is stored after the CTA-wide barrier that follows the role loops)
     double pacc[4][NBLK][2], paccx[4][NUB];
     bool validC[4];
-    const int cwC = warp - kFA, grpC = cwC / RSP, rqC = cwC - grpC * RSP;
+    const int cwC = warp - kFA, grpC = cwC / RSP, rqC = cwC - grpC * RSP;      // 32-sample group, row split
     const int jbC = 32 * grpC;          // lane's samples: jbC + 16 h + 2 gi + e  <->  MMA block mb = 2 h + e, fragment row gi
 
-    if (warp >= kFA + kFC + kFU) {
+    if (warp >= kFA + kFC + FU) {
         // =========================================================================== producer warp: the TMA ring
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        fused_set_regs<Cfg::LR, Cfg::RU>();
         const char* Ucur_g = f.U + (size_t)ucur * g.uslot_bytes;
         const char* Uprv_g = f.U + (size_t)(ucur ^ 1) * g.uslot_bytes;
         const unsigned rbytes = (unsigned)(g.ldr * 8), ubytes = (unsigned)(g.ldu * 8);
@@ -432,7 +466,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         }
     } else if (warp >= kFA + kFC) {
         // =========================================================================== U-warps: update_u on the row statistics
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        fused_set_regs<Cfg::LR, Cfg::RU>();
         const int uw = warp - (kFA + kFC);
         double* Unew_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 2) * g.uslot_bytes);
         double* Unpv_g = reinterpret_cast<double*>(f.U + (size_t)(ucur ^ 3) * g.uslot_bytes);
@@ -442,33 +476,40 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         const bool at_current = (g.mode == 2);
         const unsigned upitch = (unsigned)(g.ldu * 8);
         const uint32_t beta32 = smem_u32(&ctl->beta[0]);
-        int s = uw % NS;
-        unsigned ph = (unsigned)(uw / NS) & 1u;
-        for (int it = uw; it < n_my; it += kFU) {
+        // work unit n = (tile n / UP, pass n % UP) goes to U-warp n mod FU: with two unknown types a 32-row tile is two passes of
+        // 16 rows x 2 components that two U-warps run side by side (the tile's U latency stays that of one pass)
+        for (int n = uw; n < n_my * UP; n += FU) {
+            const int it = n / UP, pass = n - it * UP;
+            const int s = it % NS;
+            const unsigned ph = (unsigned)(it / NS) & 1u;
+            // row-statistics buffer of the tile: S = 4 double-buffers (released through sfree), the narrow classes keep one per stage
+            const uint32_t stat32 = smem32 + a.offStats + (uint32_t)(Cfg::NSTAT == 2 ? (it & 1) : s) * STATB;
             mbar_wait(smem_u32(&ctl->stats[s]), ph);
             mbar_wait(smem_u32(&ctl->full[s]), ph);        // complete long ago; orders this warp after the bulk copies
             const int nrows = tile_rows(it);
             const long long r0 = ((long long)part + (long long)it * g.n_parts) * TR;
             const uint32_t sb = stages32 + (uint32_t)s * a.stage_bytes;
             if constexpr (NUB == 2) {
-                // lane = (row, component): rows 0..15 in both half warps, component q = lane / 16
-                const int row = lane & 15, q = lane >> 4;
+                // lane = (row, component): 16 rows of the tile in both half warps, component q = lane / 16
+                const int row = 16 * pass + (lane & 15), q = lane >> 4;
                 const bool live = row < nrows;
                 double v[NG];
 #pragma unroll
                 for (int i = 0; i < NG; ++i) v[i] = 0.0;
                 {
-                    const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u) + (uint32_t)row * (NG * 8u);
+                    const uint32_t sbase = stat32 + (uint32_t)row * (NG * 8u);
 #pragma unroll
-                    for (int w = 0; w < kFusedSGroups; ++w)
+                    for (int w = 0; w < SG; ++w)
 #pragma unroll
                         for (int i = 0; i < NG; ++i) {
                             double t;
                             lds1(sbase + (uint32_t)w * (TR * NG * 8u) + (uint32_t)i * 8u, t);
                             v[i] += t;
                         }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&ctl->sfree[it & 1]));
+                    if constexpr (Cfg::NSTAT == 2) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctl->sfree[it & 1]));
+                    }
                 }
                 double cu, pv, cuo;
                 lds1(sb + a.offU + (uint32_t)row * upitch + (uint32_t)q * 8u, cu);
@@ -510,17 +551,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
 #pragma unroll
             for (int i = 0; i < NG; ++i) v[i] = 0.0;
             {
-                const uint32_t sbase = smem32 + a.offStats + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u) + (uint32_t)row * (NG * 8u);
+                const uint32_t sbase = stat32 + (uint32_t)row * (NG * 8u);
 #pragma unroll
-                for (int w = 0; w < kFusedSGroups; ++w)
+                for (int w = 0; w < SG; ++w)
 #pragma unroll
                     for (int i = 0; i < NG; ++i) {
                         double t;
                         lds1(sbase + (uint32_t)w * (TR * NG * 8u) + (uint32_t)i * 8u, t);
                         v[i] += t;
                     }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&ctl->sfree[it & 1]));
+                if constexpr (Cfg::NSTAT == 2) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->sfree[it & 1]));
+                }
             }
             double u[NUB], up[NUB];
 #pragma unroll
@@ -564,18 +607,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->udone[s]));
-            s += kFU % NS;
-            if (kFU >= NS) ph ^= (unsigned)(kFU / NS) & 1u;
-            if (s >= NS) { s -= NS; ph ^= 1u; }
         }
     } else if (warp < kFA) {
         // =========================================================================== A-warps: row statistics
-#if DMF_RA > 96
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DMF_RA));
-#elif DMF_RA < 96
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DMF_RA));
-#endif
-        const int arb = warp & 1, asg = warp >> 1;                  // row block of the tile, sample group
+        fused_set_regs<Cfg::LR, Cfg::RA>();
+        const int arb = warp % Cfg::RB, asg = warp / Cfg::RB;       // row block of the tile, sample group
         const int rowA = 8 * arb + (gi >> 1) + 4 * (gi & 1);        // fragment row gi <-> tile row: lanes of a quarter warp read rows 4 apart
         const int blk0 = asg * NSB;                                 // the warp's first block of 8 samples
         const int nblk = min(NSB, max(0, (N + 7) / 8 - blk0));      // blocks that exist
@@ -624,9 +660,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
                 acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
                 acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
             }
-            if (it >= 2) mbar_wait(smem_u32(&ctl->sfree[it & 1]), ((unsigned)((it >> 1) - 1)) & 1u);     // tile it - 2's partials were read
+            if constexpr (Cfg::NSTAT == 2) {
+                if (it >= 2) mbar_wait(smem_u32(&ctl->sfree[it & 1]), ((unsigned)((it >> 1) - 1)) & 1u);     // tile it - 2's partials were read
+            }
             {   // the 8 lanes with ti == 0 store their row's record and arrive themselves (no warp-wide reconvergence)
-                const uint32_t sbase = smem32 + srel + (uint32_t)(it & 1) * (kFusedSGroups * TR * NG * 8u);
+                const uint32_t sbase = smem32 + srel + (uint32_t)(Cfg::NSTAT == 2 ? (it & 1) : s) * STATB;
 #pragma unroll
                 for (int i = 0; i < NG; ++i)
                     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f64 [%0], %1;\n}" ::"r"(sbase + (uint32_t)i * 8u), "d"(acc[i]), "r"((unsigned)writer) : "memory");
@@ -637,11 +675,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
         }
     } else {
         // =========================================================================== C-warps: Gram panel with the new u
-#if DMF_RC > 96
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DMF_RC));
-#elif DMF_RC < 96
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DMF_RC));
-#endif
+        fused_set_regs<Cfg::LR, Cfg::RC>();
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb) {
             validC[mb] = jbC + 16 * (mb >> 1) + 2 * gi + (mb & 1) < N;
@@ -661,10 +695,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             w_off[wb] = !exists ? a.zero_off : (isr ? a.offR + (unsigned)w * 8u : a.offU + (unsigned)(w - KB) * 8u);
             w_pitch[wb] = !exists ? 0u : (isr ? rpitch : upitch);
         }
-        const bool work = jbC < N;                     // (N <= 32 S - 32: this sample group is empty, the warp only keeps the ring moving)
+        const bool work = jbC < N;                     // (else this sample group is empty, the warp only keeps the ring moving)
         const bool cols_full = jbC + 32 <= N;
         const uint32_t xoff = (uint32_t)(jbC + 2 * gi) * 8u, doff = (uint32_t)(jbC + 2 * gi) * (unsigned)sizeof(WT);
-        const int ks0 = rqC * S;
+        const int ks0 = rqC * KSW;
         int s = 0;
         unsigned ph = 0;
         uint32_t sb32 = stages32;
@@ -674,8 +708,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
             const int nrows = tile_rows(it);
 #ifndef DMF_SKIP_C
             if (work) {
-                if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, S, WB>(a, sb32, nrows, ti, ks0, xoff, doff, w_off, w_pitch, validC, pacc, paccx);
-                else fused_panel_tile<true, WT, NUB, S, WB>(a, sb32, nrows, ti, ks0, xoff, doff, w_off, w_pitch, validC, pacc, paccx);
+                if (cols_full && nrows == TR) fused_panel_tile<false, WT, NUB, KSW, WB>(a, sb32, nrows, ti, ks0, xoff, doff, w_off, w_pitch, validC, pacc, paccx);
+                else fused_panel_tile<true, WT, NUB, KSW, WB>(a, sb32, nrows, ti, ks0, xoff, doff, w_off, w_pitch, validC, pacc, paccx);
             }
 #endif
             __syncwarp();
@@ -738,7 +772,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     double* rec = reinterpret_cast<double*>(smem + kFusedCtlBytes);
     if (tid == 0) {
         double c = 0.0, q = 0.0;
-        for (int w = 0; w < kFA + kFC + kFU + kFP; ++w) { c += ctl->wsum[0][w]; q += ctl->wsum[1][w]; }
+        for (int w = 0; w < Cfg::WARPS; ++w) { c += ctl->wsum[0][w]; q += ctl->wsum[1][w]; }
         rec[0] = c;
         rec[1] = q;
     }
@@ -746,7 +780,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     const int n = 2 + (NCOL + NUB) * N;
     {
         double* p = f.part + (size_t)part * g.part_stride;
-        for (int e = tid; e < n; e += kFusedThreads) p[e] = rec[e];
+        for (int e = tid; e < n; e += THREADS) p[e] = rec[e];
     }
     if (!hier_reduce(g, f, f.red, n, &ctl->flag)) return;
     __threadfence();
@@ -787,7 +821,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_outer_kernel(const Fus
     }
     __syncthreads();
     if (!ctl->commit) return;
-    for (int e = tid; e < (NCOL + NUB) * N; e += kFusedThreads) {
+    for (int e = tid; e < (NCOL + NUB) * N; e += THREADS) {
         const int c = e / N, j = e - c * N;
         const double v = f.red[2 + e];
         if (c >= NCOL) {
