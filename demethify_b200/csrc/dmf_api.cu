@@ -1005,7 +1005,7 @@ int dmf_fused_pass(dmf_batch_t b, int32_t n_iter2, double tol, void* stream) {
     a.flags = b->sharded ? kFlagPartial : 0;      // row-sharded: publish this GPU's sums, dmf_fused_alpha_commit decides on the reduced ones
     a.tol = tol;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
-    k<<<dim3(a.g.n_parts, b->n_active, 1), fused_cfg_threads(b->s_f), b->smem_f, (cudaStream_t)stream>>>(a);
+    k<<<dim3(a.g.n_parts, b->n_active, 1), fused_cfg_threads(b->s_f, b->nub_f), b->smem_f, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     b->launches++;
     b->fused_pending = 1;

@@ -36,6 +36,9 @@ namespace dmf {
 #ifndef DMF_FU_NARROW
 #define DMF_FU_NARROW 3
 #endif
+#ifndef DMF_FU_NARROW2
+#define DMF_FU_NARROW2 7
+#endif
 #ifndef DMF_STAGES
 #define DMF_STAGES 5
 #endif
@@ -50,7 +53,7 @@ constexpr int kFA = 8, kFC = 8, kFP = 1;
 #ifndef DMF_RC
 #define DMF_RC 112
 #endif
-constexpr int kFusedMaxU = DMF_FU > DMF_FU_NARROW ? DMF_FU : DMF_FU_NARROW;
+constexpr int kFusedMaxU = 7;
 constexpr int fused_launch_regs(int threads) { return (65536 / ((threads + 127) / 128 * 128)) / 8 * 8; }
 template <int FROM, int TO>
 __device__ __forceinline__ void fused_set_regs() {
@@ -64,27 +67,31 @@ __device__ __forceinline__ void fused_set_regs() {
 //   S = 4: 16-row tiles, A-warps = 2 row blocks x 4 sample groups (8 blocks of 8 samples each), C-warps = 8 sample groups x 4 k-steps
 //   S = 2: 32-row tiles, A-warps = 4 row blocks x 2 sample groups (8 blocks),                   C-warps = 4 sample groups x 2 row splits x 4 k-steps
 //   S = 1: 32-row tiles, A-warps = 4 row blocks x 2 sample groups (4 blocks),                   C-warps = 2 sample groups x 4 row splits x 2 k-steps
-template <int S>
+template <int S, int NUB>
 struct FusedCfg {
     static constexpr int TR = S == 4 ? 16 : 32;                        // rows per tile
-    static constexpr int FU = S == 4 ? DMF_FU : DMF_FU_NARROW;         // U-warps
+    // U-warps: a pass of two unknown types covers 16 rows only, so narrow problems with n_u = 2 get 7 U-warps (measured: 500k x 64,
+    // n_u = 2: 0.201 -> 0.171 ms; 500k x 128: 0.265 -> 0.246 ms; no gain for one unknown type)
+    static constexpr int FU = S == 4 ? DMF_FU : (NUB == 2 ? DMF_FU_NARROW2 : DMF_FU_NARROW);
     static constexpr int NS = S == 4 ? DMF_STAGES : (S == 2 ? 4 : 8);  // ring stages
     static constexpr int RB = TR / 8, SG = 8 / RB, NSB = 8 * S / SG;   // A-warps: row blocks x sample groups, 8-sample blocks per warp
     static constexpr int CSG = 2 * S, RSP = 8 / CSG, KSW = (TR / 4) / RSP;   // C-warps: 32-sample groups x row splits, k-steps (4 rows) per warp
     static constexpr int WARPS = kFA + kFC + FU + kFP, THREADS = WARPS * 32;
     static constexpr int LR = fused_launch_regs(THREADS);              // registers per thread at launch
     static constexpr int RA = FU >= 5 ? 88 : DMF_RA, RC = FU >= 5 ? 96 : DMF_RC, RU = FU >= 5 ? 56 : 64;
-    static_assert(WARPS % 4 == 0 && RA % 8 == 0 && RC % 8 == 0 && 256 * (RA + RC) + 32 * (FU + 1) * RU <= THREADS * LR, "register split of the fused pass");
+    static_assert(FU <= kFusedMaxU && WARPS % 4 == 0 && RA % 8 == 0 && RC % 8 == 0 && 256 * (RA + RC) + 32 * (FU + 1) * RU <= THREADS * LR,
+                  "register split of the fused pass");
     // row-statistics buffers: S = 4 double-buffers them (released through `sfree` as soon as the U-warp holds the partials in
     // registers: shared memory is full there); the narrow classes keep one per stage (released with the stage)
     static constexpr int NSTAT = S == 4 ? 2 : NS;
-    __host__ __device__ static constexpr int u_passes(int nub) { return nub == 2 ? TR / 16 : 1; }   // U work units per tile (16 rows x 2 components, or all rows)
+    static constexpr int UP = NUB == 2 ? TR / 16 : 1;                  // U work units per tile (16 rows x 2 components, or all rows)
 };
-constexpr int fused_cfg_rows(int s) { return s == 4 ? FusedCfg<4>::TR : FusedCfg<1>::TR; }
-constexpr int fused_cfg_stages(int s) { return s == 4 ? FusedCfg<4>::NS : (s == 2 ? FusedCfg<2>::NS : FusedCfg<1>::NS); }
-constexpr int fused_cfg_threads(int s) { return s == 4 ? FusedCfg<4>::THREADS : FusedCfg<1>::THREADS; }
-constexpr int fused_cfg_sgroups(int s) { return s == 4 ? FusedCfg<4>::SG : FusedCfg<1>::SG; }
-constexpr int fused_cfg_nstat(int s) { return s == 4 ? FusedCfg<4>::NSTAT : (s == 2 ? FusedCfg<2>::NSTAT : FusedCfg<1>::NSTAT); }
+// host-side views of the same table (nub = unknown types of the instantiation)
+constexpr int fused_cfg_rows(int s) { return s == 4 ? 16 : 32; }
+constexpr int fused_cfg_stages(int s) { return s == 4 ? DMF_STAGES : (s == 2 ? 4 : 8); }
+constexpr int fused_cfg_threads(int s, int nub) { return 32 * (kFA + kFC + kFP + (s == 4 ? DMF_FU : (nub == 2 ? DMF_FU_NARROW2 : DMF_FU_NARROW))); }
+constexpr int fused_cfg_sgroups(int s) { return 8 / (fused_cfg_rows(s) / 8); }
+constexpr int fused_cfg_nstat(int s) { return s == 4 ? 2 : fused_cfg_stages(s); }
 constexpr int kFusedMaxInner = 64;       // beyond this the U-warps would bound the pass: Gram engine instead
 constexpr unsigned kFusedCtlBytes = 2048;
 
@@ -351,9 +358,9 @@ __device__ __forceinline__ void fused_panel_tile(const FusedArgs& a, uint32_t sb
 }
 
 template <typename WT, int KB, int NUB, int S>
-__global__ void __launch_bounds__(FusedCfg<S>::THREADS, 1) fused_outer_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__((FusedCfg<S, NUB>::THREADS), 1) fused_outer_kernel(const FusedArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    using Cfg = FusedCfg<S>;
+    using Cfg = FusedCfg<S, NUB>;
     constexpr int KS = (KB + 3) / 4;                  // k-steps of the c = x - R_trunc a_k MMA
     constexpr int NG = ng_of(NUB);
     constexpr int NTRI = NG - NUB;
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(FusedCfg<S>::THREADS, 1) fused_outer_kernel(co
     constexpr int NSB = Cfg::NSB;                     // A-warp: 8 rows x NSB blocks of 8 samples
     constexpr int SG = Cfg::SG;                       // partial statistics records per row (one per A-warp sample group)
     constexpr int RSP = Cfg::RSP, KSW = Cfg::KSW;     // C-warp: 32 samples x KSW k-steps (CSG sample groups x RSP row splits)
-    constexpr int UP = Cfg::u_passes(NUB);            // U work units per tile
+    constexpr int UP = Cfg::UP;                       // U work units per tile
     constexpr unsigned STATB = (unsigned)(SG * TR * NG) * 8u;   // bytes of one row-statistics buffer
     constexpr unsigned PAIRB = 2u * NUB * 8u;         // bytes of one pair record of the per-sample table
     const Geom& g = a.g;
