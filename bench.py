@@ -180,6 +180,14 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def hbm_peak_gbs():
+    """(GB/s, where it comes from): the driver's measured copy bandwidth of this pool's B200s, else the profiling recipe's fallback."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
 def bootstrap_leg(args, dev, rank, world):
     """BASELINE config 4: bootstrap confidence intervals, 500k CpG x 64 samples, K = 6, n_u = 1, CLI defaults (10000 x 20, tol 1e-2,
     init uniform_, seed 1 -> the reference's seed sequence 1, 2, 4, 7, ...), boot_resamples resamples, percentiles included
@@ -237,15 +245,22 @@ def bootstrap_leg(args, dev, rank, world):
     if os.path.exists(fpath):
         fp64_peak = json.load(open(fpath))["fp64_tflops"]
     tf = flops_outer * total_outer / t_fit / 1e12 / world
+    # materialised form: every resample streams its own gathered copy of X, d_x, R_trunc once per outer iteration (fused pass)
+    bytes_outer = Mb * (8 * (Nb + Kb + 4 * nub) + 2 * Nb)
+    gbs = bytes_outer * total_outer / t_fit / 1e9 / world
+    hbm_peak, _src = hbm_peak_gbs()
     return {"workload": "BASELINE configs[3]: bootstrap CIs, 500k CpG x 64 samples, K=6, n_u=1, 10000 x 20 iterations, tol 1e-2, uniform_ init",
             "M_cpg": Mb, "N_samples": Nb, "resamples": B, "n_gpus": world, "parallelism": f"fit-sharded x{world} (resample b on rank b mod {world})",
             "seconds_total": t_all, "seconds_fits": t_fit, "seconds_percentiles_and_gather": t_all - t_fit,
             "resample_fits_per_sec": B / t_all, "seconds_per_1000_resamples": t_all * 1000.0 / max(B, 1),
             "mean_outer_iterations": total_outer / max(B, 1), "bounds_finite_and_ordered": ok,
-            "form": "multiplicity form (shared X, d_x, R_trunc served from L2; per-position u through a CSR), Gram-form engine",
-            "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+            "form": "materialised form (every resample of a wave owns a gathered copy of X, d_x, R_trunc; device MT19937 draws), fused one-pass engine, "
+                    "32-row tiles of the N <= 64 width class",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_fit_outer_iteration": bytes_outer,
+                         "frac_fp64": tf / fp64_peak, "achieved_fp64_tflops": tf, "peak_fp64_tflops": fp64_peak,
                          "algorithmic_fp64_flops_per_fit_outer_iteration": flops_outer,
-                         "note": "per GPU; the shared matrices come from L2 (profiles/r1g_bootstrap_summary.md), so HBM is not the bound here"}}
+                         "note": "per GPU, wall clock of the fits (set-up of the waves, polling and the tails of the waves included)"}}
 
 
 def run_b200(args, rank, world, local_rank):
@@ -549,11 +564,7 @@ def run_b200(args, rank, world, local_rank):
     if args.boot_resamples > 0 and not args.profile and engine in ("gram", "fused") and args.precision == "fp64":
         boot = bootstrap_leg(args, dev, rank, world)
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        peak, peak_src = hbm_peak_gbs()
         flops = {}
         if engine == "fused":
             passes = {"fused_outer_kernel": (kern["fused_outer_kernel"], bytes_fused)}

@@ -269,7 +269,7 @@ def bootstrap_fits(n_bootstrap, n_u, meth_f, counts, ref, init_option, n_iter1, 
             idx_d = torch.from_numpy(idx_np).to(dev)                                                    # (Bw, M) int64
             u0_d = torch.from_numpy(u0_np).to(dev)                                                      # (Bw, M, n_u)
         if use_fused:
-            probs = [prob.gathered(idx_d[k]) for k in range(Bw)]                                    # this wave's resampled matrices
+            probs = prob.gathered_many(idx_d)                                                       # this wave's resampled matrices
             del idx_d
             batch = FitBatch(probs, n_u, u0_d, A0, mode=mode, purity=purity)
             del u0_d

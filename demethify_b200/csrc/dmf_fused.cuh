@@ -285,6 +285,16 @@ __device__ __forceinline__ void fused_row_stats(uint32_t xa, uint32_t da, uint32
             if (!(v0 && live)) d0 = 0.0;
             if (!(v1 && live)) d1 = 0.0;
         }
+#ifdef DMF_SPLIT_C
+        // experiment: the two k-steps accumulate separately (no dependent DMMA pair), one DADD per value joins them
+        if (KS == 2) {
+            double e0 = 0.0, e1 = 0.0;
+            dmma884(c0, c1, rfrag[0], nab[sb][0]);
+            dmma884(e0, e1, rfrag[KS - 1], nab[sb][KS - 1]);
+            c0 += e0;
+            c1 += e1;
+        } else
+#endif
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, rfrag[kk], nab[sb][kk]);     // c = x - R_trunc a_k
         const double z0 = d0 * c0, z1 = d1 * c1;

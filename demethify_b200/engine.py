@@ -172,6 +172,29 @@ class DeviceProblem:
         other.M = n
         return other
 
+    def gathered_many(self, idx):
+        """One problem per row of idx (B x n int32 device tensor): the B resampled copies of X, d_x, R_trunc live in three stacked
+        tensors (one allocation per matrix and wave instead of three per resample - the allocations dominated the set-up of a wave)."""
+        rows = idx.to(self.device, torch.int32).contiguous()
+        B, n = rows.shape
+        lib = _lib.lib()
+
+        def take(t):
+            out = torch.empty((B, n, t.shape[1]), dtype=t.dtype, device=t.device)
+            for k in range(B):
+                _lib.check(lib.dmf_gather_rows(C.c_void_p(t.data_ptr()), C.c_void_p(rows[k].data_ptr()), n, t.shape[1], t.element_size(),
+                                               C.c_void_p(out[k].data_ptr()), _stream_ptr()))
+            return out
+        Xs, Ds = take(self.X), take(self.D)
+        Rs = take(self.Rk) if self.Rk is not None else None
+        probs = []
+        for k in range(B):
+            other = object.__new__(DeviceProblem)
+            other.__dict__.update(self.__dict__)
+            other.X, other.D, other.Rk, other.M = Xs[k], Ds[k], (Rs[k] if Rs is not None else None), n
+            probs.append(other)
+        return probs
+
     def row_slice(self, lo, hi):
         """Rows [lo, hi) as a problem of its own sharing the device buffers (CpG-row shards, sharded.py)."""
         other = object.__new__(DeviceProblem)

@@ -90,11 +90,11 @@ def wave_breakdown(torch, B=64):
         torch.cuda.synchronize()
         out[key] = time.perf_counter() - t0
         return time.perf_counter()
-    for rep in range(2):
+    for rep in range(1 if B > 128 else 2):
         t = time.perf_counter()
         idx_d, u0_d, A0 = bs.device_draws(chunk, M, n_u, K, N, dev, True)
         t = lap("draws_s", t)
-        probs = [prob.gathered(idx_d[k]) for k in range(B)]
+        probs = prob.gathered_many(idx_d)
         t = lap("gather_s", t)
         batch = FitBatch(probs, n_u, u0_d, A0)
         t = lap("batch_create_s", t)
@@ -129,7 +129,7 @@ def main():
     if "s1u2" in which:
         time_case(torch, "s1u2", 500_000, 64, 6, 2, 1)
     if "wave" in which:
-        wave_breakdown(torch)
+        wave_breakdown(torch, int(os.environ.get("DMF_WAVE_B", "64")))
 
 
 if __name__ == "__main__":
