@@ -484,8 +484,9 @@ int launch_g(dmf_batch_s* b, kern_t k, int ntc, unsigned smem, int flags, int k_
     a.tol = tol;
     a.ca0 = ca0; a.cb0 = cb0; a.with_x = with_x; a.pad = 0;
     a.mom_a = b->mom_dev; a.mom_m = b->mom_dev + b->mom_cap;
-    // grid_mode 1 (alpha_inner_kernel): one warp per 32 samples of a fit
-    dim3 grid = grid_mode == 1 ? dim3(b->n_active, (b->shape.N + 31) / 32, 1) : dim3(a.g.n_parts, b->n_active, 1);
+    // grid_mode 1 (alpha_inner_kernel): one warp per 32 / L samples of a fit, L = ktb_in lanes per sample
+    const int spw = 32 / b->ktb_in;
+    dim3 grid = grid_mode == 1 ? dim3(b->n_active, (b->shape.N + spw - 1) / spw, 1) : dim3(a.g.n_parts, b->n_active, 1);
     if (grid_mode == 2) {
         a.g.n_parts = b->n_parts_u;
         a.g.n_groups = b->n_groups_u;

@@ -13,6 +13,7 @@ constexpr int kStages = 5;                  // smem ring depth (kStages - 2 tile
 constexpr int kGroup = 16;                  // CTAs per first-level reduction group
 constexpr int kMaxSrc = 5;                  // matrices streamed per stage: X, D, Rk, U, Uprev
 constexpr int kMaxKt = 32;                  // K + n_u supported by the register-tiled kernels
+constexpr int kMaxSamples = 2 * kConsumers; // N supported (make_plan: N <= kConsumers x columns per thread, at most 2)
 
 // ------------------------------------------------------------------------------------------------
 // Device-side descriptors (mirrors of the host structs in dmf_api.cu)

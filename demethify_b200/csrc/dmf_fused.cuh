@@ -44,14 +44,14 @@ namespace dmf {
 #endif
 constexpr int kFA = 8, kFC = 8, kFP = 1;
 // Registers per thread after the role split (setmaxnreg).  The pool is what the CTA got at launch (threads x the register count ptxas
-// derives from __launch_bounds__): 20 warps -> 96 per thread, 24 warps -> 80 per thread.  With 3 U-warps: A 96, C 112, U / producer 64
-// (256 (96 + 112) + 128 x 64 = 640 x 96); with 7 U-warps: A 88, C 96, U / producer 56 (256 (88 + 96) + 256 x 56 = 768 x 80).
+// derives from __launch_bounds__): 20 warps -> 96 per thread, 24 warps -> 80 per thread.  With 3 U-warps: A 96, C 96 (112 spills more and is no faster), U / producer 64
+// (256 (96 + 96) + 128 x 64 <= 640 x 96); with 7 U-warps: A 88, C 96, U / producer 56 (256 (88 + 96) + 256 x 56 = 768 x 80).
 // setmaxnreg is a warpgroup instruction: the warp count must stay a multiple of 4 (FU = 3 or 7) so that every group is one role set.
 #ifndef DMF_RA
 #define DMF_RA 96
 #endif
 #ifndef DMF_RC
-#define DMF_RC 112
+#define DMF_RC 96
 #endif
 constexpr int kFusedMaxU = 7;
 constexpr int fused_launch_regs(int threads) { return (65536 / ((threads + 127) / 128 * 128)) / 8 * 8; }
@@ -285,18 +285,18 @@ __device__ __forceinline__ void fused_row_stats(uint32_t xa, uint32_t da, uint32
             if (!(v0 && live)) d0 = 0.0;
             if (!(v1 && live)) d1 = 0.0;
         }
-#ifdef DMF_SPLIT_C
-        // experiment: the two k-steps accumulate separately (no dependent DMMA pair), one DADD per value joins them
+        // c = x - R_trunc a_k.  With two k-steps the second accumulates on its own and one DADD per value joins them: a dependent
+        // DMMA pair would hold the warp for the full MMA latency (measured with C at 96 registers: 0.847 -> 0.837 ms at 1M x 256)
         if (KS == 2) {
             double e0 = 0.0, e1 = 0.0;
             dmma884(c0, c1, rfrag[0], nab[sb][0]);
             dmma884(e0, e1, rfrag[KS - 1], nab[sb][KS - 1]);
             c0 += e0;
             c1 += e1;
-        } else
-#endif
+        } else {
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, rfrag[kk], nab[sb][kk]);     // c = x - R_trunc a_k
+            for (int kk = 0; kk < KS; ++kk) dmma884(c0, c1, rfrag[kk], nab[sb][kk]);
+        }
         const double z0 = d0 * c0, z1 = d1 * c1;
         cost = fma(z0, c0, cost);
         cost = fma(z1, c1, cost);
