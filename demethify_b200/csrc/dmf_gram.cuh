@@ -1124,7 +1124,7 @@ __device__ __forceinline__ bool project_simplex_reg(double (&v)[KTB], int p) {
 // shuffle per step), every lane divides for its own candidate threshold, the LAST lane that satisfies the condition supplies theta.
 // Same arithmetic as project_simplex_reg, value for value.  Returns false (for the whole group) when v holds a NaN.
 template <int L>
-__device__ __forceinline__ bool project_simplex_lanes(double& v, int k, int p, int base) {
+__device__ __forceinline__ bool project_simplex_lanes(double& v, int k, int p, int base, double rk) {
     constexpr unsigned kFull = 0xffffffffu;
     const unsigned gsel = L == 32 ? kFull : ((1u << (L & 31)) - 1u);
     const unsigned nanb = (__ballot_sync(kFull, (k < p) && !(v == v)) >> base) & gsel;
@@ -1139,12 +1139,17 @@ __device__ __forceinline__ bool project_simplex_lanes(double& v, int k, int p, i
             const double hi = gt ? u : o, lo = gt ? o : u;
             u = (lower == desc) ? hi : lo;
         }
-    double cs = u;                                   // lane 0: 0 + u[0]
-    for (int step = 1; step < p; ++step) {           // cs[j] = cs[j - 1] + u[j], in order
-        const double t = __shfl_up_sync(kFull, cs, 1, L);
-        if (k == step) cs = t + u;
+    // cs[k] = ((u[0] + u[1]) + ...) + u[k], the reference's left-to-right order: every lane adds its own prefix (the shuffles are
+    // independent of the chain of additions)
+    double cs = __shfl_sync(kFull, u, 0, L);
+    for (int l = 1; l < p; ++l) {
+        const double t = __shfl_sync(kFull, u, l, L);
+        if (l <= k) cs += t;
     }
-    const double th = (cs - 1.0) / (double)(k + 1);
+    // (cs - 1) / (k + 1), correctly rounded without the division sequence: rk = RN(1 / (k + 1)), q0 = RN(x rk) is faithful, the FMA
+    // remainder is exact and RN(q0 + rem rk) is the rounded quotient (Markstein); |x| is O(1) here, never subnormal or huge
+    const double x = cs - 1.0, q0 = x * rk;
+    const double th = fma(fma(-(double)(k + 1), q0, x), rk, q0);
     const unsigned condb = (__ballot_sync(kFull, (k < p) && (u - th > 0.0)) >> base) & gsel;
     const int last = condb ? 31 - __clz(condb) : 0;
     const double theta = __shfl_sync(kFull, th, last, L);
@@ -1229,6 +1234,7 @@ __global__ void __launch_bounds__(32) alpha_inner_kernel(const PassArgs a) {
         const double b = mine ? f.rgbx[(size_t)k * g.N + j] : 0.0;
         double ac = mine ? (double)Acur[(size_t)k * g.N + j] : 0.0;
         double ap = mine ? (double)Aprev[(size_t)k * g.N + j] : 0.0;
+        const double rk = 1.0 / (double)(k + 1);            // for the thresholds of the projection (one IEEE division per launch)
         if (!fw) {
             bool bad = false;                                // per sample: the iterate stays where the NaN appeared
             for (int it = 0; it < n2; ++it) {
@@ -1238,7 +1244,7 @@ __global__ void __launch_bounds__(32) alpha_inner_kernel(const PassArgs a) {
 #pragma unroll
                 for (int l = 0; l < KTB; ++l) s = fma(Grow[l], __shfl_sync(kFull, at, l, L), s);
                 double v = (double)(T)(at + (double)(T)((b - s) * inv_lh));
-                const bool ok = project_simplex_lanes<L>(v, k, Kt, base);
+                const bool ok = project_simplex_lanes<L>(v, k, Kt, base, rk);
                 if (!ok) bad = true;
                 if (!bad) { ap = ac; ac = k < Kt ? (double)(T)v : 0.0; }
                 if (__all_sync(kFull, bad || !act)) break;
