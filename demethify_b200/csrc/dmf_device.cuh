@@ -238,8 +238,13 @@ __device__ __forceinline__ bool hier_reduce(const Geom& g, const FitDev& f, doub
     __threadfence();
     const bool single = (g.n_groups == 1);
     for (int e = tid; e < n; e += blockDim.x) {
+        // the group's records in CTA order; the loads are issued together (one L2 round trip per element instead of gsize)
+        double v[kGroup];
+#pragma unroll
+        for (int p = 0; p < kGroup; ++p) v[p] = p < gsize ? __ldcg(&f.part[(size_t)(gfirst + p) * g.part_stride + e]) : 0.0;
         double s = 0.0;
-        for (int p = 0; p < gsize; ++p) s += __ldcg(&f.part[(size_t)(gfirst + p) * g.part_stride + e]);
+#pragma unroll
+        for (int p = 0; p < kGroup; ++p) s += v[p];
         if (single)
             out_sm[e] = s;
         else
@@ -258,7 +263,13 @@ __device__ __forceinline__ bool hier_reduce(const Geom& g, const FitDev& f, doub
     __threadfence();
     for (int e = tid; e < n; e += blockDim.x) {
         double s = 0.0;
-        for (int q = 0; q < g.n_groups; ++q) s += __ldcg(&f.gpart[(size_t)q * g.part_stride + e]);
+        for (int q0 = 0; q0 < g.n_groups; q0 += kGroup) {      // group records in group order, kGroup loads in flight
+            double v[kGroup];
+#pragma unroll
+            for (int q = 0; q < kGroup; ++q) v[q] = q0 + q < g.n_groups ? __ldcg(&f.gpart[(size_t)(q0 + q) * g.part_stride + e]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < kGroup; ++q) s += v[q];
+        }
         out_sm[e] = s;
     }
     if (tid == 0) f.tickets[g.n_groups] = 0u;

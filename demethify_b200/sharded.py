@@ -269,7 +269,7 @@ def mdwbssmf_deconv_sharded(u_local, alpha, X_local, d_local, R_local, n_u, n_it
     mode = _lib.DMF_MODE_PURITY if purity is not None else (_lib.DMF_MODE_PARTIAL if R_local is not None else _lib.DMF_MODE_UNSUPERVISED)
     be = GpuShardBackend(X_local, d_local, R_local, n_u, np.asarray(u_local).reshape(-1, n_u), np.asarray(alpha), mode=mode, purity=purity)
     import os
-    if os.environ.get("DMF_PEER_XCHG", "0") == "1":
+    if os.environ.get("DMF_PEER_XCHG", "1") != "0":          # the in-kernel NVLink all-reduce is the default; NCCL when symmetric memory is unavailable
         be.enable_peer_exchange(group)
     fit = RowShardedFit(be, group)
     try:

@@ -2,7 +2,7 @@
 """Timings of the BASELINE.json configurations other than the bench.py headline (run on the GPU box).  Prints one JSON line
 per configuration: wall-clock of the public call, outer iterations executed, fits/s.  Synthetic data, recipe of bench.py.
 
-  python tools/bench_configs.py [c2] [c3] [c4] [--resamples B]
+  python tools/bench_configs.py [c2] [c3] [c4] [c5] [pub] [--resamples B]
 """
 import json
 import os
@@ -79,6 +79,20 @@ def main():
             t = time.perf_counter() - t0
         out.append({"config": "pub bootstrap 2500 resamples of the shipped 350 x 10 fixture, n_u=1, 10000x20, tol 1e-2 (README / notebook cell 29)",
                     "s_total": t, "fits_per_s": 2500 / t, "mean_outer": float(np.mean(n_outer)), "published_fits_per_s_authors_laptop": 46.47})
+    if "c5" in which:      # BASELINE config 5: --ic BIC sweep n_u = 0..10 over one matrix of 1M CpGs x 256 samples, K = 6, CLI defaults
+        from demethify_b200 import ic as icm
+        from tools.time_fused import device_problem
+        dev = torch.device("cuda", 0)
+        Xd, Dd, Rd = device_problem(torch, dev, 1_000_000, 256, 6, 2, 55)
+        X, D, Rk = Xd.cpu().numpy(), Dd.cpu().numpy(), Rd.cpu().numpy()
+        del Xd, Dd, Rd
+        members = list(range(0, 11))
+        t0 = time.perf_counter()
+        res = icm.evaluate_best_ic(X, Rk, D, "uniform_", "BIC", 1, 10000, 20, 1e-2, n_restarts=1, n_u_values=members)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        out.append({"config": "c5 ic sweep (BIC) n_u = 0..10, 1M x 256, K=6, 10000x20, tol 1e-2, one resident problem, 1 GPU", "s_total": t,
+                    "best_n_u": int(res[2]) if res[2] is not None else None, "members": members, "bic": [float(v) for v in res[3]]})
     for o in out:
         print(json.dumps(o), flush=True)
 
