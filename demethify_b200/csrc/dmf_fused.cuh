@@ -44,11 +44,11 @@ namespace dmf {
 #endif
 constexpr int kFA = 8, kFC = 8, kFP = 1;
 // Registers per thread after the role split (setmaxnreg).  The pool is what the CTA got at launch (threads x the register count ptxas
-// derives from __launch_bounds__): 20 warps -> 96 per thread, 24 warps -> 80 per thread.  With 3 U-warps: A 96, C 96 (112 spills more and is no faster), U / producer 64
-// (256 (96 + 96) + 128 x 64 <= 640 x 96); with 7 U-warps: A 88, C 96, U / producer 56 (256 (88 + 96) + 256 x 56 = 768 x 80).
+// derives from __launch_bounds__): 20 warps -> 96 per thread, 24 warps -> 80 per thread.  With 3 U-warps: A 88, C 96 (measured at 1M x 256: A 88 0.788 ms, 96 0.797, 104 0.831, 112 0.824, 80 0.871; C 112 spills more and is no faster), U / producer 64
+// (256 (88 + 96) + 128 x 64 <= 640 x 96); with 7 U-warps: A 88, C 96, U / producer 56 (256 (88 + 96) + 256 x 56 = 768 x 80).
 // setmaxnreg is a warpgroup instruction: the warp count must stay a multiple of 4 (FU = 3 or 7) so that every group is one role set.
 #ifndef DMF_RA
-#define DMF_RA 96
+#define DMF_RA 88
 #endif
 #ifndef DMF_RC
 #define DMF_RC 96
