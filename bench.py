@@ -141,9 +141,11 @@ class ClockSampler:
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, None
 
     def start(self):
+        """Launch nvidia-smi in loop mode.  Called BEFORE the warm-up steps: the tool needs a few hundred ms before its first line, and
+        the timed region of the headline is well under a second."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -151,21 +153,30 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()          # start of the timed region: only later samples count
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for t, r in self.rows if t0 <= t <= t_end + 0.1]
+        window = "timed region"
+        if not inside:                               # region shorter than the sampling period: the warm-up steps ran the same kernels
+            inside, window = [r for _t, r in self.rows], "warm-up + timed region (no sample fell inside the timed region)"
+        sm = [float(r[0]) for r in inside if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def run_reference(args, rank, world):
@@ -385,11 +396,12 @@ def run_b200(args, rank, world, local_rank):
         batch.gram_init()
     else:
         batch.pass_init()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     launches0 = batch.launch_count()
     evs = []
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
