@@ -85,6 +85,10 @@ struct FusedCfg {
     // registers: shared memory is full there); the narrow classes keep one per stage (released with the stage)
     static constexpr int NSTAT = S == 4 ? 2 : NS;
     static constexpr int UP = NUB == 2 ? TR / 16 : 1;                  // U work units per tile (16 rows x 2 components, or all rows)
+    // The mbarrier waits are by phase PARITY: a U-warp that moves from tile t to tile t + ceil(FU / UP) must not find the stage of the
+    // new tile two fills behind, or the parity test passes on the wrong fill (stale statistics, then a deadlock - seen with
+    // FU = 7 at S = 4).  Fills are in tile order, so a stride of at most NS tiles guarantees it.
+    static_assert((FU + UP - 1) / UP <= NS, "U-warp tile stride must not exceed the ring depth (parity waits)");
 };
 // host-side views of the same table (nub = unknown types of the instantiation)
 constexpr int fused_cfg_rows(int s) { return s == 4 ? 16 : 32; }
