@@ -14,12 +14,13 @@
 // updates l_h, a1) only if the fit did not just terminate - so a terminated fit returns exactly the iterate whose cost passed
 // the test.  alpha_inner_kernel (dmf_gram.cuh) follows and produces alpha_{k+1}.
 //
-// One CTA = 20 warps with four roles (warp specialised, tiles flow A -> U -> C through a 5-stage shared-memory ring):
-//   8 A-warps   each owns 8 S samples; c comes from FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, SASS DMMA) with the samples on
-//               the M side, so a lane owns ONE sample and two rows per 8 x 8 block and keeps only its own alpha values
-//   3 U-warps   lane = row, tile t goes to U-warp t mod 3 (the 20 dependent iterations of a tile take about as long as the
-//               A and C stages of a tile together, so consecutive tiles must overlap)
-//   1 producer  drives the TMA ring: per-row bulk copies into bank-conflict-free padded rows
+// One CTA = 20 (or 24) warps with four roles (warp specialised, tiles flow A -> U -> C through a shared-memory ring; rows per tile,
+// ring depth, warp maps and the number of U-warps depend on the width class - FusedCfg below):
+//   8 A-warps   row blocks x sample groups; c comes from FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, SASS DMMA) with the ROWS on
+//               the M side: a lane owns one row and two samples of every 8-sample block; the row statistics run on the FMA pipe
+//   3 (7) U-warps  lane = row (one unknown type) or (row, component) (two); work unit n goes to U-warp n mod FU (the 20 dependent
+//               iterations of a unit take longer than the A and C stages of a tile, so consecutive tiles must overlap)
+//   1 producer  drives the TMA ring: one bulk copy per matrix and tile into bank-conflict-free padded rows
 //   8 C-warps   the panel is the GEMM  [N x rows] (d) x [rows x NCOL] (u (x) [R_trunc | u]) : DMMA again, accumulators stay in
 //               the MMA C fragments for the whole kernel; bx_u on the FMA pipe
 // FP64 only (tcgen05 has no FP64 kind; DMMA and DFMA share one pipe at 64 FMA/clk/SM - tools/fp64_peak.cu), which is the
