@@ -23,6 +23,7 @@ from .engine import DeviceProblem, FitBatch, _stream_ptr
 
 __all__ = ["row_range", "GpuShardBackend", "RowShardedFit", "mdwbssmf_deconv_sharded", "last_info"]
 
+_peer_cache = {}    # (group, world, device) -> (symmetric buffer, rendezvous handle, bytes): see enable_peer_exchange
 last_info = {}      # of the most recent mdwbssmf_deconv_sharded call: {"peer_exchange": bool, "peer_error": str | None, "collectives": int}
 
 
@@ -70,9 +71,17 @@ class GpuShardBackend:
             world, rank = dist.get_world_size(group), dist.get_rank(group)
             nbytes = C.c_size_t()
             _lib.check(lib.dmf_batch_peer_bytes(b.b, world, C.byref(nbytes)))
-            buf = symm_mem.empty((nbytes.value + 7) // 8, dtype=torch.float64, device=self.device)
+            # the symmetric buffer and its rendezvous (an exchange of IPC handles through the store: tens of ms) are kept for the
+            # process and reused by later fits of the same or a smaller statistics block; every use starts from zeroed flags
+            key = (id(group) if group is not None else 0, world, self.device.index)
+            cached = _peer_cache.get(key)
+            if cached is not None and cached[2] >= nbytes.value:
+                buf, hdl = cached[0], cached[1]
+            else:
+                buf = symm_mem.empty((nbytes.value + 7) // 8, dtype=torch.float64, device=self.device)
+                hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                _peer_cache[key] = (buf, hdl, nbytes.value)
             buf.zero_()
-            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
             ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
             torch.cuda.synchronize()
             dist.barrier(group)                      # every rank's buffer (flags) is zero before anybody pushes
