@@ -97,6 +97,13 @@ constexpr int fused_cfg_stages(int s) { return s == 4 ? DMF_STAGES : (s == 2 ? 4
 constexpr int fused_cfg_threads(int s, int nub) { return 32 * (kFA + kFC + kFP + (s == 4 ? DMF_FU : (nub == 2 ? DMF_FU_NARROW2 : DMF_FU_NARROW))); }
 constexpr int fused_cfg_sgroups(int s) { return 8 / (fused_cfg_rows(s) / 8); }
 constexpr int fused_cfg_nstat(int s) { return s == 4 ? 2 : fused_cfg_stages(s); }
+// the host-side views must describe the kernel's own table
+#define DMF_CFG_CHECK(S_, N_)                                                                                                      \
+    static_assert(fused_cfg_rows(S_) == FusedCfg<S_, N_>::TR && fused_cfg_stages(S_) == FusedCfg<S_, N_>::NS &&                   \
+                  fused_cfg_threads(S_, N_) == FusedCfg<S_, N_>::THREADS && fused_cfg_sgroups(S_) == FusedCfg<S_, N_>::SG &&       \
+                  fused_cfg_nstat(S_) == FusedCfg<S_, N_>::NSTAT, "fused_cfg_* out of step with FusedCfg");
+DMF_CFG_CHECK(1, 1) DMF_CFG_CHECK(1, 2) DMF_CFG_CHECK(2, 1) DMF_CFG_CHECK(2, 2) DMF_CFG_CHECK(4, 1) DMF_CFG_CHECK(4, 2)
+#undef DMF_CFG_CHECK
 constexpr int kFusedMaxInner = 64;       // beyond this the U-warps would bound the pass: Gram engine instead
 constexpr unsigned kFusedCtlBytes = 2048;
 
