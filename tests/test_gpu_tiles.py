@@ -89,3 +89,36 @@ def test_narrow_batch_matches_single_fits(pkg, n_u):
     uo, ao = orc.solve_partial_reference(U0[0].copy(), R0, A0[0].copy(), X[ih[0]], D[ih[0]].astype(float), Rk[ih[0]], n_u, 40, 20, 1e-3, trace=tr)
     assert res[0][2] == tr["n_outer"]
     assert np.abs(res[0][1] - ao).max() <= 1e-6 and np.abs(res[0][0] - uo).max() <= 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1500, 24, 20, 2), (1200, 40, 17, 4), (900, 33, 25, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_wide_alpha_kernel_vs_oracle(pkg, shape):
+    """17 .. 32 cell types in total: the Gram-form engine with the 32-lanes-per-sample alpha kernel (a whole warp per sample)."""
+    from demethify_b200 import deconvolution as dec
+    from oracle import bssmf_numpy as orc
+    M, N, K, n_u = shape
+    X, D, Rk = synth(3 * M + N + K, M, N, K, n_u)
+    u0, R0, a0 = orc.draw_init("uniform_", X, D, Rk, n_u, seed=5)
+    tr = {}
+    uo, ao = orc.solve_partial_reference(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, n_u, 4, 12, 1e-9, trace=tr)
+    u, a = dec.mdwbssmf_deconv(u0, R0, a0, X, D, Rk, n_u, n_iter1=4, n_iter2=12, tol=1e-9)
+    info = dec.last_fit_info()
+    assert info["engine"] == "gram"
+    assert info["n_outer"] == tr["n_outer"]
+    assert np.abs(a - ao).max() <= 1e-6 and np.abs(u - uo).max() <= 1e-6
+
+
+def test_wide_purity_alpha_kernel_vs_oracle(pkg):
+    """Purity (Frank-Wolfe) alpha step with 18 known types: the first-argmin reductions of the lane-parallel kernel over 32 lanes."""
+    from demethify_b200 import deconvolution as dec
+    from oracle import bssmf_numpy as orc
+    M, N, K, n_u = 1100, 20, 18, 1
+    X, D, Rk = synth(4242, M, N, K, n_u)
+    pur = np.random.RandomState(3).uniform(0.2, 0.9, size=N)
+    u0, R0, a0 = orc.draw_init_purity("uniform_", X, D, Rk, n_u, pur, seed=2)
+    tr = {}
+    uo, ao = orc.solve_purity(u0.copy(), R0, a0.copy(), X, D.astype(float), Rk, n_u, pur, 3, 25, 1e-9, trace=tr)
+    u, a = dec.mdwbssmf_deconv_p(u0, R0, a0, X, D, Rk, n_u, pur, n_iter1=3, n_iter2=25, tol=1e-9)
+    info = dec.last_fit_info()
+    assert info["n_outer"] == tr["n_outer"]
+    assert np.abs(a - ao).max() <= 1e-6 and np.abs(u - uo).max() <= 1e-6
