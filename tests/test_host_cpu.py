@@ -41,3 +41,34 @@ def test_bootstrap_seed_sequence_and_restart_jobs():
     assert bootstrap_seeds(1, 6) == [1, 2, 4, 7, 11, 16]          # bootstrap.py:27, SURVEY Q3
     with pytest.raises(TypeError):
         bootstrap_seeds([5], 3)                                    # `--seed 5` reaches bt_ci as a list (Q1)
+
+
+def test_bench_clock_sampler_window():
+    """bench.py's nvidia-smi sampler: only samples inside the timed region count; a region shorter than the sampling period falls
+    back to all samples (warm-up ran the same kernels) and says so."""
+    import importlib.util
+    import os
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+    row = lambda mhz, cap: [str(mhz), "1965", "0x4", "Not Active", "Not Active", "Not Active", cap]
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    t = time.perf_counter()
+    s.rows = [(t - 2.0, row(500, "Not Active")), (t - 1.0, row(1200, "Not Active"))]      # before the timed region
+    s.mark_begin()
+    s.rows += [(time.perf_counter(), row(1950, "Active")), (time.perf_counter(), row(1965, "Not Active"))]
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    s2 = bench.ClockSampler(0)
+    s2.proc = FakeProc()
+    s2.rows = [(time.perf_counter() - 1.0, row(1900, "Not Active"))]
+    s2.mark_begin()
+    out2 = s2.stop()
+    assert out2["samples"] == 1 and out2["sm_mhz"] == 1900.0 and out2["window"].startswith("warm-up")
